@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/GAT.py, GATNet.py) on
+oracle/pyg_standin.  Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests / golden vectors of its own, so these fixtures — outputs and
+autograd gradients of the reference's own Python in fp32 (the 1e-5 target) and fp64 (truth) on seeded inputs —
+are what pins the oracle and the CUDA path.  Dropout masks are injected by patching
+torch.nn.functional.dropout while the reference's message() runs (GAT.py:61), in ORIGINAL [edges;loops] order.
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_loader  # noqa: E402
+
+# name, N, E, F_in, C, H, concat, p, special
+LAYER_CASES = [
+    ("h3c5_cat", 60, 300, 11, 5, 3, True, 0.0, ""),
+    ("h3c5_mean", 60, 300, 11, 5, 3, False, 0.0, ""),
+    ("h1c7_mean", 80, 400, 64, 7, 1, False, 0.0, ""),
+    ("h8c8_cat", 120, 700, 33, 8, 8, True, 0.0, ""),
+    ("h8c8_cat_drop", 120, 700, 33, 8, 8, True, 0.6, ""),
+    ("h8c3_mean_drop", 90, 500, 64, 3, 8, False, 0.6, ""),
+    ("h4c64_cat", 150, 1200, 50, 64, 4, True, 0.0, ""),
+    ("h2c121_mean", 70, 420, 40, 121, 2, False, 0.0, ""),
+    ("h4c47_mean", 64, 380, 24, 47, 4, False, 0.0, ""),
+    ("h16c2_cat", 50, 260, 9, 2, 16, True, 0.0, ""),
+    ("h32c8_cat", 40, 200, 12, 8, 32, True, 0.0, ""),
+    ("h2c256_cat", 48, 400, 20, 256, 2, True, 0.0, ""),
+    ("f3_cifar", 100, 800, 3, 8, 8, True, 0.0, ""),
+    ("f5_cifar", 100, 800, 5, 8, 8, True, 0.0, ""),
+    ("no_edges", 17, 0, 6, 4, 2, True, 0.0, ""),
+    ("dups_loops_isolated", 40, 160, 10, 6, 2, True, 0.0, "dups"),
+    ("big_logits", 50, 300, 8, 8, 4, True, 0.0, "big"),
+    ("hub", 300, 900, 16, 16, 2, True, 0.0, "hub"),
+]
+
+
+def make_graph(name, n, e, special, gen):
+    if e == 0:
+        return torch.zeros(2, 0, dtype=torch.int64)
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    if special == "dups":
+        ei[:, 10:20] = ei[:, 0:10]                       # duplicate edges are kept (counted twice)
+        ei[1, 20:30] = ei[0, 20:30]                      # pre-existing self loops are kept too
+        keep = (ei != n - 1).all(dim=0)                  # node n-1 isolated: its row is the appended self loop only
+        ei = ei[:, keep]
+    if special == "hub":
+        ei[1, : e // 2] = 7                              # one destination with ~450 in-edges
+    return ei
+
+
+def pack(layer):
+    H = layer.num_heads
+    st = lambda ms, attr: torch.stack([getattr(m, attr).detach() for m in ms])
+    return dict(W=st(layer.ws, "weight"), bw=st(layer.ws, "bias"),
+                a1=st(layer.attentions1, "weight").reshape(H, -1), b1=st(layer.attentions1, "bias").reshape(H),
+                a2=st(layer.attentions2, "weight").reshape(H, -1), b2=st(layer.attentions2, "bias").reshape(H),
+                bias=layer.bias.detach())
+
+
+def grads(layer, xg):
+    H = layer.num_heads
+    st = lambda ms, attr: torch.stack([getattr(m, attr).grad for m in ms])
+    return dict(g_x=xg, g_W=st(layer.ws, "weight"), g_bw=st(layer.ws, "bias"),
+                g_a1=st(layer.attentions1, "weight").reshape(H, -1), g_b1=st(layer.attentions1, "bias").reshape(H),
+                g_a2=st(layer.attentions2, "weight").reshape(H, -1), g_b2=st(layer.attentions2, "bias").reshape(H),
+                g_bias=layer.bias.grad)
+
+
+class patched_dropout:
+    """Replace F.dropout by multiplication with a supplied keep-multiplier mask (identity if mask is None)."""
+
+    def __init__(self, mask):
+        self.mask = mask
+
+    def __enter__(self):
+        self.orig = torch.nn.functional.dropout
+        mask = self.mask
+        def fake(inp, p=0.5, training=True, inplace=False):
+            return inp if mask is None else inp * mask.to(inp.dtype)
+        torch.nn.functional.dropout = fake
+
+    def __exit__(self, *a):
+        torch.nn.functional.dropout = self.orig
+
+
+def run_layer(ref_gat, case):
+    name, n, e, f, c, h, concat, p, special = case
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    torch.manual_seed(sum(map(ord, name)) + 1)
+    layer = ref_gat.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p)
+    with torch.no_grad():
+        layer.bias.uniform_(-0.5, 0.5)                   # zero at init (GAT.py:32-35); made non-trivial here
+        if special == "big":
+            for m in list(layer.attentions1) + list(layer.attentions2):
+                m.weight.mul_(60.0)                      # logits of magnitude ~1e2: softmax stability
+    ei = make_graph(name, n, e, special, gen)
+    x = torch.randn(n, f, generator=gen)
+    ep = ei.shape[1] + n
+    mask = None
+    if p > 0:
+        mask = (torch.rand(ep, h, generator=gen) >= p).float() / (1.0 - p)
+    d_out = c * h if concat else c
+    gout = torch.randn(n, d_out, generator=gen)
+    rec = dict(x=x, edge_index=ei, gout=gout, concat=np.array(concat), p=np.array(p), **pack(layer))
+    if mask is not None:
+        rec["mask"] = mask
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        lay = layer.to(dt)
+        lay.train()
+        lay.zero_grad()
+        xx = x.detach().clone().to(dt).requires_grad_(True)
+        with patched_dropout(mask):
+            out = lay(xx, ei)
+        out.backward(gout.to(dt))
+        rec["out_" + tag] = out.detach()
+        for k, v in grads(lay, xx.grad).items():
+            rec[k + "_" + tag] = v
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else v) for k, v in rec.items()}
+
+
+def run_net(ref_net, dataset, f, n, e, graphs, seed, classes=7):
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = ref_net.GATNet("GAT", dataset, f)
+    x = torch.rand(n, f, generator=gen)
+    if graphs:
+        per = n // graphs
+        ei = torch.cat([torch.randint(0, per, (2, e // graphs), generator=gen) + b * per for b in range(graphs)], 1)
+        batch = torch.arange(n) // per
+        y = torch.randint(0, 10, (graphs,), generator=gen)
+    else:
+        ei, batch = torch.randint(0, n, (2, e), generator=gen), None
+        y = torch.randint(0, classes, (n,), generator=gen)
+    rec = dict(x=x, edge_index=ei, y=y)
+    if batch is not None:
+        rec["batch"] = batch
+    for k, v in net.state_dict().items():
+        rec["param:" + k] = v.clone()
+    net.eval()                                           # dropout off (feature dropout GATNet.py:78 and GAT.py:61)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = net.to(dt)
+        m.zero_grad()
+        out = m(SimpleNamespace(x=x.to(dt), edge_index=ei, batch=batch))
+        loss = torch.nn.functional.nll_loss(out, y)
+        loss.backward()
+        rec["out_" + tag] = out.detach()
+        rec["loss_" + tag] = loss.detach()
+        for k, p_ in m.named_parameters():
+            rec["grad:" + k + "_" + tag] = p_.grad.clone()
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else v) for k, v in rec.items()}
+
+
+def main():
+    ref_gat, ref_net = ref_loader.load()
+    for case in LAYER_CASES:
+        rec = run_layer(ref_gat, case)
+        np.savez_compressed(os.path.join(HERE, f"layer_{case[0]}.npz"), **rec)
+        print("layer", case[0], {k: v.shape for k, v in rec.items() if k in ("x", "edge_index", "out_f32")})
+    np.savez_compressed(os.path.join(HERE, "net_cora.npz"), **run_net(ref_net, "Cora", 37, 150, 700, 0, 11))
+    np.savez_compressed(os.path.join(HERE, "net_cifar_f3.npz"), **run_net(ref_net, "CIFAR10", 3, 160, 1280, 8, 12))
+    np.savez_compressed(os.path.join(HERE, "net_pubmed.npz"), **run_net(ref_net, "Pubmed", 21, 130, 600, 0, 13, classes=3))
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
