@@ -1,0 +1,118 @@
+"""ctypes binding of include/b200gat.h (the C-ABI boundary of the hot path).
+
+The library is the ONLY implementation of the path: there is no CPU or PyTorch fallback.  If libb200gat.so is missing
+or does not load, every op raises — loudly — instead of degrading.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200gat.so")
+ABI_VERSION = 3
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class Graph(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64),
+                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("eid", C.c_void_p),
+                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("in_channels", C.c_int64), ("out_channels", C.c_int64), ("heads", C.c_int64), ("c_pad", C.c_int64),
+                ("concat", C.c_int32), ("negative_slope", C.c_float)]
+
+
+class ProjFwdArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("num_nodes", C.c_int64),
+                ("x", C.c_void_p), ("ldx", C.c_int64),
+                ("w", C.c_void_p), ("bw", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
+                ("b1", C.c_void_p), ("b2", C.c_void_p),
+                ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class EdgeFwdArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("graph", Graph),
+                ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p), ("bias", C.c_void_p),
+                ("mask", C.c_void_p),
+                ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p)]
+
+
+class EdgeBwdArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("graph", Graph),
+                ("gout", C.c_void_p), ("ldgo", C.c_int64),
+                ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("o_heads", C.c_void_p), ("bias", C.c_void_p),
+                ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p),
+                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("mask", C.c_void_p),
+                ("a1", C.c_void_p), ("a2", C.c_void_p),
+                ("g_t", C.c_void_p), ("g_bw", C.c_void_p), ("g_a1", C.c_void_p), ("g_a2", C.c_void_p),
+                ("g_b1", C.c_void_p), ("g_b2", C.c_void_p), ("g_bias", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class ProjBwdArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("num_nodes", C.c_int64),
+                ("g_t", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p),
+                ("g_x", C.c_void_p), ("ldgx", C.c_int64), ("g_w", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+_SIGNATURES = {
+    "b200gat_abi_version": (C.c_int, []),
+    "b200gat_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "b200gat_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "b200gat_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 +
+                          [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200gat_proj_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
+    "b200gat_proj_fwd": (C.c_int, [C.POINTER(ProjFwdArgs), C.c_void_p]),
+    "b200gat_edge_fwd": (C.c_int, [C.POINTER(EdgeFwdArgs), C.c_void_p]),
+    "b200gat_edge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
+    "b200gat_edge_bwd": (C.c_int, [C.POINTER(EdgeBwdArgs), C.c_void_p]),
+    "b200gat_proj_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
+    "b200gat_proj_bwd": (C.c_int, [C.POINTER(ProjBwdArgs), C.c_void_p]),
+}
+
+_lib = None
+launches = 0   # number of kernel-launching ABI calls made by this process (bench.py reports it)
+
+
+class B200GatError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libb200gat.so (once).  Raises if it is absent: the CUDA extension IS the product path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise B200GatError(
+            f"{LIB_PATH} not found: build it with `python -m atmlgraphattentionnetworks_b200.build` "
+            "(there is no CPU / PyTorch fallback for the GAT hot path)")
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(handle, name)   # AttributeError if the header and the library disagree
+        fn.restype, fn.argtypes = res, args
+    got = handle.b200gat_abi_version()
+    if got != ABI_VERSION:
+        raise B200GatError(f"libb200gat.so ABI version {got} != binding version {ABI_VERSION}: rebuild the library")
+    _lib = handle
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    lib().b200gat_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        kind = "argument error" if rc < 0 else "CUDA error"
+        raise B200GatError(f"{what} failed ({kind} {rc}): {last_error()}")

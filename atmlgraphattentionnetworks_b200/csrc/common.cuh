@@ -1,0 +1,61 @@
+// Shared helpers for the b200gat kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/b200gat.h"
+
+namespace b200gat {
+
+// ---- error reporting (thread-local message, C-ABI return codes) ----
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define B200GAT_REQUIRE(cond, code, ...) \
+  do { if (!(cond)) return ::b200gat::fail((code), __VA_ARGS__); } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();   // cached multiprocessor count of the current device (148 on B200)
+
+inline int validate_layer(const b200gat_layer& L) {
+  B200GAT_REQUIRE(L.in_channels > 0 && L.out_channels > 0 && L.heads > 0, B200GAT_E_SHAPE,
+                  "layer: in_channels/out_channels/heads must be positive");
+  B200GAT_REQUIRE(L.c_pad == ((L.out_channels + 3) / 4) * 4, B200GAT_E_SHAPE,
+                  "layer: c_pad must be round_up(out_channels, 4)");
+  B200GAT_REQUIRE(L.c_pad <= 512, B200GAT_E_UNSUPPORTED, "layer: out_channels > 512 per head is not supported");
+  B200GAT_REQUIRE(L.heads <= 1024, B200GAT_E_UNSUPPORTED, "layer: more than 1024 heads is not supported");
+  return 0;
+}
+
+inline int validate_graph(const b200gat_graph& g) {
+  B200GAT_REQUIRE(g.num_nodes >= 0 && g.num_edges >= g.num_nodes, B200GAT_E_SHAPE,
+                  "graph: num_edges must include the N self loops");
+  B200GAT_REQUIRE(g.num_edges < (int64_t(1) << 31), B200GAT_E_SHAPE, "graph: E + N must be < 2^31");
+  if (g.num_nodes == 0) return 0;
+  B200GAT_REQUIRE(g.rowptr && g.col && g.colptr && g.crow, B200GAT_E_NULL, "graph: NULL array");
+  return 0;
+}
+
+// ---- device helpers ----
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
+
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, G));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+  return v;
+}
+
+}  // namespace b200gat

@@ -1,0 +1,353 @@
+// K3 — fused edge backward.  The reference has no backward code: loss.backward() (run_inductive.py:84) differentiates
+// GAT.py:53-67 through saved per-edge tensors.  Here nothing per-edge was saved; alpha is recomputed from
+// s_src, s_dst and the forward's rowmax / rowsum, and (closed form, SURVEY.md §3D, checked by oracle/closed_form.py)
+//     G[i,h,:]   = concat ? gout[i, hC:(h+1)C] : gout[i,:] / H
+//     Drow[i,h]  = <G[i,h,:], O[i,h,:]>                       (= sum_k alpha~_k dalpha_k: no second pass over edges)
+//     dalpha_k   = mask_k <G[i,h,:], Wh[j,h,:]>
+//     dz_k       = alpha_k (dalpha_k - Drow[i,h]) * (z_k > 0 ? 1 : slope)
+//     gWh[j,h,:] = sum_{k in out(j)} alpha_k mask_k G[i_k,h,:]     g_s_src[j,h] = sum_{out(j)} dz     g_s_dst[i,h] = sum_{in(i)} dz
+//     gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2 ;  g_bw = colsum gT ; g_a1 = colsum g_s_src*Wh ; g_a2 = colsum g_s_dst*Wh
+// Passes:  drow_kernel (stream)  ->  edge_bwd_kernel (CSC: one lane group per (source row j, head h); Wh[j,h,:] stays
+// in registers, G[i] rows are gathered 128 bits per lane; gWh / g_s_src are written without atomics, g_s_dst is the
+// one cross-orientation reduction: [N,H] float atomics)  ->  bwd_finish_kernel (stream: gT in place + column sums).
+#include "common.cuh"
+#include <math.h>
+
+namespace b200gat {
+
+// ---- Drow, and (when the upstream gradient is not directly gatherable) a padded copy of G ------------------------
+struct DrowParams {
+  int64_t N;
+  int H, C, Cp;
+  int concat_like;           // concat || H == 1
+  const float* gout; int64_t ldgo;
+  const float* out; int64_t ldo;      // concat_like: O = out - bias
+  const float* o_heads;               // otherwise
+  const float* bias;
+  float gscale;                       // 1 or 1/H
+  float* gp; int64_t ldgp;            // optional padded copy: concat_like ? [N, H*Cp] : [N, Cp]
+  float* drow;                        // [N, H]
+};
+
+__global__ void __launch_bounds__(256) drow_kernel(const DrowParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t items = p.N * p.H;
+  for (int64_t item = warp; item < items; item += nwarps) {
+    const int64_t i = item / p.H;
+    const int h = static_cast<int>(item - i * p.H);
+    const float* g = p.gout + i * p.ldgo + (p.concat_like ? h * p.C : 0);
+    float d = 0.f;
+    for (int c = lane; c < p.Cp; c += 32) {
+      float gv = 0.f;
+      if (c < p.C) {
+        gv = __ldg(g + c) * p.gscale;
+        const float o = p.concat_like ? __ldg(p.out + i * p.ldo + h * p.C + c) - __ldg(p.bias + h * p.C + c)
+                                      : __ldg(p.o_heads + (i * p.H + h) * int64_t(p.Cp) + c);
+        d = fmaf(gv, o, d);
+      }
+      if (p.gp && (p.concat_like || h == 0)) p.gp[i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c] = gv;
+    }
+    d = group_sum<32>(d);
+    if (lane == 0) p.drow[item] = d;
+  }
+}
+
+// ---- column sums of a [N, ncols] matrix (g_bias = sum_n gout[n,:]) ------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ in, int64_t ld, int64_t N, int ncols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < ncols)
+    for (int64_t r = int64_t(blockIdx.y) * 8 + ty; r < N; r += int64_t(gridDim.y) * 8) s += __ldg(in + r * ld + c);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < ncols) {
+#pragma unroll
+    for (int u = 1; u < 8; ++u) s += red[u][tx];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ---- the CSC pass ---------------------------------------------------------------------------------------------------
+struct EdgeBwdParams {
+  int64_t N, items;
+  int H, Cp, Dp;
+  float slope;
+  const int32_t* colptr; const int32_t* crow; const int32_t* ceid;
+  const float* wh; const float* s_src; const float* s_dst; const float* rowmax; const float* rowsum;
+  const float* drow; const float* mask;
+  const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
+  float* gwh;                              // [N, Dp]
+  float* g_s_src; float* g_s_dst;          // [N, H]; g_s_dst is zero-initialised and accumulated atomically
+};
+
+template <int G, int NV, bool HAS_MASK>
+__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
+  const int64_t Dp = p.Dp;
+
+  for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
+    const int64_t item = base + gi;
+    const bool valid = item < p.items;
+    const int64_t j = valid ? item / H : 0;
+    const int h = valid ? static_cast<int>(item - j * H) : 0;
+    const int beg = valid ? __ldg(p.colptr + j) : 0;
+    const int end = valid ? __ldg(p.colptr + j + 1) : 0;
+    const int deg = end - beg;
+    const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
+    const float ss = valid ? __ldg(p.s_src + j * H + h) : 0.f;
+
+    float4 whv[NV], acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      whv[v] = (valid && gl + v * G < Q) ? ldg4(p.wh + j * Dp + h * Cp + 4 * (gl + v * G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float gsrc = 0.f;
+    const float* gh = p.g + h * p.hs + 4 * gl;
+
+    for (int k0 = 0; k0 < maxdeg; k0 += G) {
+      const int k = beg + k0 + gl;
+      const bool ok = k < end;
+      int i = static_cast<int>(j);
+      float alpha = 0.f, at = 0.f, mk = 1.f, dr = 0.f, dslope = 0.f;
+      if (ok) {
+        i = __ldg(p.crow + k);
+        const int64_t ih = int64_t(i) * H + h;
+        const float z = __ldg(p.s_dst + ih) + ss;
+        dslope = z > 0.f ? 1.f : p.slope;
+        alpha = expf(leaky(z, p.slope) - __ldg(p.rowmax + ih)) / (__ldg(p.rowsum + ih) + 1e-16f);
+        if (HAS_MASK) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
+        at = alpha * mk;
+        dr = __ldg(p.drow + ih);
+      }
+      float dot_mine = 0.f;
+      const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const int it = __shfl_sync(FULL, i, t, G);
+        const float a_t = __shfl_sync(FULL, at, t, G);
+        const float* src = gh + int64_t(it) * p.ldg;
+        float d = 0.f;
+        if (a_t != 0.f) {   // padded / dropped / underflowed edges: dz needs no dot product (mask * dot == 0)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (gl + v * G < Q) {
+            const float4 g4 = ldg4(src + 4 * v * G);
+            acc[v].x = fmaf(a_t, g4.x, acc[v].x);
+            acc[v].y = fmaf(a_t, g4.y, acc[v].y);
+            acc[v].z = fmaf(a_t, g4.z, acc[v].z);
+            acc[v].w = fmaf(a_t, g4.w, acc[v].w);
+            d = fmaf(g4.x, whv[v].x, d);
+            d = fmaf(g4.y, whv[v].y, d);
+            d = fmaf(g4.z, whv[v].z, d);
+            d = fmaf(g4.w, whv[v].w, d);
+          }
+        }
+        }
+        d = group_sum<G>(d);
+        if (gl == t) dot_mine = d;
+      }
+      if (ok) {
+        const float dz = alpha * (mk * dot_mine - dr) * dslope;
+        gsrc += dz;
+        atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+      }
+    }
+    gsrc = group_sum<G>(gsrc);
+    if (!valid) continue;
+    if (gl == 0) p.g_s_src[j * H + h] = gsrc;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int q = gl + v * G;
+      if (q < Q) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + 4 * q) = acc[v];
+    }
+  }
+}
+
+// ---- gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2 in place, plus every column sum the parameters need ---------------
+struct FinishParams {
+  int64_t N;
+  int H, Cp, Dp;
+  const float* wh; const float* a1; const float* a2; const float* g_s_src; const float* g_s_dst;
+  float* g_t;                              // in: gWh, out: gT
+  float* g_bw; float* g_a1; float* g_a2;   // [Dp] zero-initialised
+  float* g_b1; float* g_b2;                // [H]  zero-initialised
+};
+
+__global__ void __launch_bounds__(256) bwd_finish_kernel(const FinishParams p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.Dp) return;
+  const int h = c / p.Cp;
+  const bool head_lead = (c - h * p.Cp) == 0;
+  const float a1c = __ldg(p.a1 + c), a2c = __ldg(p.a2 + c);
+  float sbw = 0.f, sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;
+  const int64_t rows_per = ceil_div(p.N, gridDim.y);
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per;
+  const int64_t r1 = r0 + rows_per < p.N ? r0 + rows_per : p.N;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const float gs = __ldg(p.g_s_src + r * p.H + h), gd = __ldg(p.g_s_dst + r * p.H + h);
+    const float w = __ldg(p.wh + r * p.Dp + c);
+    const float t = p.g_t[r * p.Dp + c] + gs * a1c + gd * a2c;
+    p.g_t[r * p.Dp + c] = t;
+    sbw += t;
+    sa1 = fmaf(gs, w, sa1);
+    sa2 = fmaf(gd, w, sa2);
+    sb1 += gs;
+    sb2 += gd;
+  }
+  atomicAdd(p.g_bw + c, sbw);
+  atomicAdd(p.g_a1 + c, sa1);
+  atomicAdd(p.g_a2 + c, sa2);
+  if (head_lead) {
+    atomicAdd(p.g_b1 + h, sb1);
+    atomicAdd(p.g_b2 + h, sb2);
+  }
+}
+
+template <int G, int NV>
+static int launch_edge_bwd(const EdgeBwdParams& p, cudaStream_t stream) {
+  constexpr int GPW = 32 / G;
+  const int threads = 256;
+  const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (p.mask) edge_bwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  else edge_bwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
+  return check_launch("edge_bwd_kernel");
+}
+
+struct BwdWorkspace { size_t off_drow, off_gsrc, off_gdst, off_gp, total; };
+
+static BwdWorkspace plan_bwd(const b200gat_layer& L, int64_t N) {
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  BwdWorkspace w;
+  const size_t nh = up(size_t(N > 0 ? N : 1) * L.heads * sizeof(float));
+  w.off_drow = 0;
+  w.off_gsrc = nh;
+  w.off_gdst = 2 * nh;
+  w.off_gp = 3 * nh;
+  w.total = 3 * nh + up(size_t(N > 0 ? N : 1) * L.heads * L.c_pad * sizeof(float));
+  return w;
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* L, int64_t N) {
+  if (!L || N < 0) return 0;
+  return plan_bwd(*L, N).total;
+}
+
+extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "edge_bwd: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  if ((rc = validate_graph(a->graph))) return rc;
+  const b200gat_layer& L = a->layer;
+  const int64_t N = a->graph.num_nodes;
+  const int H = static_cast<int>(L.heads), C = static_cast<int>(L.out_channels), Cp = static_cast<int>(L.c_pad);
+  const int64_t Dp = int64_t(H) * Cp;
+  const bool concat_like = L.concat || H == 1;
+  const int64_t d_out = L.concat ? int64_t(H) * C : C;
+  B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2 && a->g_bias, B200GAT_E_NULL,
+                  "edge_bwd: NULL parameter-gradient pointer");
+  cudaError_t ce = cudaMemsetAsync(a->g_bw, 0, Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_a1, 0, Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_a2, 0, Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_b1, 0, H * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_b2, 0, H * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_bias, 0, d_out * sizeof(float), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+  if (N == 0) return 0;
+  B200GAT_REQUIRE(a->gout && a->wh && a->s_src && a->s_dst && a->rowmax && a->rowsum && a->a1 && a->a2 && a->g_t &&
+                  a->bias && a->workspace, B200GAT_E_NULL, "edge_bwd: NULL pointer");
+  B200GAT_REQUIRE(concat_like ? (a->out != nullptr) : (a->o_heads != nullptr), B200GAT_E_NULL,
+                  "edge_bwd: forward output (out / o_heads) missing");
+  B200GAT_REQUIRE(!a->mask || a->graph.ceid, B200GAT_E_NULL, "edge_bwd: mask needs graph.ceid");
+  B200GAT_REQUIRE(a->ldgo >= d_out && (!concat_like || a->ldo >= d_out), B200GAT_E_SHAPE, "edge_bwd: leading dimension < D_out");
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t), B200GAT_E_ALIGN, "edge_bwd: wh / g_t must be 16-byte aligned");
+  const BwdWorkspace w = plan_bwd(L, N);
+  B200GAT_REQUIRE(a->workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "edge_bwd: workspace %zu < %zu bytes",
+                  a->workspace_bytes, w.total);
+  B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255u) == 0, B200GAT_E_ALIGN,
+                  "edge_bwd: workspace must be 256-byte aligned");
+  char* base = static_cast<char*>(a->workspace);
+  float* drow = reinterpret_cast<float*>(base + w.off_drow);
+  float* g_s_src = reinterpret_cast<float*>(base + w.off_gsrc);
+  float* g_s_dst = reinterpret_cast<float*>(base + w.off_gdst);
+  float* gp = reinterpret_cast<float*>(base + w.off_gp);
+  ce = cudaMemsetAsync(g_s_dst, 0, size_t(N) * H * sizeof(float), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+
+  const int64_t cap = int64_t(sm_count()) * 8;
+  // (1) Drow (+ padded G when gout rows are not 128-bit gatherable per head)
+  const bool direct_g = concat_like && C % 4 == 0 && a->ldgo % 4 == 0 && aligned16(a->gout);
+  DrowParams dp;
+  dp.N = N; dp.H = H; dp.C = C; dp.Cp = Cp; dp.concat_like = concat_like ? 1 : 0;
+  dp.gout = a->gout; dp.ldgo = a->ldgo; dp.out = a->out; dp.ldo = a->ldo; dp.o_heads = a->o_heads; dp.bias = a->bias;
+  dp.gscale = concat_like ? 1.f : 1.f / static_cast<float>(H);
+  dp.gp = direct_g ? nullptr : gp;
+  dp.ldgp = concat_like ? Dp : Cp;
+  dp.drow = drow;
+  {
+    const int64_t want = ceil_div(N * H, 8);
+    drow_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
+    if ((rc = check_launch("drow_kernel"))) return rc;
+  }
+  // (2) g_bias
+  {
+    const int64_t ysplit = ceil_div(N, 8) < 64 ? ceil_div(N, 8) : 64;
+    dim3 grid(static_cast<unsigned>(ceil_div(d_out, 32)), static_cast<unsigned>(ysplit));
+    colsum_kernel<<<grid, 256, 0, stream>>>(a->gout, a->ldgo, N, static_cast<int>(d_out), a->g_bias);
+    if ((rc = check_launch("colsum_kernel"))) return rc;
+  }
+  // (3) CSC pass
+  EdgeBwdParams p;
+  p.N = N; p.items = N * H; p.H = H; p.Cp = Cp; p.Dp = static_cast<int>(Dp); p.slope = L.negative_slope;
+  p.colptr = a->graph.colptr; p.crow = a->graph.crow; p.ceid = a->graph.ceid;
+  p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.rowmax = a->rowmax; p.rowsum = a->rowsum;
+  p.drow = drow; p.mask = a->mask;
+  if (direct_g) { p.g = a->gout; p.ldg = a->ldgo; p.hs = C; }
+  else if (concat_like) { p.g = gp; p.ldg = Dp; p.hs = Cp; }
+  else { p.g = gp; p.ldg = Cp; p.hs = 0; }
+  p.gwh = a->g_t; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
+  const int Q = Cp / 4;
+  if (Q <= 1) rc = launch_edge_bwd<1, 1>(p, stream);
+  else if (Q <= 2) rc = launch_edge_bwd<2, 1>(p, stream);
+  else if (Q <= 4) rc = launch_edge_bwd<4, 1>(p, stream);
+  else if (Q <= 8) rc = launch_edge_bwd<8, 1>(p, stream);
+  else if (Q <= 16) rc = launch_edge_bwd<16, 1>(p, stream);
+  else if (Q <= 32) rc = launch_edge_bwd<32, 1>(p, stream);
+  else if (Q <= 64) rc = launch_edge_bwd<32, 2>(p, stream);
+  else rc = launch_edge_bwd<32, 4>(p, stream);
+  if (rc) return rc;
+  // (4) gT + parameter column sums
+  FinishParams f;
+  f.N = N; f.H = H; f.Cp = Cp; f.Dp = static_cast<int>(Dp);
+  f.wh = a->wh; f.a1 = a->a1; f.a2 = a->a2; f.g_s_src = g_s_src; f.g_s_dst = g_s_dst; f.g_t = a->g_t;
+  f.g_bw = a->g_bw; f.g_a1 = a->g_a1; f.g_a2 = a->g_a2; f.g_b1 = a->g_b1; f.g_b2 = a->g_b2;
+  {
+    const int xblocks = static_cast<int>(ceil_div(Dp, 256));
+    int64_t ysplit = ceil_div(cap, xblocks);
+    const int64_t max_y = ceil_div(N, 16);
+    if (ysplit > max_y) ysplit = max_y;
+    if (ysplit < 1) ysplit = 1;
+    dim3 grid(xblocks, static_cast<unsigned>(ysplit));
+    bwd_finish_kernel<<<grid, 256, 0, stream>>>(f);
+    rc = check_launch("bwd_finish_kernel");
+  }
+  return rc;
+}

@@ -1,0 +1,216 @@
+// K2 — fused edge forward (GAT.py:53-67): for every destination row i and head h
+//     z_k = s_dst[i,h] + s_src[j_k,h]          e_k = LeakyReLU(z_k)                        (GAT.py:57-58)
+//     alpha_k = exp(e_k - max e) / (sum exp(e - max) + 1e-16)                             (GAT.py:60 [PyG] softmax)
+//     O[i,h,:] = sum_k alpha_k * mask_k * Wh[j_k,h,:]                                       (GAT.py:61-62, aggr='add')
+//     out[i]   = concat ? O[i].reshape(H*C) + bias : mean_h O[i,h,:] + bias                 (GAT.py:63-66,54)
+// over the destination-sorted CSR.  No per-edge tensor is written: only out [N,D_out] and the softmax
+// statistics rowmax/rowsum [N,H] that let the backward recompute alpha.
+//
+// Scheduling: one lane GROUP of G = pow2ceil(min(c_pad/4, 32)) lanes per (row, head) work item, 32/G items per
+// warp, items = row-major (i, h) so groups of one warp share the row's col[] lines.  Inside an item the G lanes
+// first run EDGE-parallel (coalesced col[] load, 4-byte s_src gather, one exp per (edge, head)), then
+// FEATURE-parallel: the (j, p) pair of each edge is broadcast by width-G shuffles and every lane gathers its
+// 128-bit slices of Wh[j,h,:] (ld.global.nc.v4.f32) into NV float4 accumulators.  Rows are walked twice
+// (max, then exp/aggregate) — the second walk hits L1/L2 — so there is no running-max rescale.
+#include "common.cuh"
+#include <math.h>
+
+namespace b200gat {
+
+struct EdgeFwdParams {
+  int64_t N, items;
+  int H, C, Cp, Dp;
+  float slope;
+  const int32_t* rowptr; const int32_t* col; const int32_t* eid;
+  const float* wh; const float* s_src; const float* s_dst; const float* bias; const float* mask;
+  float* out; int64_t ldo;
+  float* rowmax; float* rowsum; float* o_heads;
+  int heads_mode;   // 1: write per-head aggregate to o_heads (mean over heads done by head_mean_kernel)
+  int vec_out;      // 1: out rows / head offsets are 16-byte aligned -> float4 stores
+};
+
+template <int G, int NV, bool HAS_MASK>
+__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
+  const int64_t Dp = p.Dp;
+
+  for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
+    const int64_t item = base + gi;
+    const bool valid = item < p.items;
+    const int64_t i = valid ? item / H : 0;
+    const int h = valid ? static_cast<int>(item - i * H) : 0;
+    const int beg = valid ? __ldg(p.rowptr + i) : 0;
+    const int end = valid ? __ldg(p.rowptr + i + 1) : 0;
+    const int deg = end - beg;
+    const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
+    const float sd = valid ? __ldg(p.s_dst + i * H + h) : 0.f;
+    const float* ssrc_h = p.s_src + h;
+
+    // ---- walk 1: row maximum of the LeakyReLU logits (edge-parallel) ----
+    float m = -INFINITY;
+    for (int k0 = gl; k0 < maxdeg; k0 += G) {
+      const int k = beg + k0;
+      if (k < end) {
+        const int j = __ldg(p.col + k);
+        m = fmaxf(m, leaky(sd + __ldg(ssrc_h + int64_t(j) * H), p.slope));
+      }
+    }
+    m = group_max<G>(m);
+
+    // ---- walk 2: exp, row sum, weighted aggregation ----
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    const float* whh = p.wh + h * Cp + 4 * gl;
+    for (int k0 = 0; k0 < maxdeg; k0 += G) {
+      const int k = beg + k0 + gl;
+      const bool ok = k < end;
+      int j = static_cast<int>(i);
+      float pp = 0.f, pm = 0.f;
+      if (ok) {
+        j = __ldg(p.col + k);
+        pp = expf(leaky(sd + __ldg(ssrc_h + int64_t(j) * H), p.slope) - m);
+        pm = pp;
+        if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
+      }
+      l += pp;
+      const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const int jt = __shfl_sync(FULL, j, t, G);
+        const float pt = __shfl_sync(FULL, pm, t, G);
+        if (pt != 0.f) {   // dropped / padded / underflowed edges contribute nothing: skip the gather
+          const float* src = whh + int64_t(jt) * Dp;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (gl + v * G < Q) {
+              const float4 w = ldg4(src + 4 * v * G);
+              acc[v].x = fmaf(pt, w.x, acc[v].x);
+              acc[v].y = fmaf(pt, w.y, acc[v].y);
+              acc[v].z = fmaf(pt, w.z, acc[v].z);
+              acc[v].w = fmaf(pt, w.w, acc[v].w);
+            }
+          }
+        }
+      }
+    }
+    l = group_sum<G>(l);
+    if (!valid) continue;
+    const float inv = 1.f / (l + 1e-16f);
+    if (gl == 0) {
+      p.rowmax[i * H + h] = m;
+      p.rowsum[i * H + h] = l;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int q = gl + v * G;
+      if (q >= Q) continue;
+      float4 o = make_float4(acc[v].x * inv, acc[v].y * inv, acc[v].z * inv, acc[v].w * inv);
+      if (p.heads_mode) {
+        *reinterpret_cast<float4*>(p.o_heads + i * Dp + h * Cp + 4 * q) = o;
+      } else {
+        const int c = 4 * q;
+        const float* b = p.bias + h * p.C + c;
+        float* dst = p.out + i * p.ldo + h * p.C + c;
+        if (p.vec_out) {
+          const float4 bb = ldg4(b);
+          *reinterpret_cast<float4*>(dst) = make_float4(o.x + bb.x, o.y + bb.y, o.z + bb.z, o.w + bb.w);
+        } else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c + u < p.C) dst[u] = ov[u] + __ldg(b + u);
+        }
+      }
+    }
+  }
+}
+
+// concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c]
+__global__ void __launch_bounds__(256)
+head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bias, float* __restrict__ out,
+                 int64_t ldo, int64_t N, int H, int C, int Cp) {
+  const int64_t total = N * C;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = t / C;
+    const int c = static_cast<int>(t - i * C);
+    const float* src = o_heads + i * int64_t(H) * Cp + c;
+    float s = 0.f;
+    for (int h = 0; h < H; ++h) s += __ldg(src + h * Cp);
+    out[i * ldo + c] = s / static_cast<float>(H) + __ldg(bias + c);
+  }
+}
+
+template <int G, int NV>
+static int launch_edge_fwd(const EdgeFwdParams& p, cudaStream_t stream) {
+  constexpr int GPW = 32 / G;
+  const int threads = 256;
+  const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (p.mask) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  else edge_fwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
+  return check_launch("edge_fwd_kernel");
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "edge_fwd: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  if ((rc = validate_graph(a->graph))) return rc;
+  const b200gat_layer& L = a->layer;
+  const int64_t N = a->graph.num_nodes;
+  if (N == 0) return 0;
+  const int H = static_cast<int>(L.heads), C = static_cast<int>(L.out_channels), Cp = static_cast<int>(L.c_pad);
+  const bool heads_mode = !L.concat && H > 1;
+  const int64_t d_out = L.concat ? int64_t(H) * C : C;
+  B200GAT_REQUIRE(a->wh && a->s_src && a->s_dst && a->bias && a->out && a->rowmax && a->rowsum, B200GAT_E_NULL,
+                  "edge_fwd: NULL pointer");
+  B200GAT_REQUIRE(!heads_mode || a->o_heads, B200GAT_E_NULL, "edge_fwd: o_heads is required when !concat && heads > 1");
+  B200GAT_REQUIRE(!a->mask || a->graph.eid, B200GAT_E_NULL, "edge_fwd: mask needs graph.eid");
+  B200GAT_REQUIRE(a->ldo >= d_out, B200GAT_E_SHAPE, "edge_fwd: ldo < D_out");
+  B200GAT_REQUIRE(aligned16(a->wh) && (!heads_mode || aligned16(a->o_heads)), B200GAT_E_ALIGN,
+                  "edge_fwd: wh / o_heads must be 16-byte aligned");
+  B200GAT_REQUIRE(N * int64_t(H) * Cp < (int64_t(1) << 40), B200GAT_E_SHAPE, "edge_fwd: N * Dp too large");
+
+  EdgeFwdParams p;
+  p.N = N; p.items = N * H;
+  p.H = H; p.C = C; p.Cp = Cp; p.Dp = H * Cp;
+  p.slope = L.negative_slope;
+  p.rowptr = a->graph.rowptr; p.col = a->graph.col; p.eid = a->graph.eid;
+  p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.bias = a->bias; p.mask = a->mask;
+  p.out = a->out; p.ldo = a->ldo; p.rowmax = a->rowmax; p.rowsum = a->rowsum; p.o_heads = a->o_heads;
+  p.heads_mode = heads_mode ? 1 : 0;
+  p.vec_out = (!heads_mode && C % 4 == 0 && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
+
+  const int Q = Cp / 4;
+  if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, stream);
+  else if (Q <= 2) rc = launch_edge_fwd<2, 1>(p, stream);
+  else if (Q <= 4) rc = launch_edge_fwd<4, 1>(p, stream);
+  else if (Q <= 8) rc = launch_edge_fwd<8, 1>(p, stream);
+  else if (Q <= 16) rc = launch_edge_fwd<16, 1>(p, stream);
+  else if (Q <= 32) rc = launch_edge_fwd<32, 1>(p, stream);
+  else if (Q <= 64) rc = launch_edge_fwd<32, 2>(p, stream);
+  else rc = launch_edge_fwd<32, 4>(p, stream);
+  if (rc) return rc;
+  if (heads_mode) {
+    const int64_t total = N * C;
+    const int64_t want = ceil_div(total, 256);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    head_mean_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(a->o_heads, a->bias, a->out, a->ldo,
+                                                                                   N, H, C, Cp);
+    rc = check_launch("head_mean_kernel");
+  }
+  return rc;
+}

@@ -1,0 +1,109 @@
+// K1 / K4 — the dense per-head projection (GAT.py:42-52) and its backward.
+//   forward : Wh[N,Dp] = X[N,F] · Wp[Dp,F]^T + bw ;  s_src = <Wh_h, a1_h> + b1_h ;  s_dst = <Wh_h, a2_h> + b2_h
+//   backward: gX[N,F] = gT[N,Dp] · Wp[Dp,F] ;  gW[Dp,F] = gT^T · X
+// Dispatch: the tcgen05 (3xTF32) kernel in proj_tc.cu takes the shapes it supports; everything else runs on
+// the fp32 CUDA-core GEMM below.  Both produce fp32 results within the 1e-5 parity bar.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "proj_tc.cuh"
+
+namespace b200gat {
+
+// one warp per node row: s_src / s_dst from the freshly written Wh row (L2-resident at this point)
+__global__ void __launch_bounds__(256)
+logits_kernel(const float* __restrict__ wh, const float* __restrict__ a1, const float* __restrict__ a2,
+              const float* __restrict__ b1, const float* __restrict__ b2, float* __restrict__ s_src,
+              float* __restrict__ s_dst, int64_t N, int H, int Cp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = Cp >> 2;
+  for (int64_t i = warp; i < N; i += nwarps) {
+    const float* row = wh + i * int64_t(H) * Cp;
+    for (int h = 0; h < H; ++h) {
+      float d1 = 0.f, d2 = 0.f;
+      for (int q = lane; q < Q; q += 32) {
+        const float4 v = ldg4(row + h * Cp + 4 * q);
+        const float4 p = ldg4(a1 + h * Cp + 4 * q);
+        const float4 r = ldg4(a2 + h * Cp + 4 * q);
+        d1 += v.x * p.x + v.y * p.y + v.z * p.z + v.w * p.w;
+        d2 += v.x * r.x + v.y * r.y + v.z * r.z + v.w * r.w;
+      }
+      d1 = group_sum<32>(d1);
+      d2 = group_sum<32>(d2);
+      if (lane == 0) {
+        s_src[i * H + h] = d1 + b1[h];
+        s_dst[i * H + h] = d2 + b2[h];
+      }
+    }
+  }
+}
+
+}  // namespace b200gat
+
+using namespace b200gat;
+
+extern "C" size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* L, int64_t N) {
+  if (!L || N < 0) return 0;
+  return proj_tc_fwd_workspace_bytes(*L, N);
+}
+
+extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "proj_fwd: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  const b200gat_layer& L = a->layer;
+  const int64_t N = a->num_nodes, F = L.in_channels, H = L.heads, Cp = L.c_pad, Dp = H * Cp;
+  B200GAT_REQUIRE(N >= 0, B200GAT_E_SHAPE, "proj_fwd: negative num_nodes");
+  if (N == 0) return 0;
+  B200GAT_REQUIRE(a->x && a->w && a->bw && a->a1 && a->a2 && a->b1 && a->b2 && a->wh && a->s_src && a->s_dst,
+                  B200GAT_E_NULL, "proj_fwd: NULL pointer");
+  B200GAT_REQUIRE(a->ldx >= F, B200GAT_E_SHAPE, "proj_fwd: ldx < in_channels");
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
+                  "proj_fwd: wh/a1/a2 must be 16-byte aligned");
+  if (proj_tc_fwd_supported(L, N)) return proj_tc_fwd(*a, stream);
+  rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream);
+  if (rc) return rc;
+  const int threads = 256;
+  const int64_t want = ceil_div(N * 32, threads);
+  const int blocks = static_cast<int>(want < int64_t(sm_count()) * 8 ? want : int64_t(sm_count()) * 8);
+  logits_kernel<<<blocks, threads, 0, stream>>>(a->wh, a->a1, a->a2, a->b1, a->b2, a->s_src, a->s_dst, N,
+                                                static_cast<int>(H), static_cast<int>(Cp));
+  return check_launch("logits_kernel");
+}
+
+extern "C" size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* L, int64_t N) {
+  if (!L || N < 0) return 0;
+  return proj_tc_bwd_workspace_bytes(*L, N);
+}
+
+extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "proj_bwd: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  const b200gat_layer& L = a->layer;
+  const int64_t N = a->num_nodes, F = L.in_channels, Dp = L.heads * L.c_pad;
+  B200GAT_REQUIRE(N >= 0, B200GAT_E_SHAPE, "proj_bwd: negative num_nodes");
+  B200GAT_REQUIRE(a->g_w && a->w, B200GAT_E_NULL, "proj_bwd: NULL pointer");
+  if (N == 0) {
+    cudaError_t e = cudaMemsetAsync(a->g_w, 0, size_t(Dp) * F * sizeof(float), stream);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "proj_bwd: memset: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  B200GAT_REQUIRE(a->g_t && a->x, B200GAT_E_NULL, "proj_bwd: NULL pointer");
+  B200GAT_REQUIRE(a->ldx >= F && (!a->g_x || a->ldgx >= F), B200GAT_E_SHAPE, "proj_bwd: leading dimension < in_channels");
+  if (proj_tc_bwd_supported(L, N)) return proj_tc_bwd(*a, stream);
+  if (a->g_x) {
+    rc = gemm_simt<true, false>(a->g_t, Dp, a->w, F, a->g_x, a->ldgx, nullptr, N, F, Dp, 1, stream);
+    if (rc) return rc;
+  }
+  // gW[Dp,F] = sum_n gT[n,:]^T X[n,:] — reduction over nodes, split so that the grid covers the machine
+  const int64_t tiles = ceil_div(Dp, GM) * ceil_div(F, GN);
+  int64_t splits = ceil_div(int64_t(sm_count()) * 4, tiles);
+  const int64_t max_splits = ceil_div(N, 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return gemm_simt<false, false>(a->g_t, Dp, a->x, a->ldx, a->g_w, F, nullptr, Dp, F, N, static_cast<int>(splits), stream);
+}

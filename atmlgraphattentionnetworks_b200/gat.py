@@ -1,0 +1,189 @@
+"""Drop-in `GraphAttentionLayer` (reference: GAT.py:8-67) on the B200-native kernels.
+
+Constructor, forward signature, parameter registration order (hence seed-identical init and state_dict keys:
+`bias`, `ws.{h}.weight/bias`, `attentions1.{h}.weight/bias`, `attentions2.{h}.weight/bias`) follow GAT.py:8-35.
+forward(x, edge_index) (GAT.py:37) runs
+    csr_build (cached)  ->  proj_fwd  ->  edge_fwd           and in backward       edge_bwd  ->  proj_bwd
+through the C ABI in include/b200gat.h.  CUDA tensors only — there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _abi
+from .graph import GLOBAL_CACHE, GraphCSR
+
+NEGATIVE_SLOPE = 0.2   # GAT.py:30
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _layer_struct(f_in, c, h, concat):
+    return _abi.Layer(int(f_in), int(c), int(h), (int(c) + 3) // 4 * 4, 1 if concat else 0, NEGATIVE_SLOPE)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class GATLayerFunction(torch.autograd.Function):
+    """x [N,F], packed padded parameters (W [Dp,F], bw/a1/a2 [Dp], b1/b2 [H], bias [D_out]) -> out [N, D_out]."""
+
+    @staticmethod
+    def forward(ctx, x, w, bw, a1, a2, b1, b2, bias, graph, geom, mask):
+        f_in, c, h, concat = geom
+        lib = _abi.lib()
+        dev = x.device
+        n = x.shape[0]
+        layer = _layer_struct(f_in, c, h, concat)
+        cp = layer.c_pad
+        dp = h * cp
+        d_out = h * c if concat else c
+        heads_mode = (not concat) and h > 1
+        x = x.contiguous()
+        w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
+        f32 = dict(dtype=torch.float32, device=dev)
+        wh = torch.empty((n, dp), **f32)
+        s_src = torch.empty((n, h), **f32)
+        s_dst = torch.empty((n, h), **f32)
+        out = torch.empty((n, d_out), **f32)
+        rowmax = torch.empty((n, h), **f32)
+        rowsum = torch.empty((n, h), **f32)
+        o_heads = torch.empty((n, dp), **f32) if heads_mode else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
+            ws = _workspace(ws_bytes, dev)
+            pa = _abi.ProjFwdArgs(layer, n, x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
+                                  a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
+                                  s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes)
+            _abi.check(lib.b200gat_proj_fwd(ctypes.byref(pa), stream), "b200gat_proj_fwd")
+            ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
+                                  bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
+                                  rowsum.data_ptr(), _ptr(o_heads))
+            _abi.check(lib.b200gat_edge_fwd(ctypes.byref(ea), stream), "b200gat_edge_fwd")
+            _abi.launches += 2
+        ctx.graph, ctx.geom, ctx.mask = graph, geom, mask
+        ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, fwd_out = ctx.saved_tensors
+        graph, (f_in, c, h, concat), mask = ctx.graph, ctx.geom, ctx.mask
+        lib = _abi.lib()
+        dev = x.device
+        n = x.shape[0]
+        layer = _layer_struct(f_in, c, h, concat)
+        cp = layer.c_pad
+        dp = h * cp
+        d_out = h * c if concat else c
+        heads_mode = (not concat) and h > 1
+        gout = gout.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_t = torch.empty((n, dp), **f32)
+        g_bw = torch.empty(dp, **f32)
+        g_a1 = torch.empty(dp, **f32)
+        g_a2 = torch.empty(dp, **f32)
+        g_b1 = torch.empty(h, **f32)
+        g_b2 = torch.empty(h, **f32)
+        g_bias = torch.empty(d_out, **f32)
+        g_w = torch.empty((dp, f_in), **f32)
+        need_gx = ctx.needs_input_grad[0]
+        g_x = torch.empty((n, f_in), **f32) if need_gx else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws_bytes = int(lib.b200gat_edge_bwd_workspace_bytes(ctypes.byref(layer), n))
+            ws = _workspace(ws_bytes, dev)
+            ea = _abi.EdgeBwdArgs(layer, graph.c_struct(), gout.data_ptr(), d_out,
+                                  None if heads_mode else fwd_out.data_ptr(), d_out,
+                                  fwd_out.data_ptr() if heads_mode else None, bias.data_ptr(),
+                                  wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(), rowmax.data_ptr(),
+                                  rowsum.data_ptr(), _ptr(mask), a1.data_ptr(), a2.data_ptr(),
+                                  g_t.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(), g_a2.data_ptr(),
+                                  g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes)
+            _abi.check(lib.b200gat_edge_bwd(ctypes.byref(ea), stream), "b200gat_edge_bwd")
+            ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
+            ws2 = _workspace(ws2_bytes, dev)
+            pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
+                                  _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes)
+            _abi.check(lib.b200gat_proj_bwd(ctypes.byref(pb), stream), "b200gat_proj_bwd")
+            _abi.launches += 2
+        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None
+
+
+class GraphAttentionLayer(torch.nn.Module):
+    """GAT.py:8 — GraphAttentionLayer(input_channels, output_channels, num_heads=1, concat=False, dropout=0.6)."""
+
+    def __init__(self, input_channels, output_channels, num_heads=1, concat=False, dropout=0.6):
+        super().__init__()
+        self.input_channels = input_channels
+        self.output_channels = output_channels
+        self.num_heads = num_heads
+        self.dropout_val = dropout
+        self.ws = torch.nn.ModuleList()
+        self.attentions1 = torch.nn.ModuleList()
+        self.attentions2 = torch.nn.ModuleList()
+        for _ in range(num_heads):   # RNG order of GAT.py:19-25: three default Linear inits, then three xavier draws
+            head_transform = torch.nn.Linear(input_channels, output_channels)
+            attention1 = torch.nn.Linear(output_channels, 1)
+            attention2 = torch.nn.Linear(output_channels, 1)
+            torch.nn.init.xavier_uniform_(head_transform.weight)
+            torch.nn.init.xavier_uniform_(attention1.weight)
+            torch.nn.init.xavier_uniform_(attention2.weight)
+            self.ws.append(head_transform)
+            self.attentions1.append(attention1)
+            self.attentions2.append(attention2)
+        self.concat = concat
+        if not concat:
+            self.bias = torch.nn.Parameter(torch.zeros(output_channels))
+        else:
+            self.bias = torch.nn.Parameter(torch.zeros(output_channels * num_heads))
+        self.graph_cache = GLOBAL_CACHE
+        self.mask_hook = None   # parity tests: callable (E', H) -> keep-multiplier [E', H] in ORIGINAL edge order
+
+    # ---- parameter packing: [Dp, F] / [Dp] / [H] views of the per-head Linear modules (autograd splits the grads back)
+    def _packed(self):
+        c, h = self.output_channels, self.num_heads
+        pad = (c + 3) // 4 * 4 - c
+        w = torch.stack([m.weight for m in self.ws])                              # [H, C, F]
+        bw = torch.stack([m.bias for m in self.ws])                               # [H, C]
+        a1 = torch.cat([m.weight for m in self.attentions1])                      # [H, C]
+        a2 = torch.cat([m.weight for m in self.attentions2])
+        b1 = torch.cat([m.bias for m in self.attentions1])                        # [H]
+        b2 = torch.cat([m.bias for m in self.attentions2])
+        if pad:
+            w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            bw, a1, a2 = (torch.nn.functional.pad(t, (0, pad)) for t in (bw, a1, a2))
+        return w.reshape(h * (c + pad), -1), bw.reshape(-1), a1.reshape(-1), a2.reshape(-1), b1, b2
+
+    def _dropout_mask(self, num_edges, device):
+        """GAT.py:61: F.dropout on the [E', H] coefficients (original edge order), scaled 1/(1-p), not renormalised."""
+        if self.mask_hook is not None:
+            return self.mask_hook((num_edges, self.num_heads)).to(device=device, dtype=torch.float32).contiguous()
+        p = float(self.dropout_val)
+        if not self.training or p <= 0.0:
+            return None
+        if p >= 1.0:
+            return torch.zeros((num_edges, self.num_heads), dtype=torch.float32, device=device)
+        keep = torch.rand((num_edges, self.num_heads), device=device) >= p
+        return keep.to(torch.float32).mul_(1.0 / (1.0 - p))
+
+    def forward(self, x, edge_index, graph=None):
+        if not x.is_cuda:
+            raise _abi.B200GatError("GraphAttentionLayer runs on CUDA tensors only (B200-native path, no CPU fallback)")
+        if x.dtype != torch.float32:
+            raise TypeError(f"x must be float32, got {x.dtype}")
+        if x.dim() != 2 or x.shape[1] != self.input_channels:
+            raise ValueError(f"x must be [N, {self.input_channels}], got {tuple(x.shape)}")
+        n = x.shape[0]
+        if graph is None:
+            graph = self.graph_cache.get(edge_index, n)
+        elif not isinstance(graph, GraphCSR) or graph.num_nodes != n:
+            raise ValueError("graph does not match x")
+        mask = self._dropout_mask(graph.num_edges, x.device)
+        w, bw, a1, a2, b1, b2 = self._packed()
+        geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
+        return GATLayerFunction.apply(x, w, bw, a1, a2, b1, b2, self.bias, graph, geom, mask)

@@ -1,0 +1,95 @@
+"""Drop-in `GATNet` (reference: GATNet.py:13-87), GAT branch on the B200-native layer.
+
+Constructor table and forward glue follow GATNet.py:17-37 / :60-87 exactly (same attribute names => same
+state_dict keys).  The glue ops (feature dropout, ELU, per-graph mean readout, lin1/lin2, log_softmax) stay PyTorch
+CUDA ops in this round (SURVEY.md §8f row 2 lists their fusion as a next row); the layer is the hot path.
+The GCN branch (GATNet.py:38-58) is a third-party comparison baseline (torch_geometric.nn.GCNConv) and is only
+available when torch_geometric is installed.
+"""
+import torch
+import torch.nn.functional as F
+
+from .gat import GraphAttentionLayer
+
+# dataset -> (conv2 out_channels, conv2 heads, conv2 concat, dropout)           GATNet.py:17-37
+_GAT_TABLE = {
+    "CIFAR10": (8, 8, True, 0.0),
+    "Cora": (7, 1, False, 0.6),
+    "Citeseer": (6, 1, False, 0.6),
+    "Pubmed": (3, 8, False, 0.6),
+    "AmazonComp": (10, 8, False, 0.6),
+    "AmazonPhotos": (8, 8, False, 0.6),
+}
+_GCN_OUT = {"CIFAR10": 64, "Cora": 7, "Citeseer": 6, "Pubmed": 3, "AmazonComp": 10, "AmazonPhotos": 8}
+
+
+def segment_mean(x, batch):
+    """torch_scatter.scatter_mean(x, batch, dim=0) (GATNet.py:73): per-graph mean, empty groups -> 0."""
+    groups = int(batch.max().item()) + 1 if batch.numel() else 0
+    total = torch.zeros((groups, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
+    count = torch.zeros(groups, dtype=x.dtype, device=x.device).index_add_(
+        0, batch, torch.ones(batch.numel(), dtype=x.dtype, device=x.device)).clamp_(min=1)
+    return total / count.unsqueeze(1)
+
+
+class GATNet(torch.nn.Module):
+    """GATNet.py:13 — GATNet(model_name, dataset_name, num_features); forward(data) with data.x, data.edge_index
+    (and data.batch for CIFAR10)."""
+
+    def __init__(self, model_name, dataset_name, num_features):
+        super().__init__()
+        self.dataset_name = dataset_name
+        self.model_name = model_name
+        if model_name == "GAT":
+            if dataset_name in _GAT_TABLE:
+                out2, heads2, concat2, p = _GAT_TABLE[dataset_name]
+                self.conv1 = GraphAttentionLayer(num_features, 8, num_heads=8, concat=True, dropout=p)
+                self.conv2 = GraphAttentionLayer(64, out2, num_heads=heads2, concat=concat2, dropout=p)
+                if dataset_name == "CIFAR10":
+                    self.lin1 = torch.nn.Linear(64, 64)
+                    self.lin2 = torch.nn.Linear(64, 10)
+        elif model_name == "GCN":
+            try:
+                from torch_geometric.nn import GCNConv
+            except ImportError as e:   # pragma: no cover - PyG is not installable in this image
+                raise NotImplementedError(
+                    "the GCN comparison branch (GATNet.py:38-58) needs torch_geometric.nn.GCNConv, which is a "
+                    "third-party baseline outside the GAT hot path") from e
+            if dataset_name in _GCN_OUT:
+                self.conv1 = GCNConv(num_features, 64)
+                self.conv2 = GCNConv(64, _GCN_OUT[dataset_name])
+                if dataset_name == "CIFAR10":
+                    self.lin1 = torch.nn.Linear(64, 64)
+                    self.lin2 = torch.nn.Linear(64, 10)
+
+    def forward(self, data):
+        x, edge_index = data.x, data.edge_index
+        act = F.relu if self.model_name == "GCN" else F.elu
+        if self.dataset_name == "CIFAR10":                     # GATNet.py:62-76
+            x = act(self.conv1(x, edge_index))
+            x = act(self.conv2(x, edge_index))
+            x = segment_mean(x, data.batch)
+            x = F.relu(self.lin1(x))
+            return F.log_softmax(self.lin2(x), dim=1)
+        x = F.dropout(x, p=0.6, training=self.training)        # GATNet.py:78
+        x = act(self.conv1(x, edge_index))
+        x = F.dropout(x, p=0.6, training=self.training)
+        x = self.conv2(x, edge_index)
+        return F.log_softmax(x, dim=1)
+
+
+class GATStack(torch.nn.Module):
+    """Plain stack of GraphAttentionLayer + ELU between layers: the composition used for the PPI-shaped and
+    large-graph BASELINE configs (the reference has no 3-layer model).  spec = [(in, out, heads, concat)]."""
+
+    def __init__(self, spec, dropout=0.0):
+        super().__init__()
+        self.convs = torch.nn.ModuleList(
+            [GraphAttentionLayer(i, o, num_heads=h, concat=c, dropout=dropout) for (i, o, h, c) in spec])
+
+    def forward(self, x, edge_index):
+        for k, conv in enumerate(self.convs):
+            x = conv(x, edge_index)
+            if k + 1 < len(self.convs):
+                x = F.elu(x)
+        return x

@@ -1,0 +1,149 @@
+/* b200gat.h — C ABI of the B200-native GAT layer hot path (libb200gat.so).
+ *
+ * Every entry point replaces a stretch of the reference's Python/PyG layer (there is no FFI in the reference;
+ * the boundary a maintainer would bind is GraphAttentionLayer.forward and the autograd backward it implies):
+ *
+ *   b200gat_csr_build ..... GAT.py:38   add_self_loops + the (dst-)grouping PyG's softmax/scatter do implicitly
+ *   b200gat_proj_fwd ...... GAT.py:42-52  per-head Linear x3 + stack/transpose (Wh, s_src, s_dst)
+ *   b200gat_edge_fwd ...... GAT.py:53-67  propagate: gather, LeakyReLU logits, segment softmax, dropout mask,
+ *                                         weighting, concat/mean, scatter-add, + bias
+ *   b200gat_edge_bwd ...... autograd of GAT.py:53-67 (run_inductive.py:84), recomputing alpha
+ *   b200gat_proj_bwd ...... autograd of GAT.py:42-52 (gX, gW)
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.  All data pointers are DEVICE pointers on the
+ *     caller's current device; `stream` is a cudaStream_t passed as void*.
+ *   - the caller owns every buffer, including workspaces; the library never allocates, frees or retains
+ *     pointers past a call and never synchronises the device.
+ *   - return 0 = ok; < 0 = argument error detected on the host before any launch (B200GAT_E_*);
+ *     > 0 = cudaError_t of a failed launch.  b200gat_last_error() holds a message for the calling thread.
+ *   - fp32 values, int32 graph indices (E + N < 2^31), int64 only for the incoming COO edge_index.
+ *
+ * Internal feature layout: a layer with H heads of C channels keeps per-node rows of width Dp = H * c_pad,
+ * c_pad = round_up(C, 4), head-major; pad channels are zero (W / bw / a1 / a2 pad rows are zero).
+ */
+#ifndef B200GAT_H
+#define B200GAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GAT_ABI_VERSION 3
+
+enum {
+  B200GAT_OK = 0,
+  B200GAT_E_NULL = -1,       /* a required pointer is NULL */
+  B200GAT_E_SHAPE = -2,      /* inconsistent / unsupported sizes */
+  B200GAT_E_ALIGN = -3,      /* pointer or leading dimension not 16-byte aligned where required */
+  B200GAT_E_WORKSPACE = -4,  /* workspace too small */
+  B200GAT_E_UNSUPPORTED = -5
+};
+
+/* Destination-sorted CSR (+ source-sorted CSC) of [edge_index ; self loops].  All arrays int32 on device. */
+typedef struct {
+  int64_t num_nodes;       /* N */
+  int64_t num_edges;       /* E' = E + N */
+  const int32_t* rowptr;   /* [N+1]  CSR by destination */
+  const int32_t* col;      /* [E']   source of each CSR entry */
+  const int32_t* eid;      /* [E']   position of the entry in the ORIGINAL [edges ; loops] order */
+  const int32_t* colptr;   /* [N+1]  CSC by source (stable w.r.t. CSR order) */
+  const int32_t* crow;     /* [E']   destination of each CSC entry */
+  const int32_t* ceid;     /* [E']   original position of each CSC entry */
+} b200gat_graph;
+
+/* Layer geometry, GAT.py:8 (input_channels, output_channels, num_heads, concat). */
+typedef struct {
+  int64_t in_channels;     /* F_in */
+  int64_t out_channels;    /* C    */
+  int64_t heads;           /* H    */
+  int64_t c_pad;           /* round_up(C, 4) */
+  int32_t concat;          /* GAT.py:63-66 */
+  float negative_slope;    /* GAT.py:30 (0.2) */
+} b200gat_layer;
+
+int b200gat_abi_version(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
+int b200gat_last_error(char* buf, size_t buf_len);
+
+/* ---- K0: graph ingestion (GAT.py:38) ------------------------------------------------------------------- */
+size_t b200gat_csr_workspace_bytes(int64_t num_nodes, int64_t num_input_edges);
+/* edge_index: int64 [2, E] contiguous (row 0 = source, row 1 = target).  status: device int32[2], set to
+ * {number of out-of-range indices, reserved}; the arrays are still well-formed (indices clamped) if non-zero. */
+int b200gat_csr_build(const int64_t* edge_index, int64_t num_input_edges, int64_t num_nodes,
+                      int32_t* rowptr, int32_t* col, int32_t* eid,
+                      int32_t* colptr, int32_t* crow, int32_t* ceid,
+                      int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K1: projection + attention logits (GAT.py:42-52) ----------------------------------------------------- */
+typedef struct {
+  b200gat_layer layer;
+  int64_t num_nodes;
+  const float* x;  int64_t ldx;   /* [N, F_in], row stride ldx */
+  const float* w;                 /* [Dp, F_in] packed ws[h].weight, pad rows zero */
+  const float* bw;                /* [Dp]       packed ws[h].bias */
+  const float* a1; const float* a2;   /* [Dp]   attentions1/2[h].weight */
+  const float* b1; const float* b2;   /* [H]    attentions1/2[h].bias */
+  float* wh;                      /* out [N, Dp] */
+  float* s_src; float* s_dst;     /* out [N, H]  (a1·Wh + b1 gathered at the source, a2·Wh + b2 at the target) */
+  void* workspace; size_t workspace_bytes;
+} b200gat_proj_fwd_args;
+size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
+int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream);
+
+/* ---- K2: fused edge forward (GAT.py:53-67) ---------------------------------------------------------------- */
+typedef struct {
+  b200gat_layer layer;
+  b200gat_graph graph;
+  const float* wh;                /* [N, Dp] */
+  const float* s_src; const float* s_dst;   /* [N, H] */
+  const float* bias;              /* [H*C] if concat else [C] */
+  const float* mask;              /* optional [E', H] dropout keep-multiplier in ORIGINAL edge order (GAT.py:61) */
+  float* out;  int64_t ldo;       /* [N, D_out] */
+  float* rowmax; float* rowsum;   /* out [N, H]: softmax statistics kept for the recomputing backward */
+  float* o_heads;                 /* out [N, Dp]; required iff !concat && H > 1 (per-head aggregate) */
+} b200gat_edge_fwd_args;
+int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream);
+
+/* ---- K3: fused edge backward (recomputes alpha; no per-edge tensor) ------------------------------------------ */
+typedef struct {
+  b200gat_layer layer;
+  b200gat_graph graph;
+  const float* gout; int64_t ldgo;    /* [N, D_out] upstream gradient */
+  const float* out;  int64_t ldo;     /* [N, D_out] forward output (used when concat || H == 1) */
+  const float* o_heads;               /* [N, Dp]   (used when !concat && H > 1) */
+  const float* bias;
+  const float* wh; const float* s_src; const float* s_dst;
+  const float* rowmax; const float* rowsum;
+  const float* mask;                  /* optional, as in forward */
+  const float* a1; const float* a2;   /* [Dp] */
+  float* g_t;                         /* out [N, Dp]: total gradient w.r.t. Wh */
+  float* g_bw; float* g_a1; float* g_a2;   /* out [Dp] */
+  float* g_b1; float* g_b2;           /* out [H] */
+  float* g_bias;                      /* out [D_out] */
+  void* workspace; size_t workspace_bytes;
+} b200gat_edge_bwd_args;
+size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
+int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream);
+
+/* ---- K4: projection backward -------------------------------------------------------------------------------- */
+typedef struct {
+  b200gat_layer layer;
+  int64_t num_nodes;
+  const float* g_t;                   /* [N, Dp] */
+  const float* x; int64_t ldx;        /* [N, F_in] */
+  const float* w;                     /* [Dp, F_in] */
+  float* g_x; int64_t ldgx;           /* out [N, F_in] or NULL (input does not require grad) */
+  float* g_w;                         /* out [Dp, F_in] */
+  void* workspace; size_t workspace_bytes;
+} b200gat_proj_bwd_args;
+size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
+int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GAT_H */

@@ -1,0 +1,243 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the drop-in modules and the
+C ABI, against (1) the fixtures produced by the unmodified reference, (2) the CPU oracle on seeded inputs, and
+(3) size-independent properties at the BASELINE PPI-shaped size.
+
+Tolerances: integer CSR arrays bit-exact; fp32 outputs and all gradients max|a-b| <= 1e-5 * max|b| against the
+reference's fp32 result (north-star).  The per-edge dot products of the backward pick up
+reassociation noise of the same order as the reference's own (its distance to f64 is 3e-7..8e-7).
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import (FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, load_packed, nerr, packed_grads)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _product_layer(g):
+    import GAT
+    H, C, F = g["W"].shape
+    layer = GAT.GraphAttentionLayer(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]))
+    load_packed(layer, g)
+    return layer.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- K0: CSR, bit-exact
+def _random_graphs():
+    rng = np.random.default_rng(7)
+    yield "empty", np.zeros((2, 0), dtype=np.int64), 5
+    yield "single", np.zeros((2, 0), dtype=np.int64), 1
+    yield "small", rng.integers(0, 50, size=(2, 400)), 50
+    ei = rng.integers(0, 300, size=(2, 5000))
+    ei[1, :2500] = 7                                       # hub destination
+    ei[:, 100:200] = ei[:, 0:100]                          # duplicates
+    ei[1, 200:300] = ei[0, 200:300]                        # existing self loops
+    yield "hub_dups_loops", ei, 300
+    yield "mid", rng.integers(0, 70001, size=(2, 1_000_003)), 70001
+    yield "n_pow2", rng.integers(0, 4096, size=(2, 30000)), 4096
+
+
+@pytest.mark.parametrize("name,ei,n", list(_random_graphs()), ids=lambda v: v if isinstance(v, str) else None)
+def test_csr_build_bit_exact(name, ei, n):
+    from atmlgraphattentionnetworks_b200.graph import build_csr
+    from oracle.csr_oracle import csr_oracle
+    g = build_csr(torch.from_numpy(ei).to(DEV), n)
+    want = csr_oracle(ei, n)
+    for k, t in g.arrays().items():
+        got = t.cpu().numpy().astype(np.int64)
+        assert got.shape == want[k].shape, k
+        assert np.array_equal(got, want[k]), k
+
+
+def test_csr_build_rejects_out_of_range_indices():
+    from atmlgraphattentionnetworks_b200.graph import build_csr
+    ei = torch.tensor([[0, 1, 9], [1, 2, 0]], dtype=torch.int64, device=DEV)
+    with pytest.raises(IndexError):
+        build_csr(ei, 5)
+    with pytest.raises(IndexError):
+        build_csr(torch.tensor([[0, -1], [1, 2]], dtype=torch.int64, device=DEV), 5)
+
+
+# ------------------------------------------------------------------------- layer fwd + bwd vs the reference fixtures
+@pytest.mark.parametrize("path", LAYER_FILES, ids=case_id)
+def test_layer_matches_reference_fixture(path):
+    g = load(path)
+    layer = _product_layer(g)
+    layer.train()
+    if "mask" in g:
+        mask = torch.from_numpy(g["mask"])
+        layer.mask_hook = lambda shape: mask
+    else:
+        layer.dropout_val = 0.0
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    out = layer(x, torch.from_numpy(g["edge_index"]).to(DEV))
+    out.backward(torch.from_numpy(g["gout"]).to(DEV))
+    assert out.shape == g["out_f32"].shape and out.dtype == torch.float32
+    assert nerr(out.detach().cpu().numpy(), g["out_f32"]) <= FP32_TOL
+    got = packed_grads(layer, x.grad)
+    for k in GRAD_KEYS:
+        assert nerr(got[k], g[k + "_f32"]) <= FP32_TOL, k
+    # and against f64 truth: the CUDA path is no further from it than the stated bar
+    assert nerr(out.detach().cpu().numpy(), g["out_f64"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("path", NET_FILES, ids=case_id)
+def test_gatnet_matches_reference_fixture(path):
+    from types import SimpleNamespace
+    import GATNet
+    g = load(path)
+    ds = {"net_cora": "Cora", "net_cifar_f3": "CIFAR10", "net_pubmed": "Pubmed"}[case_id(path)]
+    net = GATNet.GATNet("GAT", ds, g["x"].shape[1])
+    sd = {k[len("param:"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param:")}
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    data = SimpleNamespace(x=torch.from_numpy(g["x"]).to(DEV), edge_index=torch.from_numpy(g["edge_index"]).to(DEV),
+                           batch=torch.from_numpy(g["batch"]).to(DEV) if "batch" in g else None)
+    out = net(data)
+    loss = torch.nn.functional.nll_loss(out, torch.from_numpy(g["y"]).to(DEV))
+    loss.backward()
+    assert nerr(out.detach().cpu().numpy(), g["out_f32"]) <= FP32_TOL
+    assert abs(float(loss) - float(g["loss_f32"])) <= 1e-5 * abs(float(g["loss_f32"]))
+    for k, p in net.named_parameters():
+        assert nerr(p.grad.cpu().numpy(), g["grad:" + k + "_f32"]) <= 2e-5, k
+
+
+# ------------------------------------------------------------------ larger seeded cases vs the CPU oracle (port, f64)
+ORACLE_CASES = [
+    # name, N, E, F, C, H, concat, p, hub
+    ("ppi_l1_like", 3000, 45000, 50, 256, 4, True, 0.0, False),
+    ("ppi_l3_like", 2000, 30000, 96, 121, 6, False, 0.0, False),
+    ("heads16x64", 2500, 30000, 50, 64, 16, True, 0.0, False),
+    ("large_l3_like", 3000, 60000, 64, 47, 4, False, 0.0, True),
+    ("cora_l1_like_drop", 2708, 10556, 143, 8, 8, True, 0.6, False),
+    ("cora_l2_like", 2708, 10556, 64, 7, 1, False, 0.0, False),
+    ("c128_hub", 4000, 80000, 100, 128, 4, True, 0.0, True),
+    ("wide_c512", 500, 6000, 32, 512, 1, True, 0.0, False),
+    ("c20_cat_unaligned_out", 900, 9000, 17, 5, 3, True, 0.0, False),
+]
+
+
+@pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: c[0])
+def test_layer_matches_cpu_oracle(case):
+    import GAT
+    from oracle.gat_port import PortGraphAttentionLayer
+    name, n, e, f, c, h, concat, p, hub = case
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    torch.manual_seed(1)
+    ref = PortGraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p).double()
+    with torch.no_grad():
+        ref.bias.uniform_(-0.5, 0.5)
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    if hub:
+        ei[1, : e // 4] = 11
+        ei[0, e // 4: e // 2] = 13                         # hub source too (CSC side)
+    x = torch.randn(n, f, generator=gen)
+    gout = torch.randn(n, h * c if concat else c, generator=gen)
+    mask = None
+    if p > 0:
+        mask = (torch.rand(e + n, h, generator=gen) >= p).float() / (1 - p)
+        ref.mask_hook = lambda shape: mask
+    ref.train()
+    xr = x.double().requires_grad_(True)
+    out_r = ref(xr, ei)
+    out_r.backward(gout.double())
+    want = packed_grads(ref, xr.grad)
+
+    layer = GAT.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p)
+    layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    layer = layer.to(DEV).train()
+    if mask is not None:
+        layer.mask_hook = lambda shape: mask
+    xg = x.to(DEV).requires_grad_(True)
+    out = layer(xg, ei.to(DEV))
+    out.backward(gout.to(DEV))
+    assert nerr(out.detach().cpu().numpy(), out_r.detach().numpy()) <= FP32_TOL
+    got = packed_grads(layer, xg.grad)
+    for k in GRAD_KEYS:
+        assert nerr(got[k], want[k]) <= FP32_TOL, k
+
+
+def test_eval_mode_ignores_dropout_and_input_without_grad():
+    import GAT
+    torch.manual_seed(0)
+    layer = GAT.GraphAttentionLayer(12, 8, num_heads=8, concat=True, dropout=0.6).to(DEV).eval()
+    x = torch.randn(200, 12, device=DEV)
+    ei = torch.randint(0, 200, (2, 1500), device=DEV)
+    a, b = layer(x, ei), layer(x, ei)
+    assert torch.equal(a, b)                                # deterministic forward, dropout off in eval (GAT.py:61)
+    a.sum().backward()                                      # x needs no grad (layer 1 of every model): g_x skipped
+    assert layer.ws[0].weight.grad is not None and x.grad is None
+    layer.train()
+    c = layer(x, ei)
+    assert not torch.equal(a, c)                            # training mode draws a mask
+    xs = torch.randn(200, 24, device=DEV)[:, ::2]           # non-contiguous input is accepted
+    assert layer(xs, ei).shape == (200, 64)
+
+
+def test_graph_cache_reuse_and_invalidation():
+    import GAT
+    from atmlgraphattentionnetworks_b200.graph import GraphCache
+    torch.manual_seed(0)
+    layer = GAT.GraphAttentionLayer(6, 4, num_heads=2, concat=True, dropout=0.0).to(DEV)
+    layer.graph_cache = GraphCache()
+    x = torch.randn(50, 6, device=DEV)
+    ei = torch.randint(0, 50, (2, 300), device=DEV)
+    o1 = layer(x, ei)
+    o2 = layer(x, ei)
+    assert layer.graph_cache.hits == 1 and layer.graph_cache.misses == 1 and torch.equal(o1, o2)
+    ei[1, 0] = (ei[1, 0] + 1) % 50                          # in-place edit bumps _version -> rebuild
+    layer(x, ei)
+    assert layer.graph_cache.misses == 2
+    layer(x, ei.clone())                                    # a new tensor object is a new graph
+    assert layer.graph_cache.misses == 3
+
+
+# -------------------------------------------------- BASELINE-size properties (PPI-shaped batch, 4 heads x 256)
+@pytest.fixture(scope="module")
+def ppi():
+    from atmlgraphattentionnetworks_b200 import synth
+    d = synth.ppi_shaped()
+    return d.x.to(DEV), d.edge_index.to(DEV)
+
+
+def test_full_size_constant_features_property(ppi):
+    """If every node carries the same Wh row, softmax weights sum to 1 per row, so out == Wh_row + bias for EVERY
+    node whatever the graph (a checksum of the whole gather/softmax/aggregate path at full size)."""
+    import GAT
+    x, ei = ppi
+    torch.manual_seed(0)
+    layer = GAT.GraphAttentionLayer(50, 256, num_heads=4, concat=True, dropout=0.0).to(DEV)
+    with torch.no_grad():
+        layer.bias.uniform_(-1, 1)
+    xc = torch.ones_like(x) * 0.37
+    out = layer(xc, ei)
+    w, bw, *_ = layer._packed()
+    row = (xc[:1] @ w.t() + bw + layer.bias).squeeze(0)
+    assert float((out - row).abs().max()) <= 1e-5 * float(row.abs().max())
+
+
+def test_full_size_edge_order_invariance_and_grad_identities(ppi):
+    """Permuting the COO edge list permutes nothing in the maths: outputs agree to fp32 reassociation noise; and
+    g_bias == column sums of gout, sum(g_b1) relations hold (size-independent identities of SURVEY.md §3D)."""
+    import GAT
+    x, ei = ppi
+    torch.manual_seed(0)
+    layer = GAT.GraphAttentionLayer(50, 256, num_heads=4, concat=True, dropout=0.0).to(DEV)
+    perm = torch.randperm(ei.shape[1], device=DEV)
+    out1 = layer(x, ei)
+    out2 = layer(x, ei[:, perm].contiguous())
+    assert float((out1 - out2).abs().max()) <= 1e-5 * float(out1.abs().max())
+    gout = torch.randn_like(out1)
+    layer.zero_grad()
+    out1.backward(gout)
+    assert nerr(layer.bias.grad.cpu().numpy(), gout.sum(0).cpu().numpy()) <= 1e-5
+    # softmax shift invariance: d loss / d b2[h] = sum_i g_s_dst[i,h] = 0 up to rounding (adding a constant to a row's
+    # logits on the positive side of the LeakyReLU does not change alpha) is NOT exact with the kink, so instead check
+    # the exact identity g_b1[h] == g_b2[h] (both are sum over ALL edges of dz)
+    g_b1 = torch.stack([m.bias.grad for m in layer.attentions1]).flatten()
+    g_b2 = torch.stack([m.bias.grad for m in layer.attentions2]).flatten()
+    scale = float(torch.stack([m.weight.grad for m in layer.attentions1]).abs().max())
+    assert float((g_b1 - g_b2).abs().max()) <= 1e-4 * max(scale, 1e-6)
