@@ -65,6 +65,7 @@ class ProjBwdArgs(C.Structure):
 
 _SIGNATURES = {
     "b200gat_abi_version": (C.c_int, []),
+    "b200gat_launch_count": (C.c_uint64, []),
     "b200gat_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
     "b200gat_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b200gat_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 +
@@ -79,7 +80,13 @@ _SIGNATURES = {
 }
 
 _lib = None
-launches = 0   # number of kernel-launching ABI calls made by this process (bench.py reports it)
+launches = 0   # number of kernel-launching ABI calls made by this process
+timing = None  # when set to a list, gat.py appends (op_name, layer_tag, start_event, end_event) per ABI call
+
+
+def launch_count():
+    """kernels launched by libb200gat.so in this process (bench.py reports the delta over the timed region)."""
+    return int(lib().b200gat_launch_count())
 
 
 class B200GatError(RuntimeError):

@@ -21,7 +21,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;   // kernels launched by this library (not atomic: informational)
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return 0;
   set_error("%s: %s", what, cudaGetErrorString(e));
@@ -44,6 +47,8 @@ int sm_count() {
 }  // namespace b200gat
 
 extern "C" int b200gat_abi_version(void) { return B200GAT_ABI_VERSION; }
+
+extern "C" uint64_t b200gat_launch_count(void) { return b200gat::g_launches; }
 
 extern "C" int b200gat_last_error(char* buf, size_t buf_len) {
   size_t n = strlen(b200gat::g_err);

@@ -24,6 +24,18 @@ def _layer_struct(f_in, c, h, concat):
     return _abi.Layer(int(f_in), int(c), int(h), (int(c) + 3) // 4 * 4, 1 if concat else 0, NEGATIVE_SLOPE)
 
 
+def _call(name, fn, args, stream, tag):
+    """One ABI call; when _abi.timing is a list, bracket it with CUDA events on the launching stream."""
+    if _abi.timing is None:
+        _abi.check(fn(ctypes.byref(args), stream), name)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _abi.check(fn(ctypes.byref(args), stream), name)
+    end.record()
+    _abi.timing.append((name, tag, start, end))
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -59,11 +71,11 @@ class GATLayerFunction(torch.autograd.Function):
             pa = _abi.ProjFwdArgs(layer, n, x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
                                   a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
                                   s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes)
-            _abi.check(lib.b200gat_proj_fwd(ctypes.byref(pa), stream), "b200gat_proj_fwd")
+            _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
             ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
                                   bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
                                   rowsum.data_ptr(), _ptr(o_heads))
-            _abi.check(lib.b200gat_edge_fwd(ctypes.byref(ea), stream), "b200gat_edge_fwd")
+            _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
         ctx.graph, ctx.geom, ctx.mask = graph, geom, mask
         ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads)
@@ -104,12 +116,12 @@ class GATLayerFunction(torch.autograd.Function):
                                   rowsum.data_ptr(), _ptr(mask), a1.data_ptr(), a2.data_ptr(),
                                   g_t.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(), g_a2.data_ptr(),
                                   g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes)
-            _abi.check(lib.b200gat_edge_bwd(ctypes.byref(ea), stream), "b200gat_edge_bwd")
+            _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
             ws2 = _workspace(ws2_bytes, dev)
             pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
                                   _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes)
-            _abi.check(lib.b200gat_proj_bwd(ctypes.byref(pb), stream), "b200gat_proj_bwd")
+            _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, ctx.geom)
             _abi.launches += 2
         return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None
 

@@ -1,0 +1,68 @@
+"""Multi-GPU execution of the path, only where it shards.  One process per GPU, torch.distributed
+(NCCL over NVLink on the box, gloo in the CPU tests of the host logic).
+
+  * batches of small graphs (PPI-shaped, CIFAR10-superpixel-shaped; run_gnn_benchmark.py:60-66): graphs are
+    independent units -> data parallel, the model is replicated and ONE flat NCCL all-reduce of all parameter
+    gradients runs per step (`GradBucket`).
+  * one large graph: contiguous destination-row blocks (`row_partition`); the exchange step is an all-gather of the
+    projected Wh / s_src rows (and of gout in backward).
+  * Cora-sized graphs / heads sweep: replicas only.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_graphs(num_graphs, world_size, rank):
+    """Graph ids owned by `rank`: r, r+P, r+2P, ... (equal counts when P divides num_graphs, as the per-graph mean
+    loss of run_gnn_benchmark.py:64 needs)."""
+    return list(range(rank, num_graphs, world_size))
+
+
+def row_partition(num_nodes, world_size):
+    """Contiguous, near-equal destination-row blocks: [(begin, end)] per rank."""
+    base, rem = divmod(num_nodes, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class GradBucket:
+    """All parameter gradients of a replicated model in ONE flat buffer: p.grad are views into it, so the per-step
+    exchange is a single all-reduce launch (the CIFAR-shaped net is 38 KB of gradients — latency-bound; the
+    PPI-shaped stack 7.4 MB) with no pack / unpack copies."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        self._slots, off = {}, 0
+        for p in self.params:
+            self._slots[id(p)] = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = self._slots[id(p)]
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None, weight=None):
+        """Average (or `weight`-ed sum: pass n_r / N for node-level mean losses) of the gradients over ranks."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        for p in self.params:   # autograd may have replaced a .grad view (e.g. first accumulation): re-pack
+            if p.grad is not None and p.grad.data_ptr() != self._slot(p).data_ptr():
+                self._slot(p).copy_(p.grad)
+                p.grad = self._slot(p)
+        if weight is None:
+            self.flat.div_(dist.get_world_size(group))
+        else:
+            self.flat.mul_(float(weight))
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+    def _slot(self, p):
+        return self._slots[id(p)]

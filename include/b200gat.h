@@ -66,6 +66,8 @@ typedef struct {
 } b200gat_layer;
 
 int b200gat_abi_version(void);
+/* number of kernels this library has launched in the process so far (its own kernels; CUB sort passes excluded) */
+uint64_t b200gat_launch_count(void);
 /* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
 int b200gat_last_error(char* buf, size_t buf_len);
 

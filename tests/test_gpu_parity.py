@@ -75,12 +75,16 @@ def test_layer_matches_reference_fixture(path):
     out = layer(x, torch.from_numpy(g["edge_index"]).to(DEV))
     out.backward(torch.from_numpy(g["gout"]).to(DEV))
     assert out.shape == g["out_f32"].shape and out.dtype == torch.float32
-    assert nerr(out.detach().cpu().numpy(), g["out_f32"]) <= FP32_TOL
     got = packed_grads(layer, x.grad)
-    for k in GRAD_KEYS:
-        assert nerr(got[k], g[k + "_f32"]) <= FP32_TOL, k
-    # and against f64 truth: the CUDA path is no further from it than the stated bar
-    assert nerr(out.detach().cpu().numpy(), g["out_f64"]) <= FP32_TOL
+    got["out"] = out.detach().cpu().numpy()
+    for k in ("out",) + GRAD_KEYS:
+        # Bar: 1e-5 relative against the reference's fp32 result AND against f64 truth.  Where the reference's own
+        # fp32 result is further than that from its f64 result (only the ill-conditioned `big_logits` fixture: logits
+        # ~1e2, its g_b1/g_a2/g_b2 sit 1e-2 from truth through cancellation), the bar widens to 4x that noise floor.
+        floor = nerr(g[k + "_f32"], g[k + "_f64"])
+        tol = max(FP32_TOL, 4.0 * floor)
+        assert nerr(got[k], g[k + "_f32"]) <= tol, (k, floor)
+        assert nerr(got[k], g[k + "_f64"]) <= tol, (k, floor)
 
 
 @pytest.mark.parametrize("path", NET_FILES, ids=case_id)
@@ -102,7 +106,18 @@ def test_gatnet_matches_reference_fixture(path):
     assert nerr(out.detach().cpu().numpy(), g["out_f32"]) <= FP32_TOL
     assert abs(float(loss) - float(g["loss_f32"])) <= 1e-5 * abs(float(g["loss_f32"]))
     for k, p in net.named_parameters():
-        assert nerr(p.grad.cpu().numpy(), g["grad:" + k + "_f32"]) <= 2e-5, k
+        got, want = p.grad.cpu().numpy(), g["grad:" + k + "_f32"]
+        if ".attentions" in k:
+            # d loss / d b1[h], d b2[h] = sum over ALL edges of dz, and d loss / d a2[h] = sum_i (sum_{k in in(i)} dz) Wh[i]:
+            # dz cancels to ~0 inside every softmax row whose LeakyReLU slopes agree, so the fixtures hold 1e-10-sized
+            # rounding residue here; these are judged on the scale of the same head's attentions1 weight gradient
+            # (sum over out-edges: no cancellation)
+            conv, _, rest = k.partition(".attentions")
+            head = rest.split(".")[1]
+            scale = max(np.abs(want).max(), np.abs(g[f"grad:{conv}.attentions1.{head}.weight_f32"]).max())
+            assert np.abs(got - want).max() <= 2e-5 * scale, k
+        else:
+            assert nerr(got, want) <= 2e-5, k
 
 
 # ------------------------------------------------------------------ larger seeded cases vs the CPU oracle (port, f64)
@@ -141,23 +156,36 @@ def test_layer_matches_cpu_oracle(case):
         mask = (torch.rand(e + n, h, generator=gen) >= p).float() / (1 - p)
         ref.mask_hook = lambda shape: mask
     ref.train()
-    xr = x.double().requires_grad_(True)
-    out_r = ref(xr, ei)
-    out_r.backward(gout.double())
-    want = packed_grads(ref, xr.grad)
+
+    def run_port(dt):
+        m = ref.to(dt)
+        m.zero_grad()
+        xr = x.detach().clone().to(dt).requires_grad_(True)
+        o = m(xr, ei)
+        o.backward(gout.to(dt))
+        res = packed_grads(m, xr.grad)
+        res["out"] = o.detach().numpy()
+        return res
+    want32 = run_port(torch.float32)       # what the reference's fp32 arithmetic gives (the 1e-5 target)
+    want = run_port(torch.float64)         # truth
+    state = {k: v.float() for k, v in ref.state_dict().items()}
 
     layer = GAT.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p)
-    layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    layer.load_state_dict(state)
     layer = layer.to(DEV).train()
     if mask is not None:
         layer.mask_hook = lambda shape: mask
-    xg = x.to(DEV).requires_grad_(True)
+    xg = x.detach().clone().to(DEV).requires_grad_(True)
     out = layer(xg, ei.to(DEV))
     out.backward(gout.to(DEV))
-    assert nerr(out.detach().cpu().numpy(), out_r.detach().numpy()) <= FP32_TOL
     got = packed_grads(layer, xg.grad)
-    for k in GRAD_KEYS:
-        assert nerr(got[k], want[k]) <= FP32_TOL, k
+    got["out"] = out.detach().cpu().numpy()
+    for k in ("out",) + GRAD_KEYS:
+        # 1e-5 against f64 truth, widened only where the reference arithmetic itself (fp32 port) is further than
+        # that from truth (g_b1 / g_b2 are sums of dz that cancel almost exactly within every row)
+        floor = nerr(want32[k], want[k])
+        tol = max(FP32_TOL, 4.0 * floor)
+        assert nerr(got[k], want[k]) <= tol, (k, floor)
 
 
 def test_eval_mode_ignores_dropout_and_input_without_grad():
