@@ -132,30 +132,50 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
       }
       float dot_mine = 0.f;
       const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
-#pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const int it = __shfl_sync(FULL, i, t, G);
-        const float a_t = __shfl_sync(FULL, at, t, G);
-        const float* src = gh + int64_t(it) * p.ldg;
-        float d = 0.f;
-        if (a_t != 0.f) {   // padded / dropped / underflowed edges: dz needs no dot product (mask * dot == 0)
+      // U edges per step: issue all U*NV gathers of G[i] rows, then the FMAs, then U interleaved group reductions
+      constexpr int U = NV >= 4 ? 2 : 4;
+      for (int t = 0; t < cnt; t += U) {
+        int it[U];
+        float a_t[U], d[U];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (gl + v * G < Q) {
-            const float4 g4 = ldg4(src + 4 * v * G);
-            acc[v].x = fmaf(a_t, g4.x, acc[v].x);
-            acc[v].y = fmaf(a_t, g4.y, acc[v].y);
-            acc[v].z = fmaf(a_t, g4.z, acc[v].z);
-            acc[v].w = fmaf(a_t, g4.w, acc[v].w);
-            d = fmaf(g4.x, whv[v].x, d);
-            d = fmaf(g4.y, whv[v].y, d);
-            d = fmaf(g4.z, whv[v].z, d);
-            d = fmaf(g4.w, whv[v].w, d);
+        for (int u = 0; u < U; ++u) {
+          it[u] = __shfl_sync(FULL, i, t + u, G);
+          a_t[u] = __shfl_sync(FULL, at, t + u, G);
+          if (t + u >= cnt) a_t[u] = 0.f;
+        }
+        float4 g4[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float* src = gh + int64_t(it[u]) * p.ldg;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            // padded / dropped / underflowed edges: dz needs no dot product (mask * dot == 0) and add nothing
+            g4[u][v] = (a_t[u] != 0.f && gl + v * G < Q) ? ldg4(src + 4 * v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          d[u] = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(a_t[u], g4[u][v].x, acc[v].x);
+            acc[v].y = fmaf(a_t[u], g4[u][v].y, acc[v].y);
+            acc[v].z = fmaf(a_t[u], g4[u][v].z, acc[v].z);
+            acc[v].w = fmaf(a_t[u], g4[u][v].w, acc[v].w);
+            d[u] = fmaf(g4[u][v].x, whv[v].x, d[u]);
+            d[u] = fmaf(g4[u][v].y, whv[v].y, d[u]);
+            d[u] = fmaf(g4[u][v].z, whv[v].z, d[u]);
+            d[u] = fmaf(g4[u][v].w, whv[v].w, d[u]);
+          }
         }
-        d = group_sum<G>(d);
-        if (gl == t) dot_mine = d;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o, G);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (gl == t + u) dot_mine = d[u];
       }
       if (ok) {
         const float dz = alpha * (mk * dot_mine - dr) * dslope;

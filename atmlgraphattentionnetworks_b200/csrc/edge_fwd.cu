@@ -81,21 +81,36 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
       }
       l += pp;
       const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
-#pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const int jt = __shfl_sync(FULL, j, t, G);
-        const float pt = __shfl_sync(FULL, pm, t, G);
-        if (pt != 0.f) {   // dropped / padded / underflowed edges contribute nothing: skip the gather
-          const float* src = whh + int64_t(jt) * Dp;
+      // U edges per step: all U*NV 128-bit gathers are issued before the first FMA consumes one (memory-level
+      // parallelism; a per-edge branch here serialises load -> FMA -> next load and leaves the kernel latency-bound)
+      constexpr int U = NV >= 4 ? 2 : 4;
+      for (int t = 0; t < cnt; t += U) {
+        int jt[U];
+        float pt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          jt[u] = __shfl_sync(FULL, j, t + u, G);
+          pt[u] = __shfl_sync(FULL, pm, t + u, G);
+          if (t + u >= cnt) pt[u] = 0.f;
+        }
+        float4 w[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float* src = whh + int64_t(jt[u]) * Dp;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            if (gl + v * G < Q) {
-              const float4 w = ldg4(src + 4 * v * G);
-              acc[v].x = fmaf(pt, w.x, acc[v].x);
-              acc[v].y = fmaf(pt, w.y, acc[v].y);
-              acc[v].z = fmaf(pt, w.z, acc[v].z);
-              acc[v].w = fmaf(pt, w.w, acc[v].w);
-            }
+            // dropped / padded / underflowed edges contribute nothing: predicate the gather off
+            w[u][v] = (pt[u] != 0.f && gl + v * G < Q) ? ldg4(src + 4 * v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(pt[u], w[u][v].x, acc[v].x);
+            acc[v].y = fmaf(pt[u], w[u][v].y, acc[v].y);
+            acc[v].z = fmaf(pt[u], w[u][v].z, acc[v].z);
+            acc[v].w = fmaf(pt[u], w[u][v].w, acc[v].w);
           }
         }
       }

@@ -39,6 +39,16 @@ logits_kernel(const float* __restrict__ wh, const float* __restrict__ a1, const 
   }
 }
 
+int launch_logits(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
+  const int64_t N = a.num_nodes;
+  const int threads = 256;
+  const int64_t want = ceil_div(N * 32, threads);
+  const int blocks = static_cast<int>(want < int64_t(sm_count()) * 8 ? want : int64_t(sm_count()) * 8);
+  logits_kernel<<<blocks, threads, 0, stream>>>(a.wh, a.a1, a.a2, a.b1, a.b2, a.s_src, a.s_dst, N,
+                                                static_cast<int>(a.layer.heads), static_cast<int>(a.layer.c_pad));
+  return check_launch("logits_kernel");
+}
+
 }  // namespace b200gat
 
 using namespace b200gat;
@@ -65,12 +75,7 @@ extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {
   if (proj_tc_fwd_supported(L, N)) return proj_tc_fwd(*a, stream);
   rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream);
   if (rc) return rc;
-  const int threads = 256;
-  const int64_t want = ceil_div(N * 32, threads);
-  const int blocks = static_cast<int>(want < int64_t(sm_count()) * 8 ? want : int64_t(sm_count()) * 8);
-  logits_kernel<<<blocks, threads, 0, stream>>>(a->wh, a->a1, a->a2, a->b1, a->b2, a->s_src, a->s_dst, N,
-                                                static_cast<int>(H), static_cast<int>(Cp));
-  return check_launch("logits_kernel");
+  return launch_logits(*a, stream);
 }
 
 extern "C" size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* L, int64_t N) {

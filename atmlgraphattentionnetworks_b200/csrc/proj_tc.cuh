@@ -8,6 +8,9 @@ bool proj_tc_fwd_supported(const b200gat_layer& L, int64_t N);
 size_t proj_tc_fwd_workspace_bytes(const b200gat_layer& L, int64_t N);
 int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream);
 
+// the stand-alone attention-logit pass (proj.cu), used when heads straddle the GEMM's output tiles
+int launch_logits(const b200gat_proj_fwd_args& a, cudaStream_t stream);
+
 bool proj_tc_bwd_supported(const b200gat_layer& L, int64_t N);
 size_t proj_tc_bwd_workspace_bytes(const b200gat_layer& L, int64_t N);
 int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream);

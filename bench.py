@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default="ppi", choices=["ppi", "heads", "large"])
     ap.add_argument("--cpu-sample-graphs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu runs): warm-up + steps, minimal JSON")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,6 +279,12 @@ def main():
     with ClockSampler(local_rank) as clocks:
         ms_step = timed(lambda: train_step(x_d, ei_d, y_d), args.steps)
     launches = _abi.launch_count() - launches0
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- end-to-end leg: pinned host buffers in, loss out, every step (new tensors => CSR rebuilt every step) ----
     def e2e_step():
