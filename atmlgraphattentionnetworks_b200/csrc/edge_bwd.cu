@@ -7,29 +7,32 @@
 //     dz_k       = alpha_k (dalpha_k - Drow[i,h]) * (z_k > 0 ? 1 : slope)
 //     gWh[j,h,:] = sum_{k in out(j)} alpha_k mask_k G[i_k,h,:]     g_s_src[j,h] = sum_{out(j)} dz     g_s_dst[i,h] = sum_{in(i)} dz
 //     gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2 ;  g_bw = colsum gT ; g_a1 = colsum g_s_src*Wh ; g_a2 = colsum g_s_dst*Wh
-// Passes:  drow_kernel (stream)  ->  edge_bwd_kernel (CSC: one lane group per (source row j, head h); Wh[j,h,:] stays
-// in registers, G[i] rows are gathered 128 bits per lane; gWh / g_s_src are written without atomics, g_s_dst is the
-// one cross-orientation reduction: [N,H] float atomics)  ->  bwd_finish_kernel (stream: gT in place + column sums).
+// Passes:  bwd_prep_kernel (stream: Drow, and the per-(node, head) record {s_dst, rowmax, 1/(rowsum+1e-16), Drow} packed
+// into one 16-byte gatherable word)  ->  edge_bwd_kernel (CSC: one lane group per (source row j, head h); Wh[j,h,:]
+// stays in registers, G[i] rows are gathered 128 bits per lane; gWh / g_s_src are written without atomics, g_s_dst is
+// the one cross-orientation reduction: [N,H] float atomics)  ->  bwd_finish_kernel (stream: gT in place + column sums).
 #include "common.cuh"
 #include <math.h>
 
 namespace b200gat {
 
-// ---- Drow, and (when the upstream gradient is not directly gatherable) a padded copy of G ------------------------
-struct DrowParams {
+// ---- Drow + row record, and (when the upstream gradient is not directly gatherable) a padded copy of G ------------
+struct PrepParams {
   int64_t N;
   int H, C, Cp;
   int concat_like;           // concat || H == 1
+  int vec;                   // gout / out rows and head offsets are 16-byte aligned (C % 4 == 0 etc.)
   const float* gout; int64_t ldgo;
   const float* out; int64_t ldo;      // concat_like: O = out - bias
   const float* o_heads;               // otherwise
   const float* bias;
+  const float* s_dst; const float* rowmax; const float* rowsum;
   float gscale;                       // 1 or 1/H
   float* gp; int64_t ldgp;            // optional padded copy: concat_like ? [N, H*Cp] : [N, Cp]
-  float* drow;                        // [N, H]
+  float4* rowrec;                     // [N, H] {s_dst, rowmax, 1/(rowsum + 1e-16), Drow}
 };
 
-__global__ void __launch_bounds__(256) drow_kernel(const DrowParams p) {
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -37,20 +40,34 @@ __global__ void __launch_bounds__(256) drow_kernel(const DrowParams p) {
   for (int64_t item = warp; item < items; item += nwarps) {
     const int64_t i = item / p.H;
     const int h = static_cast<int>(item - i * p.H);
-    const float* g = p.gout + i * p.ldgo + (p.concat_like ? h * p.C : 0);
     float d = 0.f;
-    for (int c = lane; c < p.Cp; c += 32) {
-      float gv = 0.f;
-      if (c < p.C) {
-        gv = __ldg(g + c) * p.gscale;
-        const float o = p.concat_like ? __ldg(p.out + i * p.ldo + h * p.C + c) - __ldg(p.bias + h * p.C + c)
-                                      : __ldg(p.o_heads + (i * p.H + h) * int64_t(p.Cp) + c);
-        d = fmaf(gv, o, d);
+    if (p.vec) {   // concat_like, no padded copy needed: 128-bit streaming loads
+      const float* g = p.gout + i * p.ldgo + h * p.C;
+      const float* o = p.out + i * p.ldo + h * p.C;
+      const float* b = p.bias + h * p.C;
+      for (int c = 4 * lane; c < p.C; c += 128) {
+        const float4 gv = ldg4(g + c), ov = ldg4(o + c), bv = ldg4(b + c);
+        d = fmaf(gv.x, ov.x - bv.x, d);
+        d = fmaf(gv.y, ov.y - bv.y, d);
+        d = fmaf(gv.z, ov.z - bv.z, d);
+        d = fmaf(gv.w, ov.w - bv.w, d);
       }
-      if (p.gp && (p.concat_like || h == 0)) p.gp[i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c] = gv;
+    } else {
+      const float* g = p.gout + i * p.ldgo + (p.concat_like ? h * p.C : 0);
+      for (int c = lane; c < p.Cp; c += 32) {
+        float gv = 0.f;
+        if (c < p.C) {
+          gv = __ldg(g + c) * p.gscale;
+          const float o = p.concat_like ? __ldg(p.out + i * p.ldo + h * p.C + c) - __ldg(p.bias + h * p.C + c)
+                                        : __ldg(p.o_heads + (i * p.H + h) * int64_t(p.Cp) + c);
+          d = fmaf(gv, o, d);
+        }
+        if (p.gp && (p.concat_like || h == 0)) p.gp[i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c] = gv;
+      }
     }
     d = group_sum<32>(d);
-    if (lane == 0) p.drow[item] = d;
+    if (lane == 0)
+      p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
   }
 }
 
@@ -78,22 +95,71 @@ struct EdgeBwdParams {
   int H, Cp, Dp;
   float slope;
   const int32_t* colptr; const int32_t* crow; const int32_t* ceid;
-  const float* wh; const float* s_src; const float* s_dst; const float* rowmax; const float* rowsum;
-  const float* drow; const float* mask;
+  const float* wh; const float* s_src; const float4* rowrec; const float* mask;
   const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
   float* gwh;                              // [N, Dp]
   float* g_s_src; float* g_s_dst;          // [N, H]; g_s_dst is zero-initialised and accumulated atomically
 };
 
+// Sum U per-lane partials over the G lanes of a group and hand the total of edge u to the lane with rel == u.
+// Full-warp groups use a transposing butterfly (7 shuffles for 4 edges instead of 20).
+template <int G, int U>
+__device__ __forceinline__ float reduce_deliver(float (&d)[U], int lane, int rel) {
+  constexpr unsigned FULL = 0xffffffffu;
+  float got = 0.f;
+  if (G == 32 && U == 4) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const float r0 = __shfl_xor_sync(FULL, b4 ? d[0] : d[2], 16);
+    const float r1 = __shfl_xor_sync(FULL, b4 ? d[1] : d[3], 16);
+    const float k0 = (b4 ? d[2] : d[0]) + r0;      // lanes with bit4 = 0 keep edges 0,1; bit4 = 1 keep edges 2,3
+    const float k1 = (b4 ? d[3] : d[1]) + r1;
+    const float r = __shfl_xor_sync(FULL, b3 ? k0 : k1, 8);
+    float k = (b3 ? k1 : k0) + r;                  // this lane now owns edge 2*bit4 + bit3
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    got = __shfl_sync(FULL, k, ((rel >> 1) & 1) * 16 + (rel & 1) * 8);
+  } else if (G == 32 && U == 2) {
+    const bool b4 = lane & 16;
+    const float r = __shfl_xor_sync(FULL, b4 ? d[0] : d[1], 16);
+    float k = (b4 ? d[1] : d[0]) + r;              // bit4 selects the edge
+    k += __shfl_xor_sync(FULL, k, 8);
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    got = __shfl_sync(FULL, k, (rel & 1) * 16);
+  } else {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o, G);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (rel == u) got = d[u];
+  }
+  return got;
+}
+
 template <int G, int NV, bool HAS_MASK>
 __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
+  constexpr int U = NV == 1 ? 4 : 2;   // edges gathered per step (memory-level parallelism vs registers)
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
-  const int64_t Dp = p.Dp;
+  const int64_t Dp = p.Dp, ldg = p.ldg;
+  const float slope = p.slope;
+  // lanes beyond the head width gather a clamped (valid) column and are never stored; their Wh slice is zero
+  int off[NV];
+  bool live[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    live[v] = gl + v * G < Q;
+    off[v] = 4 * (live[v] ? gl + v * G : Q - 1);
+  }
 
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
     const int64_t item = base + gi;
@@ -110,10 +176,10 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      whv[v] = (valid && gl + v * G < Q) ? ldg4(p.wh + j * Dp + h * Cp + 4 * (gl + v * G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      whv[v] = (valid && live[v]) ? ldg4(p.wh + j * Dp + h * Cp + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float gsrc = 0.f;
-    const float* gh = p.g + h * p.hs + 4 * gl;
+    const float* gh = p.g + h * p.hs;
 
     for (int k0 = 0; k0 < maxdeg; k0 += G) {
       const int k = beg + k0 + gl;
@@ -122,18 +188,16 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
       float alpha = 0.f, at = 0.f, mk = 1.f, dr = 0.f, dslope = 0.f;
       if (ok) {
         i = __ldg(p.crow + k);
-        const int64_t ih = int64_t(i) * H + h;
-        const float z = __ldg(p.s_dst + ih) + ss;
-        dslope = z > 0.f ? 1.f : p.slope;
-        alpha = expf(leaky(z, p.slope) - __ldg(p.rowmax + ih)) / (__ldg(p.rowsum + ih) + 1e-16f);
+        const float4 rr = __ldg(p.rowrec + int64_t(i) * H + h);   // {s_dst, rowmax, 1/(rowsum+eps), Drow}
+        const float z = rr.x + ss;
+        dslope = z > 0.f ? 1.f : slope;
+        alpha = expf(leaky(z, slope) - rr.y) * rr.z;
         if (HAS_MASK) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
         at = alpha * mk;
-        dr = __ldg(p.drow + ih);
+        dr = rr.w;
       }
       float dot_mine = 0.f;
       const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
-      // U edges per step: issue all U*NV gathers of G[i] rows, then the FMAs, then U interleaved group reductions
-      constexpr int U = NV >= 4 ? 2 : 4;
       for (int t = 0; t < cnt; t += U) {
         int it[U];
         float a_t[U], d[U];
@@ -146,11 +210,14 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
         float4 g4[U][NV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float* src = gh + int64_t(it[u]) * p.ldg;
+          const float* src = gh + int64_t(it[u]) * ldg;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            // padded / dropped / underflowed edges: dz needs no dot product (mask * dot == 0) and add nothing
-            g4[u][v] = (a_t[u] != 0.f && gl + v * G < Q) ? ldg4(src + 4 * v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6): dz needs no dot product, skip the gather
+              g4[u][v] = a_t[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              g4[u][v] = ldg4(src + off[v]);
+            }
           }
         }
 #pragma unroll
@@ -168,14 +235,9 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
             d[u] = fmaf(g4[u][v].w, whv[v].w, d[u]);
           }
         }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o, G);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (gl == t + u) dot_mine = d[u];
+        const int rel = gl - t;
+        const float got = reduce_deliver<G, U>(d, lane, rel);
+        if (rel >= 0 && rel < U) dot_mine = got;
       }
       if (ok) {
         const float dz = alpha * (mk * dot_mine - dr) * dslope;
@@ -187,10 +249,8 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
     if (!valid) continue;
     if (gl == 0) p.g_s_src[j * H + h] = gsrc;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int q = gl + v * G;
-      if (q < Q) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + 4 * q) = acc[v];
-    }
+    for (int v = 0; v < NV; ++v)
+      if (live[v]) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off[v]) = acc[v];
   }
 }
 
@@ -247,17 +307,17 @@ static int launch_edge_bwd(const EdgeBwdParams& p, cudaStream_t stream) {
   return check_launch("edge_bwd_kernel");
 }
 
-struct BwdWorkspace { size_t off_drow, off_gsrc, off_gdst, off_gp, total; };
+struct BwdWorkspace { size_t off_rec, off_gsrc, off_gdst, off_gp, total; };
 
 static BwdWorkspace plan_bwd(const b200gat_layer& L, int64_t N) {
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   BwdWorkspace w;
   const size_t nh = up(size_t(N > 0 ? N : 1) * L.heads * sizeof(float));
-  w.off_drow = 0;
-  w.off_gsrc = nh;
-  w.off_gdst = 2 * nh;
-  w.off_gp = 3 * nh;
-  w.total = 3 * nh + up(size_t(N > 0 ? N : 1) * L.heads * L.c_pad * sizeof(float));
+  w.off_rec = 0;
+  w.off_gsrc = 4 * nh;
+  w.off_gdst = 5 * nh;
+  w.off_gp = 6 * nh;
+  w.total = 6 * nh + up(size_t(N > 0 ? N : 1) * L.heads * L.c_pad * sizeof(float));
   return w;
 }
 
@@ -305,7 +365,7 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255u) == 0, B200GAT_E_ALIGN,
                   "edge_bwd: workspace must be 256-byte aligned");
   char* base = static_cast<char*>(a->workspace);
-  float* drow = reinterpret_cast<float*>(base + w.off_drow);
+  float4* rowrec = reinterpret_cast<float4*>(base + w.off_rec);
   float* g_s_src = reinterpret_cast<float*>(base + w.off_gsrc);
   float* g_s_dst = reinterpret_cast<float*>(base + w.off_gdst);
   float* gp = reinterpret_cast<float*>(base + w.off_gp);
@@ -313,19 +373,21 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
 
   const int64_t cap = int64_t(sm_count()) * 8;
-  // (1) Drow (+ padded G when gout rows are not 128-bit gatherable per head)
+  // (1) Drow + row records (+ padded G when gout rows are not 128-bit gatherable per head)
   const bool direct_g = concat_like && C % 4 == 0 && a->ldgo % 4 == 0 && aligned16(a->gout);
-  DrowParams dp;
+  PrepParams dp;
   dp.N = N; dp.H = H; dp.C = C; dp.Cp = Cp; dp.concat_like = concat_like ? 1 : 0;
+  dp.vec = (direct_g && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
   dp.gout = a->gout; dp.ldgo = a->ldgo; dp.out = a->out; dp.ldo = a->ldo; dp.o_heads = a->o_heads; dp.bias = a->bias;
+  dp.s_dst = a->s_dst; dp.rowmax = a->rowmax; dp.rowsum = a->rowsum;
   dp.gscale = concat_like ? 1.f : 1.f / static_cast<float>(H);
-  dp.gp = direct_g ? nullptr : gp;
+  dp.gp = (direct_g && dp.vec) ? nullptr : gp;
   dp.ldgp = concat_like ? Dp : Cp;
-  dp.drow = drow;
+  dp.rowrec = rowrec;
   {
     const int64_t want = ceil_div(N * H, 8);
-    drow_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
-    if ((rc = check_launch("drow_kernel"))) return rc;
+    bwd_prep_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
+    if ((rc = check_launch("bwd_prep_kernel"))) return rc;
   }
   // (2) g_bias
   {
@@ -338,9 +400,8 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   EdgeBwdParams p;
   p.N = N; p.items = N * H; p.H = H; p.Cp = Cp; p.Dp = static_cast<int>(Dp); p.slope = L.negative_slope;
   p.colptr = a->graph.colptr; p.crow = a->graph.crow; p.ceid = a->graph.ceid;
-  p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.rowmax = a->rowmax; p.rowsum = a->rowsum;
-  p.drow = drow; p.mask = a->mask;
-  if (direct_g) { p.g = a->gout; p.ldg = a->ldgo; p.hs = C; }
+  p.wh = a->wh; p.s_src = a->s_src; p.rowrec = rowrec; p.mask = a->mask;
+  if (dp.gp == nullptr) { p.g = a->gout; p.ldg = a->ldgo; p.hs = C; }
   else if (concat_like) { p.g = gp; p.ldg = Dp; p.hs = Cp; }
   else { p.g = gp; p.ldg = Cp; p.hs = 0; }
   p.gwh = a->g_t; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;

@@ -38,6 +38,11 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
+  const float slope = p.slope;
+  // lanes beyond the head width gather a clamped (valid) column and are never stored
+  int off[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) off[v] = 4 * ((gl + v * G < Q) ? gl + v * G : Q - 1);
 
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
     const int64_t item = base + gi;
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
       const int k = beg + k0;
       if (k < end) {
         const int j = __ldg(p.col + k);
-        m = fmaxf(m, leaky(sd + __ldg(ssrc_h + int64_t(j) * H), p.slope));
+        m = fmaxf(m, leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope));
       }
     }
     m = group_max<G>(m);
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     float l = 0.f;
-    const float* whh = p.wh + h * Cp + 4 * gl;
+    const float* whh = p.wh + h * Cp;
     for (int k0 = 0; k0 < maxdeg; k0 += G) {
       const int k = beg + k0 + gl;
       const bool ok = k < end;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
       float pp = 0.f, pm = 0.f;
       if (ok) {
         j = __ldg(p.col + k);
-        pp = expf(leaky(sd + __ldg(ssrc_h + int64_t(j) * H), p.slope) - m);
+        pp = expf(leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope) - m);
         pm = pp;
         if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
       }
@@ -99,8 +104,11 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
           const float* src = whh + int64_t(jt[u]) * Dp;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            // dropped / padded / underflowed edges contribute nothing: predicate the gather off
-            w[u][v] = (pt[u] != 0.f && gl + v * G < Q) ? ldg4(src + 4 * v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6) contribute nothing: skip the gather
+              w[u][v] = pt[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {          // no predicate, no branch: padded slots gather the row's own (valid) Wh and weigh it by 0
+              w[u][v] = ldg4(src + off[v]);
+            }
           }
         }
 #pragma unroll
