@@ -10,8 +10,8 @@
 // warp, items = row-major (i, h) so groups of one warp share the row's col[] lines.  Inside an item the G lanes
 // first run EDGE-parallel (coalesced col[] load, 4-byte s_src gather, one exp per (edge, head)), then
 // FEATURE-parallel: the (j, p) pair of each edge is broadcast by width-G shuffles and every lane gathers its
-// 128-bit slices of Wh[j,h,:] (ld.global.nc.v4.f32) into NV float4 accumulators.  Rows are walked twice
-// (max, then exp/aggregate) — the second walk hits L1/L2 — so there is no running-max rescale.
+// 128-bit slices of Wh[j,h,:] (ld.global.nc.v4.f32) into NV float4 accumulators.  The softmax is online per chunk of
+// G edges (running max / sum; only rows longer than G ever rescale), so every row is walked exactly once.
 #include "common.cuh"
 #include <math.h>
 
@@ -56,31 +56,36 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
     const float sd = valid ? __ldg(p.s_dst + i * H + h) : 0.f;
     const float* ssrc_h = p.s_src + h;
 
-    // ---- walk 1: row maximum of the LeakyReLU logits (edge-parallel) ----
-    float m = -INFINITY;
-    for (int k0 = gl; k0 < maxdeg; k0 += G) {
-      const int k = beg + k0;
-      if (k < end) {
-        const int j = __ldg(p.col + k);
-        m = fmaxf(m, leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope));
-      }
-    }
-    m = group_max<G>(m);
-
-    // ---- walk 2: exp, row sum, weighted aggregation ----
+    // ---- one walk over the row, G edges per chunk: chunk max -> online rescale (only rows longer than G ever
+    //      rescale) -> exp, row sum, weighted aggregation.  A separate max pass would add two dependent memory
+    //      round trips (col -> s_src) per item before the first gather can issue. ----
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float l = 0.f;
+    float m = -INFINITY, l = 0.f;
     const float* whh = p.wh + h * Cp;
     for (int k0 = 0; k0 < maxdeg; k0 += G) {
       const int k = beg + k0 + gl;
       const bool ok = k < end;
       int j = static_cast<int>(i);
-      float pp = 0.f, pm = 0.f;
+      float e = -INFINITY;
       if (ok) {
         j = __ldg(p.col + k);
-        pp = expf(leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope) - m);
+        e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
+      }
+      const float m_new = fmaxf(m, group_max<G>(e));
+      if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
+        const float scale = expf(m - m_new);
+        l *= scale;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale;
+        }
+      }
+      m = m_new;
+      float pp = 0.f, pm = 0.f;
+      if (ok) {
+        pp = expf(e - m);
         pm = pp;
         if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
       }

@@ -378,7 +378,7 @@ split_transpose_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, 
                        float* __restrict__ lo, int64_t ldp) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t r0 = int64_t(blockIdx.y) * 32, c0 = int64_t(blockIdx.x) * 32;
+  const int64_t r0 = int64_t(blockIdx.x) * 32, c0 = int64_t(blockIdx.y) * 32;   // x: the long (node) dimension
   for (int u = ty; u < 32; u += 8) {
     const int64_t r = r0 + u, c = c0 + tx;
     tile[u][tx] = (r < rows && c < cols) ? __ldg(src + r * ld + c) : 0.f;
@@ -458,7 +458,7 @@ static int launch_split(const float* src, int64_t ld, int64_t rows, int64_t cols
 
 static int launch_split_transpose(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo,
                                   int64_t ldp, cudaStream_t stream) {
-  dim3 grid(static_cast<unsigned>(ceil_div(cols, 32)), static_cast<unsigned>(ceil_div(ldp, 32)));
+  dim3 grid(static_cast<unsigned>(ceil_div(ldp, 32)), static_cast<unsigned>(ceil_div(cols, 32)));
   split_transpose_kernel<<<grid, 256, 0, stream>>>(src, ld, rows, cols, hi, lo, ldp);
   return check_launch("split_transpose_kernel");
 }
