@@ -107,7 +107,26 @@ template <int G, int U>
 __device__ __forceinline__ float reduce_deliver(float (&d)[U], int lane, int rel) {
   constexpr unsigned FULL = 0xffffffffu;
   float got = 0.f;
-  if (G == 32 && U == 4) {
+  if (G == 32 && U == 8) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float k4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                  // bit4 = 0 keeps edges 0..3, bit4 = 1 keeps edges 4..7
+      const float r = __shfl_xor_sync(FULL, b4 ? d[u] : d[u + 4], 16);
+      k4[u] = (b4 ? d[u + 4] : d[u]) + r;
+    }
+    float k2[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {                  // bit3 picks the pair
+      const float r = __shfl_xor_sync(FULL, b3 ? k4[u] : k4[u + 2], 8);
+      k2[u] = (b3 ? k4[u + 2] : k4[u]) + r;
+    }
+    const float r = __shfl_xor_sync(FULL, b2 ? k2[0] : k2[1], 4);
+    float k = (b2 ? k2[1] : k2[0]) + r;            // this lane now owns edge 4*bit4 + 2*bit3 + bit2
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    got = __shfl_sync(FULL, k, ((rel >> 2) & 1) * 16 + ((rel >> 1) & 1) * 8 + (rel & 1) * 4);
+  } else if (G == 32 && U == 4) {
     const bool b4 = lane & 16, b3 = lane & 8;
     const float r0 = __shfl_xor_sync(FULL, b4 ? d[0] : d[2], 16);
     const float r1 = __shfl_xor_sync(FULL, b4 ? d[1] : d[3], 16);
@@ -145,7 +164,11 @@ template <int G, int NV, bool HAS_MASK>
 __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
-  constexpr int U = NV == 1 ? 4 : 2;   // edges gathered per step (memory-level parallelism vs registers)
+  // edges gathered per step: bytes in flight decide the streaming-regime throughput (measured: 4 -> 8 gathers in
+  // flight per lane took the large-graph forward from 2.9 to 3.7 TB/s); registers bound it for wide heads
+  // (backward: 8 per step measured SLOWER than 4 on the large graph, 44.7 vs 41.0 ms — the dependent rowrec gather
+  //  and the longer transposing reduce outweigh the extra loads in flight)
+  constexpr int U = NV <= 2 ? 4 : 2;
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
       const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
       // U edges per step: all U*NV 128-bit gathers are issued before the first FMA consumes one (memory-level
       // parallelism; a per-edge branch here serialises load -> FMA -> next load and leaves the kernel latency-bound)
-      constexpr int U = NV >= 4 ? 2 : 4;
+      constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
       for (int t = 0; t < cnt; t += U) {
         int jt[U];
         float pt[U];
