@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -56,6 +56,30 @@ class EdgeBwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class EdgeBwdPrepArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("num_rows", C.c_int64),
+                ("gout", C.c_void_p), ("ldgo", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("o_heads", C.c_void_p), ("bias", C.c_void_p),
+                ("s_dst", C.c_void_p), ("rowmax", C.c_void_p), ("rowsum", C.c_void_p),
+                ("rowrec", C.c_void_p), ("g_pad", C.c_void_p), ("g_bias", C.c_void_p)]
+
+
+class EdgeBwdCscArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("num_rows", C.c_int64),
+                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p),
+                ("wh", C.c_void_p), ("s_src", C.c_void_p), ("rowrec", C.c_void_p), ("mask", C.c_void_p),
+                ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
+                ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p)]
+
+
+class EdgeBwdFinishArgs(C.Structure):
+    _fields_ = [("layer", Layer), ("num_rows", C.c_int64),
+                ("wh", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
+                ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("g_t", C.c_void_p),
+                ("g_bw", C.c_void_p), ("g_a1", C.c_void_p), ("g_a2", C.c_void_p),
+                ("g_b1", C.c_void_p), ("g_b2", C.c_void_p)]
+
+
 class ProjBwdArgs(C.Structure):
     _fields_ = [("layer", Layer), ("num_nodes", C.c_int64),
                 ("g_t", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p),
@@ -75,6 +99,9 @@ _SIGNATURES = {
     "b200gat_edge_fwd": (C.c_int, [C.POINTER(EdgeFwdArgs), C.c_void_p]),
     "b200gat_edge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_edge_bwd": (C.c_int, [C.POINTER(EdgeBwdArgs), C.c_void_p]),
+    "b200gat_edge_bwd_prep": (C.c_int, [C.POINTER(EdgeBwdPrepArgs), C.c_void_p]),
+    "b200gat_edge_bwd_csc": (C.c_int, [C.POINTER(EdgeBwdCscArgs), C.c_void_p]),
+    "b200gat_edge_bwd_finish": (C.c_int, [C.POINTER(EdgeBwdFinishArgs), C.c_void_p]),
     "b200gat_proj_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_bwd": (C.c_int, [C.POINTER(ProjBwdArgs), C.c_void_p]),
 }

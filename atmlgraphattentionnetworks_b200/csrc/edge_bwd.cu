@@ -344,6 +344,99 @@ static BwdWorkspace plan_bwd(const b200gat_layer& L, int64_t N) {
   return w;
 }
 
+// ---- the three stages, shared by the single-GPU composite and the staged (row-partitioned) entry points -------------
+struct Geom { int H, C, Cp; int64_t Dp, d_out; bool concat_like; };
+static Geom geom_of(const b200gat_layer& L) {
+  Geom g;
+  g.H = static_cast<int>(L.heads); g.C = static_cast<int>(L.out_channels); g.Cp = static_cast<int>(L.c_pad);
+  g.Dp = int64_t(g.H) * g.Cp; g.concat_like = L.concat || g.H == 1; g.d_out = L.concat ? int64_t(g.H) * g.C : g.C;
+  return g;
+}
+
+// can the CSC pass gather the upstream gradient rows directly (no padded / scaled copy)?
+static bool gout_direct(const Geom& g, const float* gout, int64_t ldgo) {
+  return g.concat_like && g.C % 4 == 0 && ldgo % 4 == 0 && aligned16(gout);
+}
+
+// stage 1: row records + Drow (+ padded G copy when gp != nullptr) + g_bias column sums, over `rows` rows
+static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int64_t ldgo, const float* out, int64_t ldo,
+                    const float* o_heads, const float* bias, const float* s_dst, const float* rowmax, const float* rowsum,
+                    float4* rowrec, float* gp, float* g_bias, cudaStream_t stream) {
+  const Geom g = geom_of(L);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  PrepParams dp;
+  dp.N = rows; dp.H = g.H; dp.C = g.C; dp.Cp = g.Cp; dp.concat_like = g.concat_like ? 1 : 0;
+  dp.vec = (gp == nullptr && ldo % 4 == 0 && aligned16(out) && aligned16(bias)) ? 1 : 0;
+  B200GAT_REQUIRE(gp != nullptr || (gout_direct(g, gout, ldgo) && dp.vec), B200GAT_E_ALIGN,
+                  "edge_bwd: the upstream gradient is not directly gatherable: a padded copy buffer is required");
+  dp.gout = gout; dp.ldgo = ldgo; dp.out = out; dp.ldo = ldo; dp.o_heads = o_heads; dp.bias = bias;
+  dp.s_dst = s_dst; dp.rowmax = rowmax; dp.rowsum = rowsum;
+  dp.gscale = g.concat_like ? 1.f : 1.f / static_cast<float>(g.H);
+  dp.gp = gp;
+  dp.ldgp = g.concat_like ? g.Dp : g.Cp;
+  dp.rowrec = rowrec;
+  const int64_t want = ceil_div(rows * g.H, 8);
+  bwd_prep_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
+  int rc = check_launch("bwd_prep_kernel");
+  if (rc) return rc;
+  cudaError_t ce = cudaMemsetAsync(g_bias, 0, g.d_out * sizeof(float), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+  const int64_t ysplit = ceil_div(rows, 8) < 64 ? ceil_div(rows, 8) : 64;
+  dim3 grid(static_cast<unsigned>(ceil_div(g.d_out, 32)), static_cast<unsigned>(ysplit));
+  colsum_kernel<<<grid, 256, 0, stream>>>(gout, ldgo, rows, static_cast<int>(g.d_out), g_bias);
+  return check_launch("colsum_kernel");
+}
+
+// stage 2: the CSC pass over `rows` source rows.  wh / s_src / gwh / g_s_src are indexed by the LOCAL source row;
+// crow holds GLOBAL destination ids indexing rowrec / g / g_s_dst (identical spaces on a single GPU).
+static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, const int32_t* crow, const int32_t* ceid,
+                   const float* wh, const float* s_src, const float4* rowrec, const float* mask, const float* gsrc_rows,
+                   int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, cudaStream_t stream) {
+  const Geom g = geom_of(L);
+  EdgeBwdParams p;
+  p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope;
+  p.colptr = colptr; p.crow = crow; p.ceid = ceid;
+  p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.mask = mask;
+  p.g = gsrc_rows; p.ldg = ldg; p.hs = hs;
+  p.gwh = gwh; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
+  const int Q = g.Cp / 4;
+  if (Q <= 1) return launch_edge_bwd<1, 1>(p, stream);
+  if (Q <= 2) return launch_edge_bwd<2, 1>(p, stream);
+  if (Q <= 4) return launch_edge_bwd<4, 1>(p, stream);
+  if (Q <= 8) return launch_edge_bwd<8, 1>(p, stream);
+  if (Q <= 16) return launch_edge_bwd<16, 1>(p, stream);
+  if (Q <= 32) return launch_edge_bwd<32, 1>(p, stream);
+  if (Q <= 64) return launch_edge_bwd<32, 2>(p, stream);
+  return launch_edge_bwd<32, 4>(p, stream);
+}
+
+// stage 3: gT in place + parameter column sums over `rows` rows (outputs are overwritten, not accumulated)
+static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, const float* a1, const float* a2,
+                      const float* g_s_src, const float* g_s_dst, float* g_t, float* g_bw, float* g_a1, float* g_a2,
+                      float* g_b1, float* g_b2, cudaStream_t stream) {
+  const Geom g = geom_of(L);
+  cudaError_t ce = cudaMemsetAsync(g_bw, 0, g.Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(g_a1, 0, g.Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(g_a2, 0, g.Dp * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(g_b1, 0, g.H * sizeof(float), stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(g_b2, 0, g.H * sizeof(float), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+  if (rows == 0) return 0;
+  FinishParams f;
+  f.N = rows; f.H = g.H; f.Cp = g.Cp; f.Dp = static_cast<int>(g.Dp);
+  f.wh = wh; f.a1 = a1; f.a2 = a2; f.g_s_src = g_s_src; f.g_s_dst = g_s_dst; f.g_t = g_t;
+  f.g_bw = g_bw; f.g_a1 = g_a1; f.g_a2 = g_a2; f.g_b1 = g_b1; f.g_b2 = g_b2;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int xblocks = static_cast<int>(ceil_div(g.Dp, 256));
+  int64_t ysplit = ceil_div(cap, xblocks);
+  const int64_t max_y = ceil_div(rows, 16);
+  if (ysplit > max_y) ysplit = max_y;
+  if (ysplit < 1) ysplit = 1;
+  dim3 grid(xblocks, static_cast<unsigned>(ysplit));
+  bwd_finish_kernel<<<grid, 256, 0, stream>>>(f);
+  return check_launch("bwd_finish_kernel");
+}
+
 }  // namespace b200gat
 
 using namespace b200gat;
@@ -361,26 +454,20 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   if ((rc = validate_graph(a->graph))) return rc;
   const b200gat_layer& L = a->layer;
   const int64_t N = a->graph.num_nodes;
-  const int H = static_cast<int>(L.heads), C = static_cast<int>(L.out_channels), Cp = static_cast<int>(L.c_pad);
-  const int64_t Dp = int64_t(H) * Cp;
-  const bool concat_like = L.concat || H == 1;
-  const int64_t d_out = L.concat ? int64_t(H) * C : C;
+  const Geom g = geom_of(L);
   B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2 && a->g_bias, B200GAT_E_NULL,
                   "edge_bwd: NULL parameter-gradient pointer");
-  cudaError_t ce = cudaMemsetAsync(a->g_bw, 0, Dp * sizeof(float), stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_a1, 0, Dp * sizeof(float), stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_a2, 0, Dp * sizeof(float), stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_b1, 0, H * sizeof(float), stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_b2, 0, H * sizeof(float), stream);
-  if (ce == cudaSuccess) ce = cudaMemsetAsync(a->g_bias, 0, d_out * sizeof(float), stream);
-  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
-  if (N == 0) return 0;
+  if (N == 0) {
+    cudaError_t ce = cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+    return run_finish(L, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2, stream);
+  }
   B200GAT_REQUIRE(a->gout && a->wh && a->s_src && a->s_dst && a->rowmax && a->rowsum && a->a1 && a->a2 && a->g_t &&
                   a->bias && a->workspace, B200GAT_E_NULL, "edge_bwd: NULL pointer");
-  B200GAT_REQUIRE(concat_like ? (a->out != nullptr) : (a->o_heads != nullptr), B200GAT_E_NULL,
+  B200GAT_REQUIRE(g.concat_like ? (a->out != nullptr) : (a->o_heads != nullptr), B200GAT_E_NULL,
                   "edge_bwd: forward output (out / o_heads) missing");
   B200GAT_REQUIRE(!a->mask || a->graph.ceid, B200GAT_E_NULL, "edge_bwd: mask needs graph.ceid");
-  B200GAT_REQUIRE(a->ldgo >= d_out && (!concat_like || a->ldo >= d_out), B200GAT_E_SHAPE, "edge_bwd: leading dimension < D_out");
+  B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd: leading dimension < D_out");
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t), B200GAT_E_ALIGN, "edge_bwd: wh / g_t must be 16-byte aligned");
   const BwdWorkspace w = plan_bwd(L, N);
   B200GAT_REQUIRE(a->workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "edge_bwd: workspace %zu < %zu bytes",
@@ -392,66 +479,71 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   float* g_s_src = reinterpret_cast<float*>(base + w.off_gsrc);
   float* g_s_dst = reinterpret_cast<float*>(base + w.off_gdst);
   float* gp = reinterpret_cast<float*>(base + w.off_gp);
-  ce = cudaMemsetAsync(g_s_dst, 0, size_t(N) * H * sizeof(float), stream);
+  cudaError_t ce = cudaMemsetAsync(g_s_dst, 0, size_t(N) * g.H * sizeof(float), stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+  const bool direct = gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
+                      aligned16(a->bias);
+  if ((rc = run_prep(L, N, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum, rowrec,
+                     direct ? nullptr : gp, a->g_bias, stream)))
+    return rc;
+  const float* grows = direct ? a->gout : gp;
+  const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
+  const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
+  if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
+                    a->g_t, g_s_src, g_s_dst, stream)))
+    return rc;
+  return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2, stream);
+}
 
-  const int64_t cap = int64_t(sm_count()) * 8;
-  // (1) Drow + row records (+ padded G when gout rows are not 128-bit gatherable per head)
-  const bool direct_g = concat_like && C % 4 == 0 && a->ldgo % 4 == 0 && aligned16(a->gout);
-  PrepParams dp;
-  dp.N = N; dp.H = H; dp.C = C; dp.Cp = Cp; dp.concat_like = concat_like ? 1 : 0;
-  dp.vec = (direct_g && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
-  dp.gout = a->gout; dp.ldgo = a->ldgo; dp.out = a->out; dp.ldo = a->ldo; dp.o_heads = a->o_heads; dp.bias = a->bias;
-  dp.s_dst = a->s_dst; dp.rowmax = a->rowmax; dp.rowsum = a->rowsum;
-  dp.gscale = concat_like ? 1.f : 1.f / static_cast<float>(H);
-  dp.gp = (direct_g && dp.vec) ? nullptr : gp;
-  dp.ldgp = concat_like ? Dp : Cp;
-  dp.rowrec = rowrec;
-  {
-    const int64_t want = ceil_div(N * H, 8);
-    bwd_prep_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
-    if ((rc = check_launch("bwd_prep_kernel"))) return rc;
-  }
-  // (2) g_bias
-  {
-    const int64_t ysplit = ceil_div(N, 8) < 64 ? ceil_div(N, 8) : 64;
-    dim3 grid(static_cast<unsigned>(ceil_div(d_out, 32)), static_cast<unsigned>(ysplit));
-    colsum_kernel<<<grid, 256, 0, stream>>>(a->gout, a->ldgo, N, static_cast<int>(d_out), a->g_bias);
-    if ((rc = check_launch("colsum_kernel"))) return rc;
-  }
-  // (3) CSC pass
-  EdgeBwdParams p;
-  p.N = N; p.items = N * H; p.H = H; p.Cp = Cp; p.Dp = static_cast<int>(Dp); p.slope = L.negative_slope;
-  p.colptr = a->graph.colptr; p.crow = a->graph.crow; p.ceid = a->graph.ceid;
-  p.wh = a->wh; p.s_src = a->s_src; p.rowrec = rowrec; p.mask = a->mask;
-  if (dp.gp == nullptr) { p.g = a->gout; p.ldg = a->ldgo; p.hs = C; }
-  else if (concat_like) { p.g = gp; p.ldg = Dp; p.hs = Cp; }
-  else { p.g = gp; p.ldg = Cp; p.hs = 0; }
-  p.gwh = a->g_t; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
-  const int Q = Cp / 4;
-  if (Q <= 1) rc = launch_edge_bwd<1, 1>(p, stream);
-  else if (Q <= 2) rc = launch_edge_bwd<2, 1>(p, stream);
-  else if (Q <= 4) rc = launch_edge_bwd<4, 1>(p, stream);
-  else if (Q <= 8) rc = launch_edge_bwd<8, 1>(p, stream);
-  else if (Q <= 16) rc = launch_edge_bwd<16, 1>(p, stream);
-  else if (Q <= 32) rc = launch_edge_bwd<32, 1>(p, stream);
-  else if (Q <= 64) rc = launch_edge_bwd<32, 2>(p, stream);
-  else rc = launch_edge_bwd<32, 4>(p, stream);
+// ---- staged entry points (destination-row partitioned multi-GPU execution: the caller runs the collectives between
+//      the stages; see include/b200gat.h) ------------------------------------------------------------------------------
+extern "C" int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "edge_bwd_prep: NULL args");
+  int rc = validate_layer(a->layer);
   if (rc) return rc;
-  // (4) gT + parameter column sums
-  FinishParams f;
-  f.N = N; f.H = H; f.Cp = Cp; f.Dp = static_cast<int>(Dp);
-  f.wh = a->wh; f.a1 = a->a1; f.a2 = a->a2; f.g_s_src = g_s_src; f.g_s_dst = g_s_dst; f.g_t = a->g_t;
-  f.g_bw = a->g_bw; f.g_a1 = a->g_a1; f.g_a2 = a->g_a2; f.g_b1 = a->g_b1; f.g_b2 = a->g_b2;
-  {
-    const int xblocks = static_cast<int>(ceil_div(Dp, 256));
-    int64_t ysplit = ceil_div(cap, xblocks);
-    const int64_t max_y = ceil_div(N, 16);
-    if (ysplit > max_y) ysplit = max_y;
-    if (ysplit < 1) ysplit = 1;
-    dim3 grid(xblocks, static_cast<unsigned>(ysplit));
-    bwd_finish_kernel<<<grid, 256, 0, stream>>>(f);
-    rc = check_launch("bwd_finish_kernel");
+  const Geom g = geom_of(a->layer);
+  B200GAT_REQUIRE(a->num_rows >= 0, B200GAT_E_SHAPE, "edge_bwd_prep: negative num_rows");
+  B200GAT_REQUIRE(a->g_bias, B200GAT_E_NULL, "edge_bwd_prep: NULL g_bias");
+  if (a->num_rows == 0) {
+    cudaError_t ce = cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream);
+    return ce == cudaSuccess ? 0 : fail(static_cast<int>(ce), "edge_bwd_prep: memset: %s", cudaGetErrorString(ce));
   }
-  return rc;
+  B200GAT_REQUIRE(a->gout && a->bias && a->s_dst && a->rowmax && a->rowsum && a->rowrec, B200GAT_E_NULL, "edge_bwd_prep: NULL pointer");
+  B200GAT_REQUIRE(g.concat_like ? (a->out != nullptr) : (a->o_heads != nullptr), B200GAT_E_NULL,
+                  "edge_bwd_prep: forward output (out / o_heads) missing");
+  B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd_prep: leading dimension < D_out");
+  B200GAT_REQUIRE(aligned16(a->rowrec), B200GAT_E_ALIGN, "edge_bwd_prep: rowrec must be 16-byte aligned");
+  return run_prep(a->layer, a->num_rows, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum,
+                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, stream);
+}
+
+extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "edge_bwd_csc: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  B200GAT_REQUIRE(a->num_rows >= 0, B200GAT_E_SHAPE, "edge_bwd_csc: negative num_rows");
+  if (a->num_rows == 0) return 0;
+  B200GAT_REQUIRE(a->colptr && a->crow && a->wh && a->s_src && a->rowrec && a->g && a->g_wh && a->g_s_src && a->g_s_dst,
+                  B200GAT_E_NULL, "edge_bwd_csc: NULL pointer");
+  B200GAT_REQUIRE(!a->mask || a->ceid, B200GAT_E_NULL, "edge_bwd_csc: mask needs ceid");
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_wh) && aligned16(a->g) && aligned16(a->rowrec) && a->ldg % 4 == 0 &&
+                  a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
+  return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
+                 reinterpret_cast<const float4*>(a->rowrec), a->mask, a->g, a->ldg, static_cast<int>(a->g_head_stride),
+                 a->g_wh, a->g_s_src, a->g_s_dst, stream);
+}
+
+extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(a, B200GAT_E_NULL, "edge_bwd_finish: NULL args");
+  int rc = validate_layer(a->layer);
+  if (rc) return rc;
+  B200GAT_REQUIRE(a->num_rows >= 0, B200GAT_E_SHAPE, "edge_bwd_finish: negative num_rows");
+  B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2, B200GAT_E_NULL, "edge_bwd_finish: NULL output");
+  B200GAT_REQUIRE(a->num_rows == 0 || (a->wh && a->a1 && a->a2 && a->g_s_src && a->g_s_dst && a->g_t), B200GAT_E_NULL,
+                  "edge_bwd_finish: NULL pointer");
+  return run_finish(a->layer, a->num_rows, a->wh, a->a1, a->a2, a->g_s_src, a->g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2,
+                    a->g_b1, a->g_b2, stream);
 }

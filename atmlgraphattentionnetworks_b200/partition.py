@@ -1,0 +1,297 @@
+"""Destination-row partitioned execution of ONE large graph over P GPUs (BASELINE config 5).
+
+Rank r owns the contiguous node block [r*B, min((r+1)*B, N)), B = ceil(N/P):
+  forward  per layer : project own rows -> ALL-GATHER Wh (+ s_src) -> fused edge forward over the local CSR
+                       (destinations = own block, sources = global ids into the gathered Wh)
+  backward per layer : row records / Drow of own rows -> ALL-GATHER the gatherable gradient rows (+ the 16-byte row
+                       records) -> CSC pass over own SOURCE rows (complete gWh / g_s_src for owned rows, no
+                       reduce-scatter of the big [N, D] tensor) -> REDUCE-SCATTER g_s_dst [N, H] -> finish + projection
+                       backward on own rows; parameter gradients are partial sums (all-reduced by the caller).
+With random power-law edges the halo of a block is ~all nodes, so a full all-gather (not a sparse halo exchange) is the
+right primitive.  The per-rank stages are the same C-ABI kernels as the single-GPU layer (staged entry points
+b200gat_edge_bwd_prep / _csc / _finish); the collectives are torch.distributed (NCCL over NVLink / NVSwitch).
+
+Graph partitioning is a one-off setup step of a static graph and is written with torch ops (usable on CPU tensors, which
+is how tests/test_partition_cpu.py checks it against the CSR oracle).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _abi
+from .gat import _call, _layer_struct, _ptr, _workspace
+
+
+# ------------------------------------------------------------------------------------------------ graph partition
+class RowPartition:
+    __slots__ = ("num_nodes", "world", "rank", "block", "lo", "hi", "rowptr", "col", "eid", "colptr", "crow", "ceid",
+                 "_struct")
+
+    @property
+    def n_own(self):
+        return self.hi - self.lo
+
+    @property
+    def padded_rows(self):
+        return self.block * self.world
+
+    def c_struct(self):
+        return self._struct
+
+
+def block_size(num_nodes, world):
+    return (num_nodes + world - 1) // world
+
+
+def build_row_partition(edge_index, num_nodes, world, rank):
+    """Local CSR (edges whose DESTINATION is in the block; rows re-based to the block, sources global) and local CSC
+    (edges whose SOURCE is in the block; columns re-based, destinations global) of [edge_index ; self loops].
+    Order inside a row / column = the single-GPU canonical order (stable sort of the original edge list)."""
+    dev = edge_index.device
+    n, e = int(num_nodes), int(edge_index.shape[1])
+    b = block_size(n, world)
+    lo, hi = min(rank * b, n), min((rank + 1) * b, n)
+    loops = torch.arange(n, dtype=torch.int64, device=dev)
+    src = torch.cat([edge_index[0], loops])
+    dst = torch.cat([edge_index[1], loops])
+    pos = torch.arange(e + n, dtype=torch.int64, device=dev)
+
+    def build(keys_own, other, ids):
+        order = torch.sort(keys_own, stable=True).indices
+        counts = torch.bincount(keys_own, minlength=hi - lo)
+        ptr = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=ptr[1:])
+        return ptr.to(torch.int32), other[order].to(torch.int32).contiguous(), ids[order].to(torch.int32).contiguous()
+
+    in_dst = (dst >= lo) & (dst < hi)
+    rowptr, col, eid = build(dst[in_dst] - lo, src[in_dst], pos[in_dst])
+    # CSC must be stable w.r.t. the CSR order (destination-major), as in the single-GPU build
+    in_src = (src >= lo) & (src < hi)
+    s_src, s_dst, s_pos = src[in_src], dst[in_src], pos[in_src]
+    by_dst = torch.sort(s_dst, stable=True).indices
+    s_src, s_dst, s_pos = s_src[by_dst], s_dst[by_dst], s_pos[by_dst]
+    colptr, crow, ceid = build(s_src - lo, s_dst, s_pos)
+
+    p = RowPartition()
+    p.num_nodes, p.world, p.rank, p.block, p.lo, p.hi = n, world, rank, b, lo, hi
+    p.rowptr, p.col, p.eid, p.colptr, p.crow, p.ceid = rowptr, col, eid, colptr, crow, ceid
+    p._struct = None
+    if rowptr.is_cuda:
+        p._struct = _abi.Graph(hi - lo, int(col.numel()), rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
+                               colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr())
+    return p
+
+
+# ------------------------------------------------------------------------------------------------ per-rank stages
+def _geom(geom):
+    f_in, c, h, concat = geom
+    layer = _layer_struct(f_in, c, h, concat)
+    cp = layer.c_pad
+    return layer, f_in, c, h, concat, cp, h * cp, (h * c if concat else c), ((not concat) and h > 1)
+
+
+def stage_proj(geom, params, x_own, block):
+    """-> wh [block, Dp] (rows >= n_own zero), s_src [block, H], s_dst [n_own, H]   (GAT.py:42-52 on own rows)"""
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    w, bw, a1, a2, b1, b2 = params
+    dev, n = x_own.device, x_own.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    wh = torch.zeros((block, dp), **f32)
+    s_src = torch.zeros((block, h), **f32)
+    s_dst = torch.empty((n, h), **f32)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
+    ws = _workspace(ws_bytes, dev)
+    pa = _abi.ProjFwdArgs(layer, n, x_own.data_ptr(), x_own.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
+                          a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(), s_src.data_ptr(),
+                          s_dst.data_ptr(), ws.data_ptr(), ws_bytes)
+    _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
+    return wh, s_src, s_dst
+
+
+def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask):
+    """-> out [n_own, D_out], rowmax, rowsum [n_own, H], o_heads or None   (GAT.py:53-67 for the own destination rows)"""
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    dev, n = wh_full.device, part.n_own
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = torch.empty((n, d_out), **f32)
+    rowmax = torch.empty((n, h), **f32)
+    rowsum = torch.empty((n, h), **f32)
+    o_heads = torch.empty((n, dp), **f32) if heads_mode else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ea = _abi.EdgeFwdArgs(layer, part.c_struct(), wh_full.data_ptr(), s_src_full.data_ptr(), s_dst_own.data_ptr(),
+                          bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(), rowsum.data_ptr(),
+                          _ptr(o_heads))
+    _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
+    return out, rowmax, rowsum, o_heads
+
+
+def gather_layout(geom):
+    """Which rows the backward all-gathers: (direct, width, ldg, head_stride).  direct: gout itself is gatherable."""
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    concat_like = concat or h == 1
+    if concat_like and c % 4 == 0:
+        return True, d_out, d_out, c
+    if concat_like:
+        return False, dp, dp, cp
+    return False, cp, cp, 0
+
+
+def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, block):
+    """-> rowrec [block, H, 4], g_rows [block, width] (zero padded), g_bias partial [D_out]"""
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    dev, n = gout_own.device, gout_own.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    direct, width, _, _ = gather_layout(geom)
+    rowrec = torch.zeros((block, h, 4), **f32)
+    g_bias = torch.empty(d_out, **f32)
+    if direct:
+        if n == block:
+            g_rows = gout_own
+        else:
+            g_rows = torch.zeros((block, width), **f32)
+            g_rows[:n].copy_(gout_own)
+        g_pad = None
+    else:
+        g_rows = torch.zeros((block, width), **f32)
+        g_pad = g_rows
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    pa = _abi.EdgeBwdPrepArgs(layer, n, gout_own.data_ptr(), d_out,
+                              None if heads_mode else fwd_out_own.data_ptr(), d_out,
+                              fwd_out_own.data_ptr() if heads_mode else None, bias.data_ptr(),
+                              s_dst_own.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), rowrec.data_ptr(),
+                              _ptr(g_pad), g_bias.data_ptr())
+    _call("b200gat_edge_bwd_prep", lib.b200gat_edge_bwd_prep, pa, stream, geom)
+    return rowrec, g_rows, g_bias
+
+
+def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
+    """-> g_wh [n_own, Dp], g_s_src [n_own, H], g_s_dst_full [P*block, H] (this rank's partial sums for ALL nodes)"""
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    dev, n = wh_own.device, part.n_own
+    f32 = dict(dtype=torch.float32, device=dev)
+    _, _, ldg, hs = gather_layout(geom)
+    g_wh = torch.empty((n, dp), **f32)
+    g_s_src = torch.empty((n, h), **f32)
+    g_s_dst_full = torch.zeros((part.padded_rows, h), **f32)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ca = _abi.EdgeBwdCscArgs(layer, n, part.colptr.data_ptr(), part.crow.data_ptr(), part.ceid.data_ptr(),
+                             wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
+                             g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr())
+    _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
+    return g_wh, g_s_src, g_s_dst_full
+
+
+def stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh):
+    """g_wh -> gT in place; -> (g_bw, g_a1, g_a2 [Dp], g_b1, g_b2 [H]) partial sums of the own block"""
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    dev, n = wh_own.device, g_wh.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    g_bw, g_a1, g_a2 = (torch.empty(dp, **f32) for _ in range(3))
+    g_b1, g_b2 = (torch.empty(h, **f32) for _ in range(2))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    fa = _abi.EdgeBwdFinishArgs(layer, n, wh_own.data_ptr(), a1.data_ptr(), a2.data_ptr(), g_s_src.data_ptr(),
+                                g_s_dst_own.data_ptr(), g_wh.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(),
+                                g_a2.data_ptr(), g_b1.data_ptr(), g_b2.data_ptr())
+    _call("b200gat_edge_bwd_finish", lib.b200gat_edge_bwd_finish, fa, stream, geom)
+    return g_bw, g_a1, g_a2, g_b1, g_b2
+
+
+def stage_proj_bwd(geom, g_t, x_own, w, need_gx):
+    lib = _abi.lib()
+    layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
+    dev, n = x_own.device, x_own.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    g_w = torch.empty((dp, f_in), **f32)
+    g_x = torch.empty((n, f_in), **f32) if need_gx else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
+    ws = _workspace(ws_bytes, dev)
+    pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x_own.data_ptr(), x_own.stride(0) if n else f_in, w.data_ptr(),
+                          _ptr(g_x), f_in, g_w.data_ptr(), ws.data_ptr(), ws_bytes)
+    _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, geom)
+    return g_x, g_w
+
+
+# ------------------------------------------------------------------------------------------------ collectives
+def all_gather_rows(own_padded, group=None):
+    """[block, W] per rank -> [P*block, W]; row r*block + k of the result is global node r*block + k."""
+    world = dist.get_world_size(group)
+    full = torch.empty((world * own_padded.shape[0],) + tuple(own_padded.shape[1:]), dtype=own_padded.dtype,
+                       device=own_padded.device)
+    dist.all_gather_into_tensor(full, own_padded.contiguous(), group=group)
+    return full
+
+
+def reduce_scatter_rows(full, block, group=None):
+    """[P*block, W] partial sums per rank -> own [block, W] total."""
+    own = torch.empty((block,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+    dist.reduce_scatter_tensor(own, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return own
+
+
+class PartitionedGATFunction(torch.autograd.Function):
+    """One GAT layer on the own row block of a partitioned graph.  Returned parameter gradients are the own block's
+    partial sums: all-reduce (SUM) them over ranks (parallel.GradBucket.all_reduce_mean(weight=1.0))."""
+
+    @staticmethod
+    def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group):
+        x_own = x_own.contiguous()
+        w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
+        with torch.cuda.device(x_own.device):
+            wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block)
+            wh_full = all_gather_rows(wh_pad, group)
+            s_src_full = all_gather_rows(s_src_pad, group)
+            out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask)
+        n = part.n_own
+        ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
+        ctx.save_for_backward(x_own, w, a1, a2, bias, wh_pad[:n], s_src_pad[:n], s_dst, rowmax, rowsum,
+                              out if o_heads is None else o_heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x_own, w, a1, a2, bias, wh_own, s_src_own, s_dst, rowmax, rowsum, fwd_out = ctx.saved_tensors
+        part, geom, mask, group = ctx.part, ctx.geom, ctx.mask, ctx.group
+        gout = gout.contiguous()
+        with torch.cuda.device(gout.device):
+            rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block)
+            g_full = all_gather_rows(g_rows, group)
+            rowrec_full = all_gather_rows(rowrec, group)
+            g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask)
+            g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
+            g_bw, g_a1, g_a2, g_b1, g_b2 = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh)
+            g_x, g_w = stage_proj_bwd(geom, g_wh, x_own, w, ctx.needs_input_grad[0])
+        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None
+
+
+def partitioned_layer_forward(layer, x_own, part, group=None):
+    """Run a GraphAttentionLayer module on the own block of a row-partitioned graph (dropout masks: not yet
+    supported in partitioned mode — the reference trains the large configs with dropout disabled in the bench)."""
+    if layer.training and float(layer.dropout_val) > 0.0:
+        raise NotImplementedError("attention dropout in row-partitioned mode")
+    w, bw, a1, a2, b1, b2 = layer._packed()
+    geom = (layer.input_channels, layer.output_channels, layer.num_heads, bool(layer.concat))
+    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, None, group)
+
+
+class PartitionedGATStack(torch.nn.Module):
+    """GATStack (plain layers + ELU) executed row-partitioned: forward(x_own, part) -> out_own."""
+
+    def __init__(self, stack):
+        super().__init__()
+        self.stack = stack
+
+    def forward(self, x_own, part, group=None):
+        convs = self.stack.convs
+        for k, conv in enumerate(convs):
+            x_own = partitioned_layer_forward(conv, x_own, part, group)
+            if k + 1 < len(convs):
+                x_own = torch.nn.functional.elu(x_own)
+        return x_own

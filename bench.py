@@ -233,23 +233,41 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus} (launch with torchrun)"
 
-    # weak scaling: every rank owns its own batch of independent graphs (seed = rank); the model is replicated
-    data, spec, loss_fn, wdesc = make_workload(args.workload, seed=rank)
+    # graph batches: weak scaling — every rank owns its own batch of independent graphs (seed = rank), model replicated.
+    # one large graph (--workload large, N > 1): strong scaling — destination-row partition, Wh all-gather per layer.
+    partitioned = args.workload == "large" and world > 1
+    data, spec, loss_fn, wdesc = make_workload(args.workload, seed=0 if partitioned else rank)
     ep = layer_edges(data)
     n = data.x.shape[0]
     torch.manual_seed(0)
     model = GATStack(spec, dropout=0.0).to(dev)
     bucket = GradBucket(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True)   # run_inductive.py:18-19,65
-    x_h, ei_h, y_h = data.x.pin_memory(), data.edge_index.pin_memory(), data.y.pin_memory()
+    part = None
+    if partitioned:
+        from atmlgraphattentionnetworks_b200.partition import PartitionedGATStack, build_row_partition
+        part = build_row_partition(data.edge_index.to(dev), n, world, rank)
+        pmodel = PartitionedGATStack(model)
+        x_h, y_h = data.x[part.lo:part.hi].contiguous().pin_memory(), data.y[part.lo:part.hi].contiguous().pin_memory()
+        ei_h = torch.zeros((2, 0), dtype=torch.int64).pin_memory()      # the partitioned graph is static and resident
+        torch.cuda.empty_cache()
+    else:
+        x_h, ei_h, y_h = data.x.pin_memory(), data.edge_index.pin_memory(), data.y.pin_memory()
     x_d, ei_d, y_d = x_h.to(dev), ei_h.to(dev), y_h.to(dev)
 
     def train_step(x, ei, y):
         bucket.zero()
-        out = model(x, ei)
-        loss = loss_fn(out, y)
-        loss.backward()
-        bucket.all_reduce_mean()
+        if partitioned:
+            out = pmodel(x, part)
+            # global mean loss = sum over ranks of (own sum / N); parameter gradients are then SUMMED over ranks
+            loss = torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(out, dim=1), y, reduction="sum") / n
+            loss.backward()
+            bucket.all_reduce_mean(weight=1.0)
+        else:
+            out = model(x, ei)
+            loss = loss_fn(out, y)
+            loss.backward()
+            bucket.all_reduce_mean()
         opt.step()
         return loss
 
@@ -305,10 +323,16 @@ def main():
     for _ in range(reps):
         train_step(x_d, ei_d, y_d)
     torch.cuda.synchronize()
-    per = {}
+    per_raw = {}
     for name, geom, s, e in _abi.timing:
-        per.setdefault((name, geom), []).append(s.elapsed_time(e))
+        per_raw.setdefault((name, geom), []).append(s.elapsed_time(e))
     _abi.timing = None
+    per = {}
+    for (name, geom), ts in per_raw.items():      # staged backward (partitioned mode): prep + csc + finish = edge_bwd
+        key = ("b200gat_edge_bwd" if name.startswith("b200gat_edge_bwd") else name, geom)
+        per[key] = [a + b for a, b in zip(per[key], ts)] if key in per else list(ts)
+    n_loc = part.n_own if partitioned else n
+    ep_loc = int(part.col.numel() + part.crow.numel()) // 2 if partitioned else ep
     peaks = measured_peaks()
     kernels = []
     for li, (f, c, h, concat) in enumerate(spec):
@@ -318,10 +342,10 @@ def main():
                 continue
             ms = statistics.median(ts)
             need_gx = li > 0
-            nbytes, bound = algorithmic_bytes(op, n, ep, f, c, h, concat, need_gx, cached=args.workload != "large")
+            nbytes, bound = algorithmic_bytes(op, n_loc, ep_loc, f, c, h, concat, need_gx, cached=args.workload != "large")
             rec = {"op": op, "layer": li, "geom": f"{f}->{h}x{c}{'cat' if concat else 'mean'}", "ms": ms,
                    "alg_bytes": nbytes, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / peaks["hbm"]}
-            fl = gemm_flops(op, n, f, c, h, need_gx)
+            fl = gemm_flops(op, n_loc, f, c, h, need_gx)
             if fl:
                 rec["TFLOPs"] = fl / ms / 1e9
             kernels.append(rec)
@@ -338,10 +362,10 @@ def main():
                          "peak_source": peaks["source"] + " (of measured)"})
     edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
     edge_bytes = sum(r["alg_bytes"] for r in kernels if r["op"].startswith("b200gat_edge"))
-    edge_phase = {"ms": edge_ms, "alg_bytes": edge_bytes, "GBps": edge_bytes / edge_ms / 1e6 if edge_ms else None,
+    edge_phase = {"per_rank": partitioned, "ms": edge_ms, "alg_bytes": edge_bytes, "GBps": edge_bytes / edge_ms / 1e6 if edge_ms else None,
                   "frac_of_measured_hbm": edge_bytes / edge_ms / 1e6 / peaks["hbm"] if edge_ms else None,
                   "frac_of_nominal_8TBps": edge_bytes / edge_ms / 1e6 / 8000.0 if edge_ms else None,
-                  "edges_per_s": len(spec) * ep / (edge_ms / 1e3) if edge_ms else None}
+                  "edges_per_s": len(spec) * ep_loc / (edge_ms / 1e3) if edge_ms else None}
 
     if rank != 0:
         if world > 1:
@@ -353,12 +377,14 @@ def main():
         val, dt, desc = cpu_reference_leg(args.workload, 3, 1, args.cpu_sample_graphs if args.workload != "large" else 1)
         cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc,
                "s_per_step": dt}
-    total_edges = len(spec) * ep * world
+    total_edges = len(spec) * ep * (1 if partitioned else world)
     line = {
         "metric": METRIC, "value": total_edges / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wdesc, "parallelism": f"dp{world} (independent graph batches per rank, flat NCCL grad all-reduce)",
+        "config": {"workload": wdesc,
+                   "parallelism": (f"row{world} (destination-row partition, NCCL all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
+                                   if partitioned else f"dp{world} (independent graph batches per rank, flat NCCL grad all-reduce)"),
                    "edges_per_layer_incl_self_loops": ep, "input_edges": int(data.edge_index.shape[1]), "nodes": n,
                    "layers": len(spec), "step": "zero_grad + fwd + BCE loss + bwd + grad all-reduce + fused Adam",
                    "l2": "inputs larger than L2 (per-step working set ~2 GB vs 126 MB L2); no explicit flush"},

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 3
+#define B200GAT_ABI_VERSION 4
 
 enum {
   B200GAT_OK = 0,
@@ -130,6 +130,53 @@ typedef struct {
 } b200gat_edge_bwd_args;
 size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream);
+
+/* ---- K3 staged: the three passes of b200gat_edge_bwd as separate calls, for destination-row partitioned multi-GPU
+ * execution of ONE large graph (the caller all-gathers `rowrec` and the gatherable gradient rows between prep and
+ * csc, and all-reduces g_s_dst between csc and finish).  Row counts are the caller's OWN block; `crow` holds GLOBAL
+ * destination ids indexing rowrec / g / g_s_dst. ------------------------------------------------------------------- */
+typedef struct {
+  b200gat_layer layer;
+  int64_t num_rows;                   /* own destination rows */
+  const float* gout; int64_t ldgo;    /* [rows, D_out] */
+  const float* out;  int64_t ldo;     /* [rows, D_out] (concat || H == 1) */
+  const float* o_heads;               /* [rows, Dp]    (!concat && H > 1) */
+  const float* bias;
+  const float* s_dst; const float* rowmax; const float* rowsum;   /* [rows, H] */
+  float* rowrec;                      /* out [rows, H, 4]: {s_dst, rowmax, 1/(rowsum+1e-16), Drow} */
+  float* g_pad;                       /* out: padded / 1/H-scaled copy of G ([rows, Dp] if concat || H == 1 else
+                                         [rows, c_pad]); NULL iff gout is directly gatherable (concat-like, C % 4 == 0) */
+  float* g_bias;                      /* out [D_out] (this block's partial column sums) */
+} b200gat_edge_bwd_prep_args;
+int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* stream);
+
+typedef struct {
+  b200gat_layer layer;
+  int64_t num_rows;                   /* own SOURCE rows */
+  const int32_t* colptr;              /* [rows+1] CSC of the edges whose source is in the own block */
+  const int32_t* crow;                /* global destination ids */
+  const int32_t* ceid;                /* original edge positions (mask lookup) or NULL */
+  const float* wh; const float* s_src;       /* own rows: [rows, Dp], [rows, H] */
+  const float* rowrec;                /* ALL nodes: [N, H, 4] */
+  const float* mask;                  /* optional [E', H] in original edge order */
+  const float* g; int64_t ldg; int64_t g_head_stride;   /* ALL nodes: G[i,h,c] = g[i*ldg + h*g_head_stride + c] */
+  float* g_wh;                        /* out [rows, Dp] */
+  float* g_s_src;                     /* out [rows, H] */
+  float* g_s_dst;                     /* in/out ALL nodes [N, H]: zero-initialised by the caller, accumulated atomically */
+} b200gat_edge_bwd_csc_args;
+int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
+
+typedef struct {
+  b200gat_layer layer;
+  int64_t num_rows;
+  const float* wh;                    /* [rows, Dp] */
+  const float* a1; const float* a2;   /* [Dp] */
+  const float* g_s_src; const float* g_s_dst;   /* [rows, H] (g_s_dst already reduced over all ranks) */
+  float* g_t;                         /* in: g_wh, out: gT  [rows, Dp] */
+  float* g_bw; float* g_a1; float* g_a2;   /* out [Dp] (partial sums of this block) */
+  float* g_b1; float* g_b2;           /* out [H] */
+} b200gat_edge_bwd_finish_args;
+int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream);
 
 /* ---- K4: projection backward -------------------------------------------------------------------------------- */
 typedef struct {
