@@ -186,7 +186,20 @@ def cpu_reference_leg(workload, steps, warmup, sample):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 while the bench runs (NCCL prints
+    its version banner there) is diverted to stderr so that the line stays machine-readable."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -215,7 +228,7 @@ def main():
                                  "sample": desc},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     if not torch.cuda.is_available():
@@ -299,7 +312,7 @@ def main():
     launches = _abi.launch_count() - launches0
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches}))
+            _emit({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -393,7 +406,7 @@ def main():
         "gpu_launches": launches, "roofline": roofline, "edge_phase": edge_phase, "kernels": kernels,
         "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
