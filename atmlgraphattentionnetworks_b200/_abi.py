@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -32,7 +32,8 @@ class ProjFwdArgs(C.Structure):
                 ("w", C.c_void_p), ("bw", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
                 ("b1", C.c_void_p), ("b2", C.c_void_p),
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t)]
 
 
 class EdgeFwdArgs(C.Structure):
@@ -84,7 +85,8 @@ class ProjBwdArgs(C.Structure):
     _fields_ = [("layer", Layer), ("num_nodes", C.c_int64),
                 ("g_t", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p),
                 ("g_x", C.c_void_p), ("ldgx", C.c_int64), ("g_w", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t)]
 
 
 _SIGNATURES = {
@@ -95,6 +97,7 @@ _SIGNATURES = {
     "b200gat_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 +
                           [C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200gat_proj_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
+    "b200gat_proj_split_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_fwd": (C.c_int, [C.POINTER(ProjFwdArgs), C.c_void_p]),
     "b200gat_edge_fwd": (C.c_int, [C.POINTER(EdgeFwdArgs), C.c_void_p]),
     "b200gat_edge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),

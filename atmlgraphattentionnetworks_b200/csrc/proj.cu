@@ -1,7 +1,7 @@
 // K1 / K4 — the dense per-head projection (GAT.py:42-52) and its backward.
 //   forward : Wh[N,Dp] = X[N,F] · Wp[Dp,F]^T + bw ;  s_src = <Wh_h, a1_h> + b1_h ;  s_dst = <Wh_h, a2_h> + b2_h
 //   backward: gX[N,F] = gT[N,Dp] · Wp[Dp,F] ;  gW[Dp,F] = gT^T · X
-// Dispatch: the tcgen05 (3xTF32) kernel in proj_tc.cu takes the shapes it supports; everything else runs on
+// Dispatch: the tcgen05 (3xFP16 split) kernel in proj_tc.cu takes the shapes it supports; everything else runs on
 // the fp32 CUDA-core GEMM below.  Both produce fp32 results within the 1e-5 parity bar.
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -56,6 +56,11 @@ using namespace b200gat;
 extern "C" size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* L, int64_t N) {
   if (!L || N < 0) return 0;
   return proj_tc_fwd_workspace_bytes(*L, N);
+}
+
+extern "C" size_t b200gat_proj_split_bytes(const b200gat_layer* L, int64_t N) {
+  if (!L || N < 0) return 0;
+  return proj_tc_split_bytes(*L, N);
 }
 
 extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {

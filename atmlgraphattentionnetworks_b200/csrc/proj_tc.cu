@@ -1,40 +1,48 @@
 // tcgen05 projection kernels (sm_100a): the only dense contraction of the path (GAT.py:43, per-head Linear) and its
 // two backward GEMMs, on the 5th-gen tensor cores with TMA-fed shared-memory operands and TMEM accumulators.
 //
-// fp32 parity on tensor cores: the reference's Linear is a true-fp32 sgemm (torch allow_tf32=False).  One TF32 MMA
-// lands ~1e-4 from it (fails the 1e-5 bar), so every operand is split  a = a_hi + a_lo  with a_hi = a & 0xffffe000
-// (exactly TF32-representable) and a_lo = (a - a_hi) & 0xffffe000, and three kind::tf32 MMAs accumulate
-//     a_lo*b_hi + a_hi*b_lo + a_hi*b_hi                                   ("3xTF32", error ~2^-21 relative)
-// The split is a streaming pre-pass that also pads K to a multiple of 32 (TMA needs 16-byte row strides; F_in = 50,
-// 1433, ... do not have them).
+// fp32 parity on tensor cores ("3xFP16 split"): the reference's Linear is a true-fp32 sgemm (torch allow_tf32=False);
+// one TF32 or one 16-bit MMA lands 1e-4..1e-3 from it (fails the 1e-5 bar).  Every operand tensor T is therefore
+// stored as TWO fp16 planes of  T * s  (s = a power of two chosen from max|T| so that max|T*s| is in [2^14, 2^15)):
+//     hi = fp16(T*s)            (11 significant bits)
+//     lo = fp16(T*s - hi)       (the next 11 bits; exact residual, unscaled, so one accumulator serves all products)
+// and three kind::f16 MMAs accumulate  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  in fp32 — every product is exact, the
+// dropped a_lo*b_lo term is 2^-22 relative.  Per element the representation error is max(2^-22 |t|, 2^-40 max|T|):
+// elements within 2^-18 of the tensor's largest magnitude carry 22 bits, smaller ones an absolute 2^-40 max|T|.
+// kind::f16 runs at twice the kind::tf32 rate and the planes are half the bytes of a TF32 hi/lo pair, so this is 2x the
+// 3xTF32 ceiling in both the tensor pipe and shared-memory / L2 operand traffic.  The result is multiplied by
+// 1/(s_a s_b) (exact) in the epilogue.
+//
+// No transposes: tcgen05 takes either major-ness from shared memory (instruction-descriptor bits 15/16), so the same
+// row-major planes feed   X·W^T (A, B K-major),   gT·W (A K-major, B = W planes MN-major)   and   gT^T·X (A = gT planes
+// MN-major, B = X planes MN-major, K = nodes, split-K) — X and W are split once in the forward and reused.
 //
 // Tensor-core fp32 accumulation TRUNCATES (measured on B200: the error of one long TMEM accumulation chain grows
-// ~0.5 ulp per MMA, 9e-6 relative at K = 1024), so a TMEM accumulator only ever holds a SHORT chain: two 128 x BN
-// accumulators alternate every TC_KC k-blocks (8 k-steps x 3 MMAs) and the epilogue warps promote each finished
-// chunk into fp32 REGISTER accumulators with round-to-nearest adds while the tensor core fills the other buffer.
-// The result is as accurate as an fp32 CUDA-core GEMM for any K (the split-K gW reduction runs K = 57k nodes).
+// ~0.5 ulp per MMA), so a TMEM accumulator only ever holds a SHORT chain: two 128 x BN accumulators alternate every
+// TC_KC k-blocks (8 k-steps x 3 MMAs) and the epilogue warps promote each finished chunk into fp32 REGISTER
+// accumulators with round-to-nearest adds while the tensor core fills the other buffer.
 //
-// Kernel anatomy (one 128 x BN output tile per CTA):
-//   warp 0    : TMA producer — cp.async.bulk.tensor.2d of the four operand tiles (A_hi, A_lo, B_hi, B_lo) of one
-//               32-deep k-block into a 128B-swizzled stage, mbarrier complete_tx
-//   warp 1    : TMEM allocator + MMA issuer — one elected lane issues 4 k-steps x 3 tcgen05.mma.kind::tf32
-//               (M=128, N=BN, K=8) per stage; tcgen05.commit frees the stage / hands a finished chunk to the epilogue
-//   warps 2.. : epilogue, 4 warps per 128 output columns — tcgen05.ld 32x32b.x32 of each finished chunk (TMEM lane
-//               quarter = warp_id % 4) into 128 register accumulators; at the end + bias, fused attention-logit
-//               reductions s_src = <Wh_h, a1_h> + b1_h, s_dst = <Wh_h, a2_h> + b2_h, fp32 store (or red.global.add
-//               for the split-K gW reduction)
-// All operands are K-major ([rows, K] row-major, K contiguous): X·W^T directly, gT·W through a transposed copy of the
-// small W, and gT^T·X through transposing split pre-passes of gT and X (K = nodes).
+// Kernel anatomy (persistent: one CTA per SM walks a static list of (split, m-tile, n-tile) work items, n fastest):
+//   warp 0    : TMA producer — cp.async.bulk.tensor.2d of the four operand planes (A_hi, A_lo, B_hi, B_lo) of one
+//               64-deep k-block into a 128B-swizzled stage, mbarrier complete_tx
+//   warp 1    : TMEM allocator + MMA issuer — one elected lane issues 4 k-steps x 3 tcgen05.mma.kind::f16
+//               (M=128, N=BN, K=16) per stage; tcgen05.commit frees the stage / hands a finished chunk to the epilogue
+//   warps 2.. : epilogue, 4 warps per 128 output columns — tcgen05.ld 32x32b.x16 of each finished chunk (TMEM lane
+//               quarter = warp_id % 4) into 128 register accumulators; at the end of a work item: * 1/(s_a s_b), + bias,
+//               fused attention-logit reductions s_src = <Wh_h, a1_h> + b1_h, s_dst = <Wh_h, a2_h> + b2_h, fp32 store
+//               (or red.global.add for the split-K gW reduction) — overlapping the next item's first chunks
 #include "proj_tc.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <stdlib.h>
 
 namespace b200gat {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;   // fp32 elements per k-block row = 128 bytes = one SWIZZLE_128B atom row
+constexpr int TC_BK = 64;   // fp16 elements per k-block row = 128 bytes = one SWIZZLE_128B atom row
 constexpr int TC_KC = 2;    // k-blocks per TMEM accumulation chunk (2 x 4 k-steps x 3 MMAs = 24 MMAs per chain)
+constexpr int TC_MN_CHUNK_BYTES = 64 * TC_BK * 2;   // one MN-major TMA box: 64 k-rows x 64 fp16 (128 B) = 8 KB
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -59,10 +67,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -76,54 +84,63 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
-// K-major shared-memory matrix descriptor: 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1
+// Shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100).
+//   K-major  operand (rows of 64 fp16 = 128 B along K): 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major operand (rows of 64 fp16 = 128 B along M/N, one row per k): 8-k groups 1024 B apart (SBO), the next
+//            64 M/N elements TC_MN_CHUNK_BYTES further (LBO) — each chunk is one 64 x 64 TMA box.
+template <bool MN>
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   uint64_t d = 0;
   d |= uint64_t((saddr & 0x3FFFFu) >> 4);
-  d |= uint64_t(1) << 16;            // LBO (unused for swizzled K-major)
-  d |= uint64_t(1024 >> 4) << 32;    // SBO
-  d |= uint64_t(1) << 46;            // descriptor version (sm_100)
-  d |= uint64_t(2) << 61;            // LayoutType::SWIZZLE_128B
+  d |= uint64_t(MN ? (TC_MN_CHUNK_BYTES >> 4) : 1) << 16;   // LBO
+  d |= uint64_t(1024 >> 4) << 32;                           // SBO
+  d |= uint64_t(1) << 46;                                   // descriptor version (sm_100)
+  d |= uint64_t(2) << 61;                                   // LayoutType::SWIZZLE_128B
   return d;
 }
+// bytes to advance an operand's start address per 16-deep k-step
+template <bool MN>
+__device__ __forceinline__ constexpr uint32_t kstep_bytes() { return MN ? 16 * 128 : 16 * 2; }
 
-// instruction descriptor: kind::tf32 (a/b format 2), fp32 accumulate (c format 1), K-major A and B, M=128, N=BN
-template <int BN>
+// instruction descriptor: kind::f16 with fp16 A/B (format 0), fp32 accumulate (c format 1), M=128, N=BN
+template <int BN, bool A_MN, bool B_MN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+  return (1u << 4) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
 struct TcGemmParams {
   int64_t M, N;            // output extent
-  int k_blocks;            // total k-blocks (K padded / 32)
-  int k_blocks_per_split;  // k-blocks per blockIdx.z
+  int k_blocks;            // total k-blocks (ceil(K / 64))
+  int k_blocks_per_split;  // k-blocks per split
+  int m_tiles, n_tiles, splits;
   float* C; int64_t ldc;
   const float* bias;       // [N] or null
+  const float* inv_a; const float* inv_b;   // device scalars: 1/s of the two operand splits
   // fused attention-logit epilogue (EPI_LOGITS)
   const float* a1; const float* a2; const float* b1; const float* b2; float* s_src; float* s_dst; int H, Cp;
 };
@@ -135,16 +152,27 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 2 : 3;
   static constexpr int EPI_WARPS = 4 * (BN / 128);
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;            // 16 KB
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;            // 16 KB per plane
+  static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int VEC_BYTES = 3 * BN * 4;                 // bias / a1 / a2 slices of the tile
+  static constexpr int VEC_BYTES = 3 * BN * 4;                 // bias / a1 / a2 slices of the current tile
   static constexpr int RED_BYTES = 2 * TC_BM * 4;              // cross-half logit partials (BN = 256, Cp = 256)
   static constexpr int BAR_BYTES = 128;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + VEC_BYTES + RED_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
 
-template <int BN, int EPI>
+// one operand plane of one k-block: K-major = one box {64 k, ROWS}; MN-major = ROWS/64 boxes {64 mn, 64 k}
+template <bool MN, int ROWS>
+__device__ __forceinline__ void load_plane(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int k0, int mn0) {
+  if (!MN) {
+    tma_load_2d(dst, map, bar, k0, mn0);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ROWS / 64; ++c) tma_load_2d(dst + c * TC_MN_CHUNK_BYTES, map, bar, mn0 + 64 * c, k0);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
@@ -163,14 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // n-tiles vary fastest: the CTAs resident together share one A (row) tile and sweep the small B operand, so A is
-  // streamed from HBM once instead of once per n-tile (ncu, r1b: 1.9 GB -> the 4 n-tiles of Dp = 1024 re-read it)
-  const int64_t n0 = int64_t(blockIdx.x) * BN;
-  const int64_t m0 = int64_t(blockIdx.y) * TC_BM;
-  const int kb0 = blockIdx.z * p.k_blocks_per_split;
-  const int kb1 = (kb0 + p.k_blocks_per_split < p.k_blocks) ? kb0 + p.k_blocks_per_split : p.k_blocks;
-  const int nkb = kb1 - kb0;
-  const int nchunks = (nkb + TC_KC - 1) / TC_KC;
+  const int total_items = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
@@ -188,68 +209,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_ptr);
-  if (warp >= 2) {   // epilogue warps stage the per-column vectors of this tile
-    for (int c = threadIdx.x - 64; c < BN; c += 32 * S::EPI_WARPS) {
-      const int64_t col = n0 + c;
-      const bool ok = col < p.N;
-      vec[c] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
-      if (EPI == EPI_LOGITS) {
-        vec[BN + c] = ok ? __ldg(p.a1 + col) : 0.f;
-        vec[2 * BN + c] = ok ? __ldg(p.a2 + col) : 0.f;
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // work item w -> (split, m-tile, n-tile); n-tiles vary fastest so that the CTAs resident together share A (row)
+  // tiles and sweep the small B operand: A is streamed from HBM once instead of once per n-tile
+  auto item_coords = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+    const int nt = w % p.n_tiles;
+    const int r = w / p.n_tiles;
+    const int mt = r % p.m_tiles, sp = r / p.m_tiles;
+    m0 = mt * TC_BM;
+    n0 = nt * BN;
+    kb0 = sp * p.k_blocks_per_split;
+    const int kb1 = (kb0 + p.k_blocks_per_split < p.k_blocks) ? kb0 + p.k_blocks_per_split : p.k_blocks;
+    nkb = kb1 - kb0;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = stage_base + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        const int k0 = (kb0 + i) * TC_BK;
-        tma_load_2d(st, &map_ah, &full_bar[s], k0, static_cast<int>(m0));
-        tma_load_2d(st + S::A_BYTES, &map_al, &full_bar[s], k0, static_cast<int>(m0));
-        tma_load_2d(st + 2 * S::A_BYTES, &map_bh, &full_bar[s], k0, static_cast<int>(n0));
-        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_bl, &full_bar[s], k0, static_cast<int>(n0));
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_coords(w, m0, n0, kb0, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t st = smem_u32(stage_base + s * S::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          const int k0 = (kb0 + i) * TC_BK;
+          load_plane<A_MN, TC_BM>(st, &map_ah, &full_bar[s], k0, m0);
+          load_plane<A_MN, TC_BM>(st + S::A_BYTES, &map_al, &full_bar[s], k0, m0);
+          load_plane<B_MN, BN>(st + 2 * S::A_BYTES, &map_bh, &full_bar[s], k0, n0);
+          load_plane<B_MN, BN>(st + 2 * S::A_BYTES + S::B_BYTES, &map_bl, &full_bar[s], k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>();
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        const int chunk = i / TC_KC, b = chunk & 1;
-        const bool chunk_first = (i % TC_KC) == 0;
-        const bool chunk_last = (i % TC_KC) == TC_KC - 1 || i == nkb - 1;
-        if (chunk_first) {
-          mbar_wait(&tempty_bar[b], ((chunk >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      uint32_t it = 0, chunk = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_coords(w, m0, n0, kb0, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          const int b = chunk & 1;
+          const bool chunk_first = (i % TC_KC) == 0;
+          const bool chunk_last = (i % TC_KC) == TC_KC - 1 || i == nkb - 1;
+          if (chunk_first) {
+            mbar_wait(&tempty_bar[b], ((chunk >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
+            tc_fence_after();
+          }
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-        }
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(b * BN);
-        const uint32_t st = smem_u32(stage_base + s * S::STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+          const uint32_t d_tmem = tmem_base + uint32_t(b * BN);
+          const uint32_t st = smem_u32(stage_base + s * S::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          // 8 fp32 = 32 B along the swizzled 128-B row
-          const uint64_t dah = make_sdesc(a_hi + ks * 32), dal = make_sdesc(a_lo + ks * 32);
-          const uint64_t dbh = make_sdesc(b_hi + ks * 32), dbl = make_sdesc(b_lo + ks * 32);
-          mma_tf32(d_tmem, dal, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
-          mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-          mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+          for (int ks = 0; ks < TC_BK / 16; ++ks) {
+            const uint32_t ao = ks * kstep_bytes<A_MN>(), bo = ks * kstep_bytes<B_MN>();
+            const uint64_t dah = make_sdesc<A_MN>(a_hi + ao), dal = make_sdesc<A_MN>(a_lo + ao);
+            const uint64_t dbh = make_sdesc<B_MN>(b_hi + bo), dbl = make_sdesc<B_MN>(b_lo + bo);
+            mma_f16(d_tmem, dal, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
+            mma_f16(d_tmem, dah, dbl, idesc, 1u);
+            mma_f16(d_tmem, dah, dbh, idesc, 1u);
+          }
+          mma_commit(&empty_bar[s]);                  // frees the stage once these MMAs have read it
+          if (chunk_last) {
+            mma_commit(&tfull_bar[b]);                // chunk complete in TMEM buffer b
+            ++chunk;
+          }
         }
-        mma_commit(&empty_bar[s]);                  // frees the stage once these MMAs have read it
-        if (chunk_last) mma_commit(&tfull_bar[b]);  // chunk complete in TMEM buffer b
       }
     }
   } else {
@@ -257,89 +293,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int ew = warp - 2;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int half = ew >> 2;                       // which 128-column half of the tile
-    const int64_t row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
     const int cbase = half * 128;                   // first tile column of this thread
-    float acc[128];
-#pragma unroll
-    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int b = c & 1;
-      mbar_wait(&tfull_bar[b], (c >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + cbase);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[ch * 32 + j] += __uint_as_float(v[j]);   // round-to-nearest promotion
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[b]);
-    }
-
-    const int64_t col0 = n0 + cbase;                // first global column of this thread
-    float* dst = p.C + row * p.ldc + col0;
-    if (EPI == EPI_ATOMIC) {
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < 128; ++j)
-          if (col0 + j < p.N) atomicAdd(dst + j, acc[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 128; ++j) acc[j] += vec[cbase + j];
-      if (EPI == EPI_LOGITS) {
-        float d1 = 0.f, d2 = 0.f;
-        if (p.Cp <= 128) {
-          // heads tile this thread's 128 columns (128 % Cp == 0, checked on the host)
-#pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
-            d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
-            if ((j + 1) % p.Cp == 0) {
-              const int64_t col = col0 + j;
-              if (row_ok && col < p.N) {
-                const int h = static_cast<int>(col / p.Cp);
-                p.s_src[row * p.H + h] = d1 + __ldg(p.b1 + h);
-                p.s_dst[row * p.H + h] = d2 + __ldg(p.b2 + h);
-              }
-              d1 = 0.f;
-              d2 = 0.f;
-            }
-          }
-        } else {
-          // Cp == 256 == BN: one head per tile, its two halves live in two warps -> combine through shared memory
-#pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
-            d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
-          }
-          const int r = q * 32 + lane;
-          if (half == 1) {
-            red[r] = d1;
-            red[TC_BM + r] = d2;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
-          if (half == 0 && row_ok && n0 < p.N) {
-            const int h = static_cast<int>(n0 / p.Cp);
-            p.s_src[row * p.H + h] = d1 + red[r] + __ldg(p.b1 + h);
-            p.s_dst[row * p.H + h] = d2 + red[TC_BM + r] + __ldg(p.b2 + h);
+    const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
+    uint32_t chunk = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      item_coords(w, m0, n0, kb0, nkb);
+      const int nchunks = (nkb + TC_KC - 1) / TC_KC;
+      const int64_t row = int64_t(m0) + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      if (EPI != EPI_ATOMIC) {
+        // stage the per-column vectors of this tile (the previous item's readers are past the barrier)
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
+        for (int c = threadIdx.x - 64; c < BN; c += 32 * S::EPI_WARPS) {
+          const int64_t col = int64_t(n0) + c;
+          const bool ok = col < p.N;
+          vec[c] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+          if (EPI == EPI_LOGITS) {
+            vec[BN + c] = ok ? __ldg(p.a1 + col) : 0.f;
+            vec[2 * BN + c] = ok ? __ldg(p.a2 + col) : 0.f;
           }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
       }
-      if (row_ok) {
-        const bool vec_ok = (col0 + 128 <= p.N) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
-        if (vec_ok) {
+      float acc[128];
 #pragma unroll
-          for (int j = 0; j < 128; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        } else {
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++chunk) {
+        const int b = chunk & 1;
+        mbar_wait(&tfull_bar[b], (chunk >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + cbase);
 #pragma unroll
-          for (int j = 0; j < 128; ++j)
-            if (col0 + j < p.N) dst[j] = acc[j];
+        for (int ch = 0; ch < 8; ++ch) {   // x16 loads: 128 accumulators + 32 in-flight values would not fit 168 registers
+          uint32_t v[16];
+          tmem_ld16(taddr + ch * 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[ch * 16 + j] += __uint_as_float(v[j]);   // round-to-nearest promotion
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[b]);
+      }
+
+      const int64_t col0 = int64_t(n0) + cbase;       // first global column of this thread
+      float* dst = p.C + row * p.ldc + col0;
+      const bool vec_ok = (col0 + 128 <= p.N) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+      if (EPI == EPI_ATOMIC) {
+        if (row_ok) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 128; j += 4)
+              red_add_v4(dst + j, acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 128; ++j)
+              if (col0 + j < p.N) atomicAdd(dst + j, acc[j] * inv);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = fmaf(acc[j], inv, vec[cbase + j]);
+        if (EPI == EPI_LOGITS) {
+          float d1 = 0.f, d2 = 0.f;
+          if (p.Cp <= 128) {
+            // heads tile this thread's 128 columns (128 % Cp == 0, checked on the host)
+#pragma unroll
+            for (int j = 0; j < 128; ++j) {
+              d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
+              d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
+              if ((j + 1) % p.Cp == 0) {
+                const int64_t col = col0 + j;
+                if (row_ok && col < p.N) {
+                  const int h = static_cast<int>(col / p.Cp);
+                  p.s_src[row * p.H + h] = d1 + __ldg(p.b1 + h);
+                  p.s_dst[row * p.H + h] = d2 + __ldg(p.b2 + h);
+                }
+                d1 = 0.f;
+                d2 = 0.f;
+              }
+            }
+          } else {
+            // Cp == 256 == BN: one head per tile, its two halves live in two warps -> combine through shared memory
+#pragma unroll
+            for (int j = 0; j < 128; ++j) {
+              d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
+              d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
+            }
+            const int r = q * 32 + lane;
+            if (half == 1) {
+              red[r] = d1;
+              red[TC_BM + r] = d2;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
+            if (half == 0 && row_ok && n0 < p.N) {
+              const int h = n0 / p.Cp;
+              p.s_src[row * p.H + h] = d1 + red[r] + __ldg(p.b1 + h);
+              p.s_dst[row * p.H + h] = d2 + red[TC_BM + r] + __ldg(p.b2 + h);
+            }
+          }
+        }
+        if (row_ok) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 128; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 128; ++j)
+              if (col0 + j < p.N) dst[j] = acc[j];
+          }
         }
       }
     }
@@ -353,45 +416,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ split pre-passes
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+// A "split blob" holds one operand tensor [rows, cols] as fp16 planes:
+//   +0    float    inv_scale (1/s)        +4  uint32  max|T| bit pattern (scratch of the amax pass)
+//   +256  __half   hi[rows, ldp]          +256 + plane_bytes   __half lo[rows, ldp]        ldp = round_up(cols, 8)
+constexpr size_t BLOB_HEADER = 256;
+static inline int64_t pad8(int64_t v) { return (v + 7) / 8 * 8; }
+static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+static inline size_t plane_bytes(int64_t rows, int64_t cols) { return up256(size_t(rows) * size_t(pad8(cols)) * 2); }
+static inline size_t blob_bytes(int64_t rows, int64_t cols) { return BLOB_HEADER + 2 * plane_bytes(rows, cols); }
+
+struct Blob {
+  uint8_t* base; int64_t rows, cols, ldp;
+  float* inv_scale() const { return reinterpret_cast<float*>(base); }
+  uint32_t* amax_bits() const { return reinterpret_cast<uint32_t*>(base) + 1; }
+  __half* hi() const { return reinterpret_cast<__half*>(base + BLOB_HEADER); }
+  __half* lo() const { return reinterpret_cast<__half*>(base + BLOB_HEADER + plane_bytes(rows, cols)); }
+};
+static inline Blob make_blob(void* base, int64_t rows, int64_t cols) {
+  return Blob{static_cast<uint8_t*>(base), rows, cols, pad8(cols)};
 }
 
-// src [rows, cols] (row stride ld) -> hi / lo [rows, ldp] with zero padding of columns [cols, ldp)
+// max |src| as a uint bit pattern (non-negative floats order like unsigned integers; NaN sorts above inf and is kept)
 __global__ void __launch_bounds__(256)
-split_pad_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, float* __restrict__ hi,
-                 float* __restrict__ lo, int64_t ldp) {
-  const int64_t total = rows * ldp;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = t / ldp, c = t - r * ldp;
-    float h = 0.f, l = 0.f;
-    if (c < cols) split_tf32(__ldg(src + r * ld + c), h, l);
-    hi[t] = h;
-    lo[t] = l;
-  }
-}
-
-// src [rows, cols] -> TRANSPOSED hi / lo [cols, ldp] (ldp = pad32(rows)), zero padded
-__global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, float* __restrict__ hi,
-                       float* __restrict__ lo, int64_t ldp) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t r0 = int64_t(blockIdx.x) * 32, c0 = int64_t(blockIdx.y) * 32;   // x: the long (node) dimension
-  for (int u = ty; u < 32; u += 8) {
-    const int64_t r = r0 + u, c = c0 + tx;
-    tile[u][tx] = (r < rows && c < cols) ? __ldg(src + r * ld + c) : 0.f;
-  }
-  __syncthreads();
-  for (int u = ty; u < 32; u += 8) {
-    const int64_t c = c0 + u, r = r0 + tx;       // output row = source column
-    if (c < cols && r < ldp) {
-      float h, l;
-      split_tf32(tile[tx][u], h, l);
-      hi[c * ldp + r] = h;
-      lo[c * ldp + r] = l;
+amax_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+  if (ld == cols && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const int64_t total = rows * cols, n4 = total >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int64_t t = tid; t < n4; t += nth) {
+      const float4 v = __ldg(s4 + t);
+      m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
     }
+    for (int64_t t = (n4 << 2) + tid; t < total; t += nth) m = max(m, __float_as_uint(fabsf(__ldg(src + t))));
+  } else {
+    const int64_t total = rows * cols;
+    for (int64_t t = tid; t < total; t += nth) {
+      const int64_t r = t / cols, c = t - r * cols;
+      m = max(m, __float_as_uint(fabsf(__ldg(src + r * ld + c))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ uint32_t sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = max(m, sm[i]);
+    if (m) atomicMax(out, m);
+  }
+}
+
+// power-of-two scale putting max|T| * s in [2^14, 2^15) (fp16 max is 65504); 1 for an all-zero or non-finite tensor
+__device__ __forceinline__ float scale_from_amax(uint32_t bits) {
+  const float a = __uint_as_float(bits);
+  if (!(a > 0.f) || !(a <= 3.4028234e38f)) return 1.f;
+  int e;
+  frexpf(a, &e);                 // a = m * 2^e, m in [0.5, 1)
+  int sh = 15 - e;
+  if (sh > 126) sh = 126;
+  return ldexpf(1.f, sh);
+}
+
+// src [rows, cols] (row stride ld) -> hi / lo fp16 planes [rows, ldp]; pad columns [cols, ldp) are zero
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, __half* __restrict__ hi,
+             __half* __restrict__ lo, int64_t ldp, const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale) {
+  const float s = scale_from_amax(*amax_bits);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = 1.f / s;
+  const int64_t groups = ldp >> 3, total = rows * groups;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = t / groups, c0 = (t - r * groups) << 3;
+    float v[8];
+    const float* p = src + r * ld + c0;
+    if (vec && c0 + 8 <= cols) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(p)), x1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(p + j) : 0.f;
+    }
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = v[j] * s;
+      h[j] = __float2half_rn(x);
+      l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldp + c0) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + r * ldp + c0) = *reinterpret_cast<const uint4*>(l);
   }
 }
 
@@ -413,28 +528,40 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch `ld` elements; box = {32 cols (128 B, inner), box_rows}, SWIZZLE_128B
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp16 plane [rows, cols] with row pitch `ld` elements; box = {64 cols (128 B, inner), box_rows}, SWIZZLE_128B;
+// out-of-range parts of a box are zero-filled (K / M / N tails need no padding in memory)
+static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(B200GAT_E_UNSUPPORTED, "proj_tc: cuTensorMapEncodeTiled is not available");
   cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t gstr[1] = {cuuint64_t(ld) * 4};
+  cuuint64_t gstr[1] = {cuuint64_t(ld) * 2};
   cuuint32_t box[2] = {cuuint32_t(TC_BK), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200GAT_E_SHAPE, "proj_tc: cuTensorMapEncodeTiled failed (%d)", int(r));
   return 0;
 }
 
-static inline int64_t pad32(int64_t v) { return (v + 31) / 32 * 32; }
-static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+static int launch_split(const float* src, int64_t ld, const Blob& b, cudaStream_t stream) {
+  cudaError_t ce = cudaMemsetAsync(b.base, 0, 8, stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "proj_tc: memset: %s", cudaGetErrorString(ce));
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int64_t want_a = ceil_div(b.rows * b.cols, 256 * 4);
+  amax_kernel<<<static_cast<int>(want_a < cap ? (want_a > 0 ? want_a : 1) : cap), 256, 0, stream>>>(src, ld, b.rows, b.cols, b.amax_bits());
+  int rc = check_launch("amax_kernel");
+  if (rc) return rc;
+  const int64_t want_s = ceil_div(b.rows * (b.ldp >> 3), 256);
+  split_kernel<<<static_cast<int>(want_s < 2 * cap ? (want_s > 0 ? want_s : 1) : 2 * cap), 256, 0, stream>>>(
+      src, ld, b.rows, b.cols, b.hi(), b.lo(), b.ldp, b.amax_bits(), b.inv_scale());
+  return check_launch("split_kernel");
+}
 
-template <int BN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                     const TcGemmParams& p, int splits, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<BN, EPI>;
+                     TcGemmParams p, cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -442,43 +569,36 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "proj_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  dim3 grid(static_cast<unsigned>(ceil_div(p.N, BN)), static_cast<unsigned>(ceil_div(p.M, TC_BM)), static_cast<unsigned>(splits));
+  p.m_tiles = static_cast<int>(ceil_div(p.M, TC_BM));
+  p.n_tiles = static_cast<int>(ceil_div(p.N, BN));
+  const int64_t items = int64_t(p.m_tiles) * p.n_tiles * p.splits;
+  const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
   kern<<<grid, TcCfg<BN>::THREADS, TcCfg<BN>::TOTAL, stream>>>(ah, al, bh, bl, p);
   return check_launch("gemm_tc_kernel");
 }
 
-static int launch_split(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldp,
-                        cudaStream_t stream) {
-  const int64_t total = rows * ldp;
-  const int64_t want = ceil_div(total, 256);
-  const int64_t cap = int64_t(sm_count()) * 16;
-  split_pad_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(src, ld, rows, cols, hi, lo, ldp);
-  return check_launch("split_pad_kernel");
-}
-
-static int launch_split_transpose(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo,
-                                  int64_t ldp, cudaStream_t stream) {
-  dim3 grid(static_cast<unsigned>(ceil_div(ldp, 32)), static_cast<unsigned>(ceil_div(cols, 32)));
-  split_transpose_kernel<<<grid, 256, 0, stream>>>(src, ld, rows, cols, hi, lo, ldp);
-  return check_launch("split_transpose_kernel");
-}
-
-// C[M,N] (=, +bias | +=) A[M,K] · B[N,K]^T with pre-split K-major operands of pitch Kp; `splits` > 1 => EPI_ATOMIC
-template <int EPI>
-static int gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int64_t M, int64_t N,
-                   int64_t Kp, TcGemmParams p, int splits, cudaStream_t stream) {
-  p.M = M; p.N = N; p.k_blocks = static_cast<int>(Kp / TC_BK);
+// C[M,N] (=, +bias | +=) A · B^T.  A is the blob of a [M,K] (K-major) or [K,M] (A_MN) tensor, B of a [N,K] (K-major)
+// or [K,N] (B_MN) tensor; `splits` > 1 requires EPI_ATOMIC on a zeroed C.
+template <bool A_MN, bool B_MN, int EPI>
+static int gemm_blobs(const Blob& A, const Blob& B, int64_t M, int64_t N, int64_t K, TcGemmParams p, int splits,
+                      cudaStream_t stream) {
+  p.M = M; p.N = N;
+  p.k_blocks = static_cast<int>(ceil_div(K, TC_BK));
+  if (splits < 1) splits = 1;
   p.k_blocks_per_split = static_cast<int>(ceil_div(p.k_blocks, splits));
-  splits = static_cast<int>(ceil_div(p.k_blocks, p.k_blocks_per_split));
+  p.splits = static_cast<int>(ceil_div(p.k_blocks, p.k_blocks_per_split));
+  p.inv_a = A.inv_scale();
+  p.inv_b = B.inv_scale();
+  const int bn = N > 128 ? 256 : 128;
   CUtensorMap ah, al, bh, bl;
   int rc;
-  const int bn = N > 128 ? 256 : 128;
-  if ((rc = make_map(&ah, a_hi, M, Kp, Kp, TC_BM))) return rc;
-  if ((rc = make_map(&al, a_lo, M, Kp, Kp, TC_BM))) return rc;
-  if ((rc = make_map(&bh, b_hi, N, Kp, Kp, bn))) return rc;
-  if ((rc = make_map(&bl, b_lo, N, Kp, Kp, bn))) return rc;
-  if (bn == 256) return launch_tc<256, EPI>(ah, al, bh, bl, p, splits, stream);
-  return launch_tc<128, EPI>(ah, al, bh, bl, p, splits, stream);
+  const int a_box = A_MN ? 64 : TC_BM, b_box = B_MN ? 64 : bn;
+  if ((rc = make_map(&ah, A.hi(), A.rows, A.cols, A.ldp, a_box))) return rc;
+  if ((rc = make_map(&al, A.lo(), A.rows, A.cols, A.ldp, a_box))) return rc;
+  if ((rc = make_map(&bh, B.hi(), B.rows, B.cols, B.ldp, b_box))) return rc;
+  if ((rc = make_map(&bl, B.lo(), B.rows, B.cols, B.ldp, b_box))) return rc;
+  if (bn == 256) return launch_tc<256, A_MN, B_MN, EPI>(ah, al, bh, bl, p, stream);
+  return launch_tc<128, A_MN, B_MN, EPI>(ah, al, bh, bl, p, stream);
 }
 
 // ---- shape gates: the tensor-core path takes the projections that are worth a 128-row tile pipeline -----------------
@@ -497,33 +617,38 @@ bool proj_tc_fwd_supported(const b200gat_layer& L, int64_t N) {
 }
 bool proj_tc_bwd_supported(const b200gat_layer& L, int64_t N) { return proj_tc_fwd_supported(L, N); }
 
-struct FwdWs { size_t x_hi, x_lo, w_hi, w_lo, total; };
-static FwdWs plan_fwd(const b200gat_layer& L, int64_t N) {
-  const int64_t Kp = pad32(L.in_channels), Dp = L.heads * L.c_pad;
-  FwdWs w;
-  const size_t xs = up256(size_t(N) * Kp * 4), wsz = up256(size_t(Dp) * Kp * 4);
-  w.x_hi = 0; w.x_lo = xs; w.w_hi = 2 * xs; w.w_lo = 2 * xs + wsz; w.total = 2 * xs + 2 * wsz;
-  return w;
+size_t proj_tc_split_bytes(const b200gat_layer& L, int64_t N) {
+  return proj_tc_fwd_supported(L, N) ? blob_bytes(N, L.in_channels) : 0;
 }
+
 size_t proj_tc_fwd_workspace_bytes(const b200gat_layer& L, int64_t N) {
-  return proj_tc_fwd_supported(L, N) ? plan_fwd(L, N).total : 0;
+  if (!proj_tc_fwd_supported(L, N)) return 0;
+  return blob_bytes(N, L.in_channels) + blob_bytes(L.heads * L.c_pad, L.in_channels);
+}
+
+static int check_ws(const void* ws, size_t have, size_t need, const char* what) {
+  B200GAT_REQUIRE(ws && have >= need, B200GAT_E_WORKSPACE, "%s: workspace %zu < %zu bytes", what, have, need);
+  B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, B200GAT_E_ALIGN, "%s: workspace must be 256-byte aligned", what);
+  return 0;
 }
 
 int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   const b200gat_layer& L = a.layer;
-  const int64_t N = a.num_nodes, F = L.in_channels, H = L.heads, Cp = L.c_pad, Dp = H * Cp, Kp = pad32(F);
-  const FwdWs w = plan_fwd(L, N);
-  B200GAT_REQUIRE(a.workspace && a.workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "proj_fwd: workspace %zu < %zu bytes",
-                  a.workspace_bytes, w.total);
-  B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0, B200GAT_E_ALIGN, "proj_fwd: workspace must be 256-byte aligned");
-  char* base = static_cast<char*>(a.workspace);
-  float* x_hi = reinterpret_cast<float*>(base + w.x_hi);
-  float* x_lo = reinterpret_cast<float*>(base + w.x_lo);
-  float* w_hi = reinterpret_cast<float*>(base + w.w_hi);
-  float* w_lo = reinterpret_cast<float*>(base + w.w_lo);
+  const int64_t N = a.num_nodes, F = L.in_channels, H = L.heads, Cp = L.c_pad, Dp = H * Cp;
+  const size_t xb = blob_bytes(N, F), wb = blob_bytes(Dp, F);
   int rc;
-  if ((rc = launch_split(a.x, a.ldx, N, F, x_hi, x_lo, Kp, stream))) return rc;
-  if ((rc = launch_split(a.w, F, Dp, F, w_hi, w_lo, Kp, stream))) return rc;
+  // the split of x is written into the caller's x_split buffer when given (kept for b200gat_proj_bwd), else into workspace
+  const bool keep = a.x_split != nullptr;
+  if (keep) {
+    B200GAT_REQUIRE(a.x_split_bytes >= xb, B200GAT_E_WORKSPACE, "proj_fwd: x_split %zu < %zu bytes", a.x_split_bytes, xb);
+    B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.x_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_fwd: x_split must be 256-byte aligned");
+  }
+  if ((rc = check_ws(a.workspace, a.workspace_bytes, (keep ? 0 : xb) + wb, "proj_fwd"))) return rc;
+  char* base = static_cast<char*>(a.workspace);
+  const Blob X = make_blob(keep ? a.x_split : static_cast<void*>(base), N, F);
+  const Blob W = make_blob(base + (keep ? 0 : xb), Dp, F);
+  if ((rc = launch_split(a.x, a.ldx, X, stream))) return rc;
+  if ((rc = launch_split(a.w, F, W, stream))) return rc;
   TcGemmParams p{};
   p.C = a.wh; p.ldc = Dp; p.bias = a.bw;
   p.a1 = a.a1; p.a2 = a.a2; p.b1 = a.b1; p.b2 = a.b2; p.s_src = a.s_src; p.s_dst = a.s_dst;
@@ -531,61 +656,54 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   const int bn = Dp > 128 ? 256 : 128;
   // heads must not straddle an epilogue thread's 128 columns, or be exactly one 256-wide tile
   const bool fuse_logits = (Cp <= 128 && 128 % Cp == 0) || (Cp == 256 && bn == 256);
-  if (fuse_logits) return gemm_nt<EPI_LOGITS>(x_hi, x_lo, w_hi, w_lo, N, Dp, Kp, p, 1, stream);
-  if ((rc = gemm_nt<EPI_STORE>(x_hi, x_lo, w_hi, w_lo, N, Dp, Kp, p, 1, stream))) return rc;
+  if (fuse_logits) return gemm_blobs<false, false, EPI_LOGITS>(X, W, N, Dp, F, p, 1, stream);
+  if ((rc = gemm_blobs<false, false, EPI_STORE>(X, W, N, Dp, F, p, 1, stream))) return rc;
   return launch_logits(a, stream);
 }
 
-struct BwdWs { size_t g_hi, g_lo, wt_hi, wt_lo, gt_hi, gt_lo, xt_hi, xt_lo, total; };
-static BwdWs plan_bwd_ws(const b200gat_layer& L, int64_t N) {
-  const int64_t F = L.in_channels, Dp = L.heads * L.c_pad, Dk = pad32(Dp), Np = pad32(N);
-  BwdWs w;
-  const size_t gs = up256(size_t(N) * Dk * 4), ws = up256(size_t(F) * Dk * 4);
-  const size_t gts = up256(size_t(Dp) * Np * 4), xts = up256(size_t(F) * Np * 4);
-  size_t o = 0;
-  w.g_hi = o; o += gs; w.g_lo = o; o += gs;
-  w.wt_hi = o; o += ws; w.wt_lo = o; o += ws;
-  w.gt_hi = o; o += gts; w.gt_lo = o; o += gts;
-  w.xt_hi = o; o += xts; w.xt_lo = o; o += xts;
-  w.total = o;
-  return w;
-}
 size_t proj_tc_bwd_workspace_bytes(const b200gat_layer& L, int64_t N) {
-  return proj_tc_bwd_supported(L, N) ? plan_bwd_ws(L, N).total : 0;
+  if (!proj_tc_bwd_supported(L, N)) return 0;
+  const int64_t F = L.in_channels, Dp = L.heads * L.c_pad;
+  return blob_bytes(N, Dp) + blob_bytes(Dp, F) + blob_bytes(N, F);
 }
 
 int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   const b200gat_layer& L = a.layer;
-  const int64_t N = a.num_nodes, F = L.in_channels, Dp = L.heads * L.c_pad, Dk = pad32(Dp), Np = pad32(N);
-  const BwdWs w = plan_bwd_ws(L, N);
-  B200GAT_REQUIRE(a.workspace && a.workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "proj_bwd: workspace %zu < %zu bytes",
-                  a.workspace_bytes, w.total);
-  B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0, B200GAT_E_ALIGN, "proj_bwd: workspace must be 256-byte aligned");
-  char* base = static_cast<char*>(a.workspace);
-  auto at = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int64_t N = a.num_nodes, F = L.in_channels, Dp = L.heads * L.c_pad;
+  const size_t gb = blob_bytes(N, Dp), wb = blob_bytes(Dp, F), xb = blob_bytes(N, F);
+  const bool have_x = a.x_split != nullptr;
+  if (have_x) {
+    B200GAT_REQUIRE(a.x_split_bytes >= xb, B200GAT_E_WORKSPACE, "proj_bwd: x_split %zu < %zu bytes", a.x_split_bytes, xb);
+    B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.x_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_bwd: x_split must be 256-byte aligned");
+  }
   int rc;
+  if ((rc = check_ws(a.workspace, a.workspace_bytes, gb + wb + (have_x ? 0 : xb), "proj_bwd"))) return rc;
+  char* base = static_cast<char*>(a.workspace);
+  const Blob G = make_blob(base, N, Dp);
+  const Blob W = make_blob(base + gb, Dp, F);
+  const Blob X = make_blob(have_x ? const_cast<void*>(a.x_split) : static_cast<void*>(base + gb + wb), N, F);
+  if ((rc = launch_split(a.g_t, Dp, G, stream))) return rc;
+  if (!have_x && (rc = launch_split(a.x, a.ldx, X, stream))) return rc;
   if (a.g_x) {
-    // gX[N,F] = gT[N,Dp] · (W^T)[F,Dp]^T : K = Dp
-    if ((rc = launch_split(a.g_t, Dp, N, Dp, at(w.g_hi), at(w.g_lo), Dk, stream))) return rc;
-    if ((rc = launch_split_transpose(a.w, F, Dp, F, at(w.wt_hi), at(w.wt_lo), Dk, stream))) return rc;
+    // gX[N,F] = gT[N,Dp] · W[Dp,F] : K = Dp; B = the W planes read MN-major (F contiguous)
+    if ((rc = launch_split(a.w, F, W, stream))) return rc;
     TcGemmParams p{};
     p.C = a.g_x; p.ldc = a.ldgx;
-    if ((rc = gemm_nt<EPI_STORE>(at(w.g_hi), at(w.g_lo), at(w.wt_hi), at(w.wt_lo), N, F, Dk, p, 1, stream))) return rc;
+    if ((rc = gemm_blobs<false, true, EPI_STORE>(G, W, N, F, Dp, p, 1, stream))) return rc;
   }
-  // gW[Dp,F] = (gT^T)[Dp,N] · (X^T)[F,N]^T : K = nodes, split across CTAs, red.global.add epilogue
-  if ((rc = launch_split_transpose(a.g_t, Dp, N, Dp, at(w.gt_hi), at(w.gt_lo), Np, stream))) return rc;
-  if ((rc = launch_split_transpose(a.x, a.ldx, N, F, at(w.xt_hi), at(w.xt_lo), Np, stream))) return rc;
+  // gW[Dp,F] = gT^T · X : K = nodes; both operands MN-major straight from the row-major planes; split-K across CTAs
+  // with a red.global.add epilogue
   cudaError_t ce = cudaMemsetAsync(a.g_w, 0, size_t(Dp) * F * sizeof(float), stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "proj_bwd: memset: %s", cudaGetErrorString(ce));
   const int bn = F > 128 ? 256 : 128;
   const int64_t tiles = ceil_div(Dp, TC_BM) * ceil_div(F, bn);
-  int64_t splits = ceil_div(int64_t(sm_count()) * 2, tiles);
-  const int64_t kblocks = Np / TC_BK;
+  const int64_t kblocks = ceil_div(N, TC_BK);
+  int64_t splits = ceil_div(int64_t(sm_count()) * 2, tiles);       // ~2 work items per SM
   if (splits > kblocks / (2 * TC_KC)) splits = kblocks / (2 * TC_KC);
   if (splits < 1) splits = 1;
   TcGemmParams p{};
   p.C = a.g_w; p.ldc = F;
-  return gemm_nt<EPI_ATOMIC>(at(w.gt_hi), at(w.gt_lo), at(w.xt_hi), at(w.xt_lo), Dp, F, Np, p, static_cast<int>(splits), stream);
+  return gemm_blobs<true, true, EPI_ATOMIC>(G, X, Dp, F, N, p, static_cast<int>(splits), stream);
 }
 
 }  // namespace b200gat

@@ -6,6 +6,7 @@ namespace b200gat {
 
 bool proj_tc_fwd_supported(const b200gat_layer& L, int64_t N);
 size_t proj_tc_fwd_workspace_bytes(const b200gat_layer& L, int64_t N);
+size_t proj_tc_split_bytes(const b200gat_layer& L, int64_t N);   // the x_split blob kept from forward to backward
 int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream);
 
 // the stand-alone attention-logit pass (proj.cu), used when heads straddle the GEMM's output tiles

@@ -68,9 +68,13 @@ class GATLayerFunction(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
             ws = _workspace(ws_bytes, dev)
+            # the tensor-core operand split of x is kept for the backward's gW GEMM when a backward will run
+            split_bytes = int(lib.b200gat_proj_split_bytes(ctypes.byref(layer), n)) if any(ctx.needs_input_grad) else 0
+            x_split = _workspace(split_bytes, dev) if split_bytes else None
             pa = _abi.ProjFwdArgs(layer, n, x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
                                   a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
-                                  s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes)
+                                  s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes,
+                                  _ptr(x_split), split_bytes)
             _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
             ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
                                   bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
@@ -78,12 +82,13 @@ class GATLayerFunction(torch.autograd.Function):
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
         ctx.graph, ctx.geom, ctx.mask = graph, geom, mask
-        ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads)
+        ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads,
+                              x_split)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, fwd_out = ctx.saved_tensors
+        x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, fwd_out, x_split = ctx.saved_tensors
         graph, (f_in, c, h, concat), mask = ctx.graph, ctx.geom, ctx.mask
         lib = _abi.lib()
         dev = x.device
@@ -120,7 +125,8 @@ class GATLayerFunction(torch.autograd.Function):
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
             ws2 = _workspace(ws2_bytes, dev)
             pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
-                                  _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes)
+                                  _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes,
+                                  _ptr(x_split), x_split.numel() if x_split is not None else 0)
             _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, ctx.geom)
             _abi.launches += 2
         return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None

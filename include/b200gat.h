@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 4
+#define B200GAT_ABI_VERSION 5
 
 enum {
   B200GAT_OK = 0,
@@ -92,8 +92,13 @@ typedef struct {
   float* wh;                      /* out [N, Dp] */
   float* s_src; float* s_dst;     /* out [N, H]  (a1·Wh + b1 gathered at the source, a2·Wh + b2 at the target) */
   void* workspace; size_t workspace_bytes;
+  void* x_split; size_t x_split_bytes;   /* optional out: the tensor-core operand split of x (two fp16 planes + scale),
+                                            kept by the caller for b200gat_proj_bwd; b200gat_proj_split_bytes() bytes,
+                                            256-byte aligned.  NULL: the split lives in workspace and is redone in backward */
 } b200gat_proj_fwd_args;
 size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
+/* bytes of an x_split buffer for this geometry; 0 when the shape runs on the CUDA-core path (pass x_split = NULL) */
+size_t b200gat_proj_split_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream);
 
 /* ---- K2: fused edge forward (GAT.py:53-67) ---------------------------------------------------------------- */
@@ -188,6 +193,7 @@ typedef struct {
   float* g_x; int64_t ldgx;           /* out [N, F_in] or NULL (input does not require grad) */
   float* g_w;                         /* out [Dp, F_in] */
   void* workspace; size_t workspace_bytes;
+  const void* x_split; size_t x_split_bytes;   /* optional in: the split of x written by b200gat_proj_fwd */
 } b200gat_proj_bwd_args;
 size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);

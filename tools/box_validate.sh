@@ -1,0 +1,13 @@
+#!/bin/bash
+# Runs ON the GPU box (via tools/gpu.sh): parity tests, the default bench line, an ncu launch list and one
+# `--set full` capture of the hot kernels.  Outputs land in gpurun_out/<tag>_*.
+TAG=${1:-run}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_test.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/${TAG}_test.log
+python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+python bench.py --profile --steps 2 --warmup 3 > gpurun_out/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --profile --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu1.log 2>&1
+echo "ncu launches rc=$?"
+bash tools/box_ncu_full.sh ${TAG} ${2:-42} ${3:-14}
