@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -33,7 +33,8 @@ class ProjFwdArgs(C.Structure):
                 ("b1", C.c_void_p), ("b2", C.c_void_p),
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t)]
+                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
+                ("x_activation", C.c_int32), ("x_amax", C.c_void_p)]
 
 
 class EdgeFwdArgs(C.Structure):
@@ -41,7 +42,7 @@ class EdgeFwdArgs(C.Structure):
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p), ("bias", C.c_void_p),
                 ("mask", C.c_void_p),
                 ("out", C.c_void_p), ("ldo", C.c_int64),
-                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p)]
+                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p), ("out_amax", C.c_void_p)]
 
 
 class EdgeBwdArgs(C.Structure):
@@ -54,7 +55,8 @@ class EdgeBwdArgs(C.Structure):
                 ("a1", C.c_void_p), ("a2", C.c_void_p),
                 ("g_t", C.c_void_p), ("g_bw", C.c_void_p), ("g_a1", C.c_void_p), ("g_a2", C.c_void_p),
                 ("g_b1", C.c_void_p), ("g_b2", C.c_void_p), ("g_bias", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("out_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
 
 
 class EdgeBwdPrepArgs(C.Structure):
@@ -86,8 +88,11 @@ class ProjBwdArgs(C.Structure):
                 ("g_t", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p),
                 ("g_x", C.c_void_p), ("ldgx", C.c_int64), ("g_w", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t)]
+                ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
+                ("x_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
 
+
+ACT_NONE, ACT_ELU = 0, 1
 
 _SIGNATURES = {
     "b200gat_abi_version": (C.c_int, []),
@@ -101,6 +106,7 @@ _SIGNATURES = {
     "b200gat_proj_fwd": (C.c_int, [C.POINTER(ProjFwdArgs), C.c_void_p]),
     "b200gat_edge_fwd": (C.c_int, [C.POINTER(EdgeFwdArgs), C.c_void_p]),
     "b200gat_edge_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
+    "b200gat_edge_bwd_split_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_edge_bwd": (C.c_int, [C.POINTER(EdgeBwdArgs), C.c_void_p]),
     "b200gat_edge_bwd_prep": (C.c_int, [C.POINTER(EdgeBwdPrepArgs), C.c_void_p]),
     "b200gat_edge_bwd_csc": (C.c_int, [C.POINTER(EdgeBwdCscArgs), C.c_void_p]),

@@ -12,6 +12,8 @@
 // stays in registers, G[i] rows are gathered 128 bits per lane; gWh / g_s_src are written without atomics, g_s_dst is
 // the one cross-orientation reduction: [N,H] float atomics)  ->  bwd_finish_kernel (stream: gT in place + column sums).
 #include "common.cuh"
+#include "split_blob.cuh"
+#include "proj_tc.cuh"
 #include <math.h>
 
 namespace b200gat {
@@ -28,6 +30,7 @@ struct PrepParams {
   const float* bias;
   const float* s_dst; const float* rowmax; const float* rowsum;
   float gscale;                       // 1 or 1/H
+  int act;                            // 1: gout is d/d ELU(out) (concat_like only): G = gout * ELU'(out), needs gp
   float* gp; int64_t ldgp;            // optional padded copy: concat_like ? [N, H*Cp] : [N, Cp]
   float4* rowrec;                     // [N, H] {s_dst, rowmax, 1/(rowsum + 1e-16), Drow}
 };
@@ -58,8 +61,14 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepParams p) {
         float gv = 0.f;
         if (c < p.C) {
           gv = __ldg(g + c) * p.gscale;
-          const float o = p.concat_like ? __ldg(p.out + i * p.ldo + h * p.C + c) - __ldg(p.bias + h * p.C + c)
-                                        : __ldg(p.o_heads + (i * p.H + h) * int64_t(p.Cp) + c);
+          float o;
+          if (p.concat_like) {
+            const float pre = __ldg(p.out + i * p.ldo + h * p.C + c);
+            if (p.act) gv *= elu_grad(pre);
+            o = pre - __ldg(p.bias + h * p.C + c);
+          } else {
+            o = __ldg(p.o_heads + (i * p.H + h) * int64_t(p.Cp) + c);
+          }
           d = fmaf(gv, o, d);
         }
         if (p.gp && (p.concat_like || h == 0)) p.gp[i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c] = gv;
@@ -71,15 +80,126 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepParams p) {
   }
 }
 
+// ---- fast prep: one warp per destination ROW (all heads), for concat-like layers with D_out <= 1024 and a head
+// width that is a power of two <= 128 or a multiple of 128 channels.  All of a row's 128-bit loads are in flight
+// together; the column sums of G (g_bias) ride along in registers; with an output activation the upstream gradient is
+// first multiplied by ELU'(out) and the product is written to the gatherable copy gp. -------------------------------
+struct PrepRowsParams {
+  int64_t N;
+  int H, C, D;                        // D = H * C = D_out
+  const float* gout; int64_t ldgo;
+  const float* out; int64_t ldo;      // forward output BEFORE the activation (O = out - bias)
+  const float* bias;
+  const float* s_dst; const float* rowmax; const float* rowsum;
+  float* gp;                          // [N, D] (ACT only)
+  float4* rowrec;
+  float* g_bias;                      // [D], zero-initialised, accumulated atomically
+};
+
+template <bool ACT>
+__global__ void __launch_bounds__(256, 2) bwd_prep_rows_kernel(const PrepRowsParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int T = 8;                                    // float4 slots per lane: D <= 4 * 32 * 8 = 1024
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = p.C >> 2, DQ = p.D >> 2;
+  float4 cs[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) cs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = warp; i < p.N; i += nwarps) {
+    const float* g = p.gout + i * p.ldgo;
+    const float* o = p.out + i * p.ldo;
+    float pd[T];
+    // two halves of T/2 slots: 8 128-bit loads in flight per lane, half the live registers of a single pass
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 gv[T / 2], ov[T / 2];
+#pragma unroll
+      for (int u = 0; u < T / 2; ++u) {
+        const int q = lane + 32 * (half * (T / 2) + u);
+        if (q < DQ) {
+          gv[u] = ldg4(g + 4 * q);
+          ov[u] = ldg4(o + 4 * q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < T / 2; ++u) {
+        const int t = half * (T / 2) + u;
+        const int q = lane + 32 * t;
+        pd[t] = 0.f;
+        if (q < DQ) {
+          const float4 bv = ldg4(p.bias + 4 * q);
+          if (ACT) {
+            gv[u].x *= elu_grad(ov[u].x); gv[u].y *= elu_grad(ov[u].y);
+            gv[u].z *= elu_grad(ov[u].z); gv[u].w *= elu_grad(ov[u].w);
+            *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * q) = gv[u];
+          }
+          cs[t].x += gv[u].x; cs[t].y += gv[u].y; cs[t].z += gv[u].z; cs[t].w += gv[u].w;
+          pd[t] = gv[u].x * (ov[u].x - bv.x) + gv[u].y * (ov[u].y - bv.y) + gv[u].z * (ov[u].z - bv.z) + gv[u].w * (ov[u].w - bv.w);
+        }
+      }
+    }
+    if (Q >= 32) {                                        // a head spans Q/32 whole slots
+      const int per = Q >> 5;
+      for (int h = 0; h < p.H; ++h) {
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (t >= h * per && t < (h + 1) * per) d += pd[t];
+        d = group_sum<32>(d);
+        if (lane == 0) {
+          const int64_t item = i * p.H + h;
+          p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
+        }
+      }
+    } else {                                              // 32/Q heads per slot: width-Q segmented sums
+      const int hps = 32 / Q;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (32 * t >= DQ) break;
+        float d = pd[t];
+        for (int o2 = Q >> 1; o2 > 0; o2 >>= 1) d += __shfl_xor_sync(FULL, d, o2);
+        const int h = t * hps + lane / Q;
+        if ((lane & (Q - 1)) == 0 && h < p.H) {
+          const int64_t item = i * p.H + h;
+          p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
+        }
+      }
+    }
+  }
+  // column sums: combine the 8 warps of the CTA through shared memory, then one atomic per column per CTA
+  __shared__ float4 red[8][32];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (32 * t >= DQ) break;
+    __syncthreads();
+    red[threadIdx.x >> 5][lane] = cs[t];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float4 s = red[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
+      const int q = lane + 32 * t;
+      if (q < DQ) {
+        atomicAdd(p.g_bias + 4 * q + 0, s.x); atomicAdd(p.g_bias + 4 * q + 1, s.y);
+        atomicAdd(p.g_bias + 4 * q + 2, s.z); atomicAdd(p.g_bias + 4 * q + 3, s.w);
+      }
+    }
+  }
+}
+
 // ---- column sums of a [N, ncols] matrix (g_bias = sum_n gout[n,:]) ------------------------------------------------
+// (C, Cp): output column c reads input column (c / C) * Cp + c % C — the head-padded copy gp; C == Cp: identity
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ in, int64_t ld, int64_t N, int ncols, float* __restrict__ out) {
+colsum_kernel(const float* __restrict__ in, int64_t ld, int64_t N, int ncols, int C, int Cp, float* __restrict__ out) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
+  const int cin = (C == Cp) ? c : (c / C) * Cp + c % C;
   float s = 0.f;
   if (c < ncols)
-    for (int64_t r = int64_t(blockIdx.y) * 8 + ty; r < N; r += int64_t(gridDim.y) * 8) s += __ldg(in + r * ld + c);
+    for (int64_t r = int64_t(blockIdx.y) * 8 + ty; r < N; r += int64_t(gridDim.y) * 8) s += __ldg(in + r * ld + cin);
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && c < ncols) {
@@ -277,41 +397,111 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
   }
 }
 
-// ---- gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2 in place, plus every column sum the parameters need ---------------
+// ---- gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2, plus every column sum the parameters need.  gT is written in
+// place as fp32, or — when the projection backward runs on the tensor cores — directly as that GEMM's operand split
+// (two fp16 planes, split_blob.cuh), which saves the fp32 write and the split pass over [N, Dp].
+// The split's scale needs max|gT| BEFORE the pass: it uses the bound max|gWh| + max|g_s_src| max|a1| + max|g_s_dst| max|a2|
+// (gt_amax_kernel), at most a couple of binades loose. ----
 struct FinishParams {
   int64_t N;
   int H, Cp, Dp;
   const float* wh; const float* a1; const float* a2; const float* g_s_src; const float* g_s_dst;
-  float* g_t;                              // in: gWh, out: gT
+  float* g_t;                              // in: gWh, out: gT (fp32 mode)
   float* g_bw; float* g_a1; float* g_a2;   // [Dp] zero-initialised
   float* g_b1; float* g_b2;                // [H]  zero-initialised
+  const uint32_t* amax;                    // planes mode: [5] bit patterns {gWh, g_s_src, g_s_dst, a1, a2}
+  __half* hi; __half* lo; int64_t ldp;     // planes mode: the split blob's planes
+  float* inv_scale; uint32_t* bound_bits;  // planes mode: blob header
 };
 
+// amax[0] = max|gWh| over [n_nd], amax[1] / amax[2] = max|g_s_src| / max|g_s_dst| over [n_nh], amax[3] / amax[4] = max|a1| /
+// max|a2| over [Dp] (slots zeroed by the host)
+__global__ void __launch_bounds__(256)
+gt_amax_kernel(const float* __restrict__ gwh, int64_t n_nd, const float* __restrict__ g_s_src, const float* __restrict__ g_s_dst,
+               int64_t n_nh, const float* __restrict__ a1, const float* __restrict__ a2, int Dp, uint32_t* __restrict__ amax) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+  float m = 0.f;
+  const float4* g4 = reinterpret_cast<const float4*>(gwh);       // 16-byte aligned, n_nd % 4 == 0 (Dp = H * c_pad)
+  for (int64_t t = tid; t < (n_nd >> 2); t += nth) {
+    const float4 v = __ldg(g4 + t);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  warp_atomic_amax(amax, m);
+  float ms = 0.f, md = 0.f;
+  for (int64_t t = tid; t < n_nh; t += nth) {
+    ms = fmaxf(ms, fabsf(__ldg(g_s_src + t)));
+    md = fmaxf(md, fabsf(__ldg(g_s_dst + t)));
+  }
+  warp_atomic_amax(amax + 1, ms);
+  warp_atomic_amax(amax + 2, md);
+  if (blockIdx.x == 0) {
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = threadIdx.x; c < Dp; c += blockDim.x) {
+      m1 = fmaxf(m1, fabsf(__ldg(a1 + c)));
+      m2 = fmaxf(m2, fabsf(__ldg(a2 + c)));
+    }
+    warp_atomic_amax(amax + 3, m1);
+    warp_atomic_amax(amax + 4, m2);
+  }
+}
+
+// one thread per FOUR adjacent columns (same head: c_pad % 4 == 0), a strip of rows per blockIdx.y
+template <bool PLANES>
 __global__ void __launch_bounds__(256) bwd_finish_kernel(const FinishParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= p.Dp) return;
   const int h = c / p.Cp;
   const bool head_lead = (c - h * p.Cp) == 0;
-  const float a1c = __ldg(p.a1 + c), a2c = __ldg(p.a2 + c);
-  float sbw = 0.f, sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;
+  const float4 a1c = ldg4(p.a1 + c), a2c = ldg4(p.a2 + c);
+  float scale = 1.f;
+  if (PLANES) {
+    const float bound = __uint_as_float(p.amax[0]) + __uint_as_float(p.amax[1]) * __uint_as_float(p.amax[3]) +
+                        __uint_as_float(p.amax[2]) * __uint_as_float(p.amax[4]);
+    scale = scale_from_amax(__float_as_uint(bound));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      *p.inv_scale = 1.f / scale;
+      *p.bound_bits = __float_as_uint(bound);
+    }
+  }
+  float4 sbw = make_float4(0.f, 0.f, 0.f, 0.f), sa1 = sbw, sa2 = sbw;
+  float sb1 = 0.f, sb2 = 0.f;
   const int64_t rows_per = ceil_div(p.N, gridDim.y);
   const int64_t r0 = int64_t(blockIdx.y) * rows_per;
   const int64_t r1 = r0 + rows_per < p.N ? r0 + rows_per : p.N;
 #pragma unroll 4
   for (int64_t r = r0; r < r1; ++r) {
     const float gs = __ldg(p.g_s_src + r * p.H + h), gd = __ldg(p.g_s_dst + r * p.H + h);
-    const float w = __ldg(p.wh + r * p.Dp + c);
-    const float t = p.g_t[r * p.Dp + c] + gs * a1c + gd * a2c;
-    p.g_t[r * p.Dp + c] = t;
-    sbw += t;
-    sa1 = fmaf(gs, w, sa1);
-    sa2 = fmaf(gd, w, sa2);
+    const float4 w = ldg4(p.wh + r * p.Dp + c);
+    float4 t = *reinterpret_cast<const float4*>(p.g_t + r * p.Dp + c);
+    t.x += gs * a1c.x + gd * a2c.x;
+    t.y += gs * a1c.y + gd * a2c.y;
+    t.z += gs * a1c.z + gd * a2c.z;
+    t.w += gs * a1c.w + gd * a2c.w;
+    if (PLANES) {
+      __align__(8) __half hv[4];
+      __align__(8) __half lv[4];
+      split_half(t.x * scale, hv[0], lv[0]);
+      split_half(t.y * scale, hv[1], lv[1]);
+      split_half(t.z * scale, hv[2], lv[2]);
+      split_half(t.w * scale, hv[3], lv[3]);
+      *reinterpret_cast<uint2*>(p.hi + r * p.ldp + c) = *reinterpret_cast<const uint2*>(hv);
+      *reinterpret_cast<uint2*>(p.lo + r * p.ldp + c) = *reinterpret_cast<const uint2*>(lv);
+    } else {
+      *reinterpret_cast<float4*>(p.g_t + r * p.Dp + c) = t;
+    }
+    sbw.x += t.x; sbw.y += t.y; sbw.z += t.z; sbw.w += t.w;
+    sa1.x = fmaf(gs, w.x, sa1.x); sa1.y = fmaf(gs, w.y, sa1.y); sa1.z = fmaf(gs, w.z, sa1.z); sa1.w = fmaf(gs, w.w, sa1.w);
+    sa2.x = fmaf(gd, w.x, sa2.x); sa2.y = fmaf(gd, w.y, sa2.y); sa2.z = fmaf(gd, w.z, sa2.z); sa2.w = fmaf(gd, w.w, sa2.w);
     sb1 += gs;
     sb2 += gd;
   }
-  atomicAdd(p.g_bw + c, sbw);
-  atomicAdd(p.g_a1 + c, sa1);
-  atomicAdd(p.g_a2 + c, sa2);
+  const float bw4[4] = {sbw.x, sbw.y, sbw.z, sbw.w}, a14[4] = {sa1.x, sa1.y, sa1.z, sa1.w}, a24[4] = {sa2.x, sa2.y, sa2.z, sa2.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    atomicAdd(p.g_bw + c + u, bw4[u]);
+    atomicAdd(p.g_a1 + c + u, a14[u]);
+    atomicAdd(p.g_a2 + c + u, a24[u]);
+  }
   if (head_lead) {
     atomicAdd(p.g_b1 + h, sb1);
     atomicAdd(p.g_b2 + h, sb2);
@@ -330,7 +520,7 @@ static int launch_edge_bwd(const EdgeBwdParams& p, cudaStream_t stream) {
   return check_launch("edge_bwd_kernel");
 }
 
-struct BwdWorkspace { size_t off_rec, off_gsrc, off_gdst, off_gp, total; };
+struct BwdWorkspace { size_t off_rec, off_gsrc, off_gdst, off_amax, off_gp, total; };
 
 static BwdWorkspace plan_bwd(const b200gat_layer& L, int64_t N) {
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -339,8 +529,9 @@ static BwdWorkspace plan_bwd(const b200gat_layer& L, int64_t N) {
   w.off_rec = 0;
   w.off_gsrc = 4 * nh;
   w.off_gdst = 5 * nh;
-  w.off_gp = 6 * nh;
-  w.total = 6 * nh + up(size_t(N > 0 ? N : 1) * L.heads * L.c_pad * sizeof(float));
+  w.off_amax = 6 * nh;
+  w.off_gp = (6 * nh + 256 + (size_t(2) << 20) - 1) / (size_t(2) << 20) * (size_t(2) << 20);   // 2 MB aligned
+  w.total = w.off_gp + up(size_t(N > 0 ? N : 1) * L.heads * L.c_pad * sizeof(float));
   return w;
 }
 
@@ -358,20 +549,41 @@ static bool gout_direct(const Geom& g, const float* gout, int64_t ldgo) {
   return g.concat_like && g.C % 4 == 0 && ldgo % 4 == 0 && aligned16(gout);
 }
 
-// stage 1: row records + Drow (+ padded G copy when gp != nullptr) + g_bias column sums, over `rows` rows
+// stage 1: row records + Drow (+ padded / activation-scaled G copy when gp != nullptr) + g_bias column sums
 static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int64_t ldgo, const float* out, int64_t ldo,
                     const float* o_heads, const float* bias, const float* s_dst, const float* rowmax, const float* rowsum,
-                    float4* rowrec, float* gp, float* g_bias, cudaStream_t stream) {
+                    float4* rowrec, float* gp, float* g_bias, int act, cudaStream_t stream) {
   const Geom g = geom_of(L);
   const int64_t cap = int64_t(sm_count()) * 8;
+  B200GAT_REQUIRE(!act || (g.concat_like && gp), B200GAT_E_UNSUPPORTED,
+                  "edge_bwd: out_activation needs a concat-like layer (concat or one head) and the G copy buffer");
+  cudaError_t ce = cudaMemsetAsync(g_bias, 0, g.d_out * sizeof(float), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+  const bool vec = ldo % 4 == 0 && aligned16(out) && aligned16(bias);
+  const int Q = g.C / 4;
+  const bool fast = g.concat_like && g.C % 4 == 0 && vec && gout_direct(g, gout, ldgo) && g.d_out <= 1024 &&
+                    ((Q <= 32 && (Q & (Q - 1)) == 0) || Q % 32 == 0) && (act || gp == nullptr);
+  if (fast) {
+    PrepRowsParams pr;
+    pr.N = rows; pr.H = g.H; pr.C = g.C; pr.D = static_cast<int>(g.d_out);
+    pr.gout = gout; pr.ldgo = ldgo; pr.out = out; pr.ldo = ldo; pr.bias = bias;
+    pr.s_dst = s_dst; pr.rowmax = rowmax; pr.rowsum = rowsum; pr.gp = gp; pr.rowrec = rowrec; pr.g_bias = g_bias;
+    const int64_t want = ceil_div(rows, 8);
+    const int64_t cap_rows = int64_t(sm_count()) * 4;       // few, fat CTAs: one g_bias atomic per column per CTA
+    const int blocks = static_cast<int>(want < cap_rows ? want : cap_rows);
+    if (act) bwd_prep_rows_kernel<true><<<blocks, 256, 0, stream>>>(pr);
+    else bwd_prep_rows_kernel<false><<<blocks, 256, 0, stream>>>(pr);
+    return check_launch("bwd_prep_rows_kernel");
+  }
   PrepParams dp;
   dp.N = rows; dp.H = g.H; dp.C = g.C; dp.Cp = g.Cp; dp.concat_like = g.concat_like ? 1 : 0;
-  dp.vec = (gp == nullptr && ldo % 4 == 0 && aligned16(out) && aligned16(bias)) ? 1 : 0;
+  dp.vec = (gp == nullptr && vec) ? 1 : 0;
   B200GAT_REQUIRE(gp != nullptr || (gout_direct(g, gout, ldgo) && dp.vec), B200GAT_E_ALIGN,
                   "edge_bwd: the upstream gradient is not directly gatherable: a padded copy buffer is required");
   dp.gout = gout; dp.ldgo = ldgo; dp.out = out; dp.ldo = ldo; dp.o_heads = o_heads; dp.bias = bias;
   dp.s_dst = s_dst; dp.rowmax = rowmax; dp.rowsum = rowsum;
   dp.gscale = g.concat_like ? 1.f : 1.f / static_cast<float>(g.H);
+  dp.act = act;
   dp.gp = gp;
   dp.ldgp = g.concat_like ? g.Dp : g.Cp;
   dp.rowrec = rowrec;
@@ -379,11 +591,10 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
   bwd_prep_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(dp);
   int rc = check_launch("bwd_prep_kernel");
   if (rc) return rc;
-  cudaError_t ce = cudaMemsetAsync(g_bias, 0, g.d_out * sizeof(float), stream);
-  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
   const int64_t ysplit = ceil_div(rows, 8) < 64 ? ceil_div(rows, 8) : 64;
   dim3 grid(static_cast<unsigned>(ceil_div(g.d_out, 32)), static_cast<unsigned>(ysplit));
-  colsum_kernel<<<grid, 256, 0, stream>>>(gout, ldgo, rows, static_cast<int>(g.d_out), g_bias);
+  if (act) colsum_kernel<<<grid, 256, 0, stream>>>(gp, dp.ldgp, rows, static_cast<int>(g.d_out), g.C, g.Cp, g_bias);
+  else colsum_kernel<<<grid, 256, 0, stream>>>(gout, ldgo, rows, static_cast<int>(g.d_out), 1, 1, g_bias);
   return check_launch("colsum_kernel");
 }
 
@@ -410,10 +621,11 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
   return launch_edge_bwd<32, 4>(p, stream);
 }
 
-// stage 3: gT in place + parameter column sums over `rows` rows (outputs are overwritten, not accumulated)
+// stage 3: gT (fp32 in place, or as the operand split `gsplit` when given) + parameter column sums over `rows` rows
+// (outputs are overwritten, not accumulated).  amax: the 5 slots described at FinishParams (planes mode only).
 static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, const float* a1, const float* a2,
                       const float* g_s_src, const float* g_s_dst, float* g_t, float* g_bw, float* g_a1, float* g_a2,
-                      float* g_b1, float* g_b2, cudaStream_t stream) {
+                      float* g_b1, float* g_b2, void* gsplit, uint32_t* amax, cudaStream_t stream) {
   const Geom g = geom_of(L);
   cudaError_t ce = cudaMemsetAsync(g_bw, 0, g.Dp * sizeof(float), stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(g_a1, 0, g.Dp * sizeof(float), stream);
@@ -422,18 +634,33 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
   if (ce == cudaSuccess) ce = cudaMemsetAsync(g_b2, 0, g.H * sizeof(float), stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
   if (rows == 0) return 0;
-  FinishParams f;
+  FinishParams f{};
   f.N = rows; f.H = g.H; f.Cp = g.Cp; f.Dp = static_cast<int>(g.Dp);
   f.wh = wh; f.a1 = a1; f.a2 = a2; f.g_s_src = g_s_src; f.g_s_dst = g_s_dst; f.g_t = g_t;
   f.g_bw = g_bw; f.g_a1 = g_a1; f.g_a2 = g_a2; f.g_b1 = g_b1; f.g_b2 = g_b2;
   const int64_t cap = int64_t(sm_count()) * 8;
-  const int xblocks = static_cast<int>(ceil_div(g.Dp, 256));
+  if (gsplit) {
+    const int64_t n_nh = rows * g.H;
+    const int64_t want = ceil_div(rows * g.Dp, 256 * 16);
+    gt_amax_kernel<<<static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, stream>>>(
+        g_t, rows * g.Dp, g_s_src, g_s_dst, n_nh, a1, a2, f.Dp, amax);
+    int rc = check_launch("gt_amax_kernel");
+    if (rc) return rc;
+    const Blob B = make_blob(gsplit, rows, g.Dp);
+    f.amax = amax; f.hi = B.hi(); f.lo = B.lo(); f.ldp = B.ldp; f.inv_scale = B.inv_scale(); f.bound_bits = B.amax_bits();
+    if (B.ldp != g.Dp) {   // pad columns of the planes must be zero
+      ce = cudaMemsetAsync(B.base + BLOB_HEADER, 0, 2 * plane_bytes(rows, g.Dp), stream);
+      if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
+    }
+  }
+  const int xblocks = static_cast<int>(ceil_div(g.Dp, 4 * 256));
   int64_t ysplit = ceil_div(cap, xblocks);
   const int64_t max_y = ceil_div(rows, 16);
   if (ysplit > max_y) ysplit = max_y;
   if (ysplit < 1) ysplit = 1;
   dim3 grid(xblocks, static_cast<unsigned>(ysplit));
-  bwd_finish_kernel<<<grid, 256, 0, stream>>>(f);
+  if (gsplit) bwd_finish_kernel<true><<<grid, 256, 0, stream>>>(f);
+  else bwd_finish_kernel<false><<<grid, 256, 0, stream>>>(f);
   return check_launch("bwd_finish_kernel");
 }
 
@@ -444,6 +671,11 @@ using namespace b200gat;
 extern "C" size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* L, int64_t N) {
   if (!L || N < 0) return 0;
   return plan_bwd(*L, N).total;
+}
+
+extern "C" size_t b200gat_edge_bwd_split_bytes(const b200gat_layer* L, int64_t N) {
+  if (!L || N < 0 || !proj_tc_bwd_supported(*L, N)) return 0;
+  return blob_bytes(N, L->heads * L->c_pad);
 }
 
 extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
@@ -460,7 +692,8 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   if (N == 0) {
     cudaError_t ce = cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
-    return run_finish(L, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2, stream);
+    return run_finish(L, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
+                      nullptr, nullptr, stream);
   }
   B200GAT_REQUIRE(a->gout && a->wh && a->s_src && a->s_dst && a->rowmax && a->rowsum && a->a1 && a->a2 && a->g_t &&
                   a->bias && a->workspace, B200GAT_E_NULL, "edge_bwd: NULL pointer");
@@ -468,7 +701,8 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
                   "edge_bwd: forward output (out / o_heads) missing");
   B200GAT_REQUIRE(!a->mask || a->graph.ceid, B200GAT_E_NULL, "edge_bwd: mask needs graph.ceid");
   B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd: leading dimension < D_out");
-  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t), B200GAT_E_ALIGN, "edge_bwd: wh / g_t must be 16-byte aligned");
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
+                  "edge_bwd: wh / g_t / a1 / a2 must be 16-byte aligned");
   const BwdWorkspace w = plan_bwd(L, N);
   B200GAT_REQUIRE(a->workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "edge_bwd: workspace %zu < %zu bytes",
                   a->workspace_bytes, w.total);
@@ -479,12 +713,23 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   float* g_s_src = reinterpret_cast<float*>(base + w.off_gsrc);
   float* g_s_dst = reinterpret_cast<float*>(base + w.off_gdst);
   float* gp = reinterpret_cast<float*>(base + w.off_gp);
-  cudaError_t ce = cudaMemsetAsync(g_s_dst, 0, size_t(N) * g.H * sizeof(float), stream);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(base + w.off_amax);
+  // zero g_s_dst (accumulated atomically) and, right behind it, the amax slots
+  cudaError_t ce = cudaMemsetAsync(g_s_dst, 0, w.off_gp - w.off_gdst, stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
-  const bool direct = gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
+  const int act = a->out_activation;
+  B200GAT_REQUIRE(act == ACT_NONE || act == ACT_ELU, B200GAT_E_UNSUPPORTED, "edge_bwd: unknown out_activation %d", act);
+  void* gsplit = a->g_t_split;
+  if (gsplit) {
+    const size_t need = blob_bytes(N, g.Dp);
+    B200GAT_REQUIRE(a->g_t_split_bytes >= need, B200GAT_E_WORKSPACE, "edge_bwd: g_t_split %zu < %zu bytes", a->g_t_split_bytes, need);
+    B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(gsplit) & 255u) == 0, B200GAT_E_ALIGN, "edge_bwd: g_t_split must be 256-byte aligned");
+  }
+  // with an output activation the gathered rows are gout * ELU'(out): always the copy
+  const bool direct = !act && gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
                       aligned16(a->bias);
   if ((rc = run_prep(L, N, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum, rowrec,
-                     direct ? nullptr : gp, a->g_bias, stream)))
+                     direct ? nullptr : gp, a->g_bias, act, stream)))
     return rc;
   const float* grows = direct ? a->gout : gp;
   const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
@@ -492,7 +737,8 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
                     a->g_t, g_s_src, g_s_dst, stream)))
     return rc;
-  return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2, stream);
+  return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
+                    gsplit, amax, stream);
 }
 
 // ---- staged entry points (destination-row partitioned multi-GPU execution: the caller runs the collectives between
@@ -515,7 +761,7 @@ extern "C" int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* 
   B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd_prep: leading dimension < D_out");
   B200GAT_REQUIRE(aligned16(a->rowrec), B200GAT_E_ALIGN, "edge_bwd_prep: rowrec must be 16-byte aligned");
   return run_prep(a->layer, a->num_rows, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum,
-                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, stream);
+                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, ACT_NONE, stream);
 }
 
 extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream_) {
@@ -544,6 +790,8 @@ extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, vo
   B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2, B200GAT_E_NULL, "edge_bwd_finish: NULL output");
   B200GAT_REQUIRE(a->num_rows == 0 || (a->wh && a->a1 && a->a2 && a->g_s_src && a->g_s_dst && a->g_t), B200GAT_E_NULL,
                   "edge_bwd_finish: NULL pointer");
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
+                  "edge_bwd_finish: wh / g_t / a1 / a2 must be 16-byte aligned");
   return run_finish(a->layer, a->num_rows, a->wh, a->a1, a->a2, a->g_s_src, a->g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2,
-                    a->g_b1, a->g_b2, stream);
+                    a->g_b1, a->g_b2, nullptr, nullptr, stream);
 }

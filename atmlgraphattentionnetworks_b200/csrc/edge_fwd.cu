@@ -13,6 +13,7 @@
 // 128-bit slices of Wh[j,h,:] (ld.global.nc.v4.f32) into NV float4 accumulators.  The softmax is online per chunk of
 // G edges (running max / sum; only rows longer than G ever rescale), so every row is walked exactly once.
 #include "common.cuh"
+#include "split_blob.cuh"
 #include <math.h>
 
 namespace b200gat {
@@ -27,6 +28,7 @@ struct EdgeFwdParams {
   float* rowmax; float* rowsum; float* o_heads;
   int heads_mode;   // 1: write per-head aggregate to o_heads (mean over heads done by head_mean_kernel)
   int vec_out;      // 1: out rows / head offsets are 16-byte aligned -> float4 stores
+  uint32_t* out_amax;   // optional: bit pattern of max|out| (atomicMax; zeroed by the host)
 };
 
 template <int G, int NV, bool HAS_MASK>
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) off[v] = 4 * ((gl + v * G < Q) ? gl + v * G : Q - 1);
 
+  float amax = 0.f;
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
     const int64_t item = base + gi;
     const bool valid = item < p.items;
@@ -148,31 +151,42 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
         float* dst = p.out + i * p.ldo + h * p.C + c;
         if (p.vec_out) {
           const float4 bb = ldg4(b);
-          *reinterpret_cast<float4*>(dst) = make_float4(o.x + bb.x, o.y + bb.y, o.z + bb.z, o.w + bb.w);
+          const float4 r = make_float4(o.x + bb.x, o.y + bb.y, o.z + bb.z, o.w + bb.w);
+          *reinterpret_cast<float4*>(dst) = r;
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
         } else {
           const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (c + u < p.C) dst[u] = ov[u] + __ldg(b + u);
+            if (c + u < p.C) {
+              const float r = ov[u] + __ldg(b + u);
+              dst[u] = r;
+              amax = fmaxf(amax, fabsf(r));
+            }
         }
       }
     }
   }
+  if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
 }
 
 // concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c]
 __global__ void __launch_bounds__(256)
 head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bias, float* __restrict__ out,
-                 int64_t ldo, int64_t N, int H, int C, int Cp) {
+                 int64_t ldo, int64_t N, int H, int C, int Cp, uint32_t* __restrict__ out_amax) {
   const int64_t total = N * C;
+  float amax = 0.f;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
     const int64_t i = t / C;
     const int c = static_cast<int>(t - i * C);
     const float* src = o_heads + i * int64_t(H) * Cp + c;
     float s = 0.f;
     for (int h = 0; h < H; ++h) s += __ldg(src + h * Cp);
-    out[i * ldo + c] = s / static_cast<float>(H) + __ldg(bias + c);
+    const float r = s / static_cast<float>(H) + __ldg(bias + c);
+    out[i * ldo + c] = r;
+    amax = fmaxf(amax, fabsf(r));
   }
+  if (out_amax) warp_atomic_amax(out_amax, amax);
 }
 
 template <int G, int NV>
@@ -221,6 +235,11 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   p.out = a->out; p.ldo = a->ldo; p.rowmax = a->rowmax; p.rowsum = a->rowsum; p.o_heads = a->o_heads;
   p.heads_mode = heads_mode ? 1 : 0;
   p.vec_out = (!heads_mode && C % 4 == 0 && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
+  p.out_amax = a->out_amax;
+  if (a->out_amax) {
+    cudaError_t ce = cudaMemsetAsync(a->out_amax, 0, sizeof(uint32_t), stream);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_fwd: memset: %s", cudaGetErrorString(ce));
+  }
 
   const int Q = Cp / 4;
   if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, stream);
@@ -237,7 +256,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
     const int64_t want = ceil_div(total, 256);
     const int64_t cap = int64_t(sm_count()) * 8;
     head_mean_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(a->o_heads, a->bias, a->out, a->ldo,
-                                                                                   N, H, C, Cp);
+                                                                                   N, H, C, Cp, a->out_amax);
     rc = check_launch("head_mean_kernel");
   }
   return rc;

@@ -2,9 +2,10 @@
 // D = 7, ...) and as the reduction engine for gW (split-K over the node dimension).
 //   C[m, n] (+)= sum_k A(m, k) * B(k, n) (+ bias[n])
 //   A(m,k) = A_KMAJOR ? A[m*lda + k] : A[k*lda + m]        B(k,n) = B_KMAJOR ? B[n*ldb + k] : B[k*ldb + n]
+//   act_a / act_b = ACT_ELU applies the fused inter-layer activation to the operand as it is loaded (the operand is x)
 // 64x64x16 tiles, 256 threads, 4x4 register micro-tile, true fp32 FMA (matches torch's allow_tf32=False default).
 #pragma once
-#include "common.cuh"
+#include "split_blob.cuh"
 
 namespace b200gat {
 
@@ -14,7 +15,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, bool ATOMIC>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                  float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int64_t M, int64_t N, int64_t K,
-                 int64_t k_per_split) {
+                 int64_t k_per_split, int act_a, int act_b) {
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   const int tid = threadIdx.x;
@@ -36,7 +37,8 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t gk = k0 + kk + u;
-        As[kk + u][m] = (gm < M && gk < kend) ? A[gm * lda + gk] : 0.f;
+        float v = (gm < M && gk < kend) ? A[gm * lda + gk] : 0.f;
+        As[kk + u][m] = act_a ? elu_fwd(v) : v;
       }
     } else {
       const int kk = tid >> 4, m = (tid & 15) * 4;
@@ -44,7 +46,8 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t gm = m0 + m + u;
-        As[kk][m + u] = (gm < M && gk < kend) ? A[gk * lda + gm] : 0.f;
+        float v = (gm < M && gk < kend) ? A[gk * lda + gm] : 0.f;
+        As[kk][m + u] = act_a ? elu_fwd(v) : v;
       }
     }
     // ---- stage B tile (GK x GN) ----
@@ -54,7 +57,8 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t gk = k0 + kk + u;
-        Bs[kk + u][n] = (gn < N && gk < kend) ? B[gn * ldb + gk] : 0.f;
+        float v = (gn < N && gk < kend) ? B[gn * ldb + gk] : 0.f;
+        Bs[kk + u][n] = act_b ? elu_fwd(v) : v;
       }
     } else {
       const int kk = tid >> 4, n = (tid & 15) * 4;
@@ -62,7 +66,8 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t gn = n0 + n + u;
-        Bs[kk][n + u] = (gn < N && gk < kend) ? B[gk * ldb + gn] : 0.f;
+        float v = (gn < N && gk < kend) ? B[gk * ldb + gn] : 0.f;
+        Bs[kk][n + u] = act_b ? elu_fwd(v) : v;
       }
     }
     __syncthreads();
@@ -99,17 +104,18 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 inline int gemm_simt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                     const float* bias, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t stream) {
+                     const float* bias, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t stream,
+                     int act_a = ACT_NONE, int act_b = ACT_NONE) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid(static_cast<unsigned>(ceil_div(M, GM)), static_cast<unsigned>(ceil_div(N, GN)), 1);
   if (splits <= 1) {
-    gemm_simt_kernel<A_KMAJOR, B_KMAJOR, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, bias, M, N, K, K);
+    gemm_simt_kernel<A_KMAJOR, B_KMAJOR, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, bias, M, N, K, K, act_a, act_b);
   } else {
     int64_t kps = ceil_div(ceil_div(K, splits), GK) * GK;
     grid.z = static_cast<unsigned>(ceil_div(K, kps));
     cudaError_t e = cudaMemsetAsync(C, 0, size_t(M) * ldc * sizeof(float), stream);   // caller passes ldc == N here
     if (e != cudaSuccess) return fail(static_cast<int>(e), "gemm_simt: memset: %s", cudaGetErrorString(e));
-    gemm_simt_kernel<A_KMAJOR, B_KMAJOR, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, nullptr, M, N, K, kps);
+    gemm_simt_kernel<A_KMAJOR, B_KMAJOR, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, nullptr, M, N, K, kps, act_a, act_b);
   }
   return check_launch("gemm_simt");
 }

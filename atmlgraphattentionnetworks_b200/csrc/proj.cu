@@ -77,8 +77,10 @@ extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->ldx >= F, B200GAT_E_SHAPE, "proj_fwd: ldx < in_channels");
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
                   "proj_fwd: wh/a1/a2 must be 16-byte aligned");
+  B200GAT_REQUIRE(a->x_activation == ACT_NONE || a->x_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
+                  "proj_fwd: unknown x_activation %d", a->x_activation);
   if (proj_tc_fwd_supported(L, N)) return proj_tc_fwd(*a, stream);
-  rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream);
+  rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream, a->x_activation);
   if (rc) return rc;
   return launch_logits(*a, stream);
 }
@@ -102,9 +104,12 @@ extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
     if (e != cudaSuccess) return fail(static_cast<int>(e), "proj_bwd: memset: %s", cudaGetErrorString(e));
     return 0;
   }
-  B200GAT_REQUIRE(a->g_t && a->x, B200GAT_E_NULL, "proj_bwd: NULL pointer");
+  B200GAT_REQUIRE(a->x_activation == ACT_NONE || a->x_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
+                  "proj_bwd: unknown x_activation %d", a->x_activation);
+  B200GAT_REQUIRE((a->g_t || a->g_t_split) && (a->x || a->x_split), B200GAT_E_NULL, "proj_bwd: NULL pointer");
   B200GAT_REQUIRE(a->ldx >= F && (!a->g_x || a->ldgx >= F), B200GAT_E_SHAPE, "proj_bwd: leading dimension < in_channels");
   if (proj_tc_bwd_supported(L, N)) return proj_tc_bwd(*a, stream);
+  B200GAT_REQUIRE(a->g_t && a->x, B200GAT_E_NULL, "proj_bwd: the CUDA-core path needs fp32 g_t and x");
   if (a->g_x) {
     rc = gemm_simt<true, false>(a->g_t, Dp, a->w, F, a->g_x, a->ldgx, nullptr, N, F, Dp, 1, stream);
     if (rc) return rc;
@@ -115,5 +120,6 @@ extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
   const int64_t max_splits = ceil_div(N, 256);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  return gemm_simt<false, false>(a->g_t, Dp, a->x, a->ldx, a->g_w, F, nullptr, Dp, F, N, static_cast<int>(splits), stream);
+  return gemm_simt<false, false>(a->g_t, Dp, a->x, a->ldx, a->g_w, F, nullptr, Dp, F, N, static_cast<int>(splits), stream,
+                                 ACT_NONE, a->x_activation);
 }

@@ -32,8 +32,8 @@
 //               fused attention-logit reductions s_src = <Wh_h, a1_h> + b1_h, s_dst = <Wh_h, a2_h> + b2_h, fp32 store
 //               (or red.global.add for the split-K gW reduction) — overlapping the next item's first chunks
 #include "proj_tc.cuh"
+#include "split_blob.cuh"
 #include <cuda.h>
-#include <cuda_fp16.h>
 #include <mutex>
 #include <stdlib.h>
 
@@ -416,27 +416,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ split pre-passes
-// A "split blob" holds one operand tensor [rows, cols] as fp16 planes:
-//   +0    float    inv_scale (1/s)        +4  uint32  max|T| bit pattern (scratch of the amax pass)
-//   +256  __half   hi[rows, ldp]          +256 + plane_bytes   __half lo[rows, ldp]        ldp = round_up(cols, 8)
-constexpr size_t BLOB_HEADER = 256;
-static inline int64_t pad8(int64_t v) { return (v + 7) / 8 * 8; }
-static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-static inline size_t plane_bytes(int64_t rows, int64_t cols) { return up256(size_t(rows) * size_t(pad8(cols)) * 2); }
-static inline size_t blob_bytes(int64_t rows, int64_t cols) { return BLOB_HEADER + 2 * plane_bytes(rows, cols); }
-
-struct Blob {
-  uint8_t* base; int64_t rows, cols, ldp;
-  float* inv_scale() const { return reinterpret_cast<float*>(base); }
-  uint32_t* amax_bits() const { return reinterpret_cast<uint32_t*>(base) + 1; }
-  __half* hi() const { return reinterpret_cast<__half*>(base + BLOB_HEADER); }
-  __half* lo() const { return reinterpret_cast<__half*>(base + BLOB_HEADER + plane_bytes(rows, cols)); }
-};
-static inline Blob make_blob(void* base, int64_t rows, int64_t cols) {
-  return Blob{static_cast<uint8_t*>(base), rows, cols, pad8(cols)};
-}
-
 // max |src| as a uint bit pattern (non-negative floats order like unsigned integers; NaN sorts above inf and is kept)
+// (no activation variant: |ELU(x)| <= |x|, so max|x| is a valid — at most slightly loose — bound for the scale)
 __global__ void __launch_bounds__(256)
 amax_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, uint32_t* __restrict__ out) {
   uint32_t m = 0;
@@ -467,18 +448,8 @@ amax_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t col
   }
 }
 
-// power-of-two scale putting max|T| * s in [2^14, 2^15) (fp16 max is 65504); 1 for an all-zero or non-finite tensor
-__device__ __forceinline__ float scale_from_amax(uint32_t bits) {
-  const float a = __uint_as_float(bits);
-  if (!(a > 0.f) || !(a <= 3.4028234e38f)) return 1.f;
-  int e;
-  frexpf(a, &e);                 // a = m * 2^e, m in [0.5, 1)
-  int sh = 15 - e;
-  if (sh > 126) sh = 126;
-  return ldexpf(1.f, sh);
-}
-
 // src [rows, cols] (row stride ld) -> hi / lo fp16 planes [rows, ldp]; pad columns [cols, ldp) are zero
+template <int ACT>
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, __half* __restrict__ hi,
              __half* __restrict__ lo, int64_t ldp, const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale) {
@@ -500,11 +471,7 @@ split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t co
     __align__(16) __half h[8];
     __align__(16) __half l[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = v[j] * s;
-      h[j] = __float2half_rn(x);
-      l[j] = __float2half_rn(x - __half2float(h[j]));
-    }
+    for (int j = 0; j < 8; ++j) split_half((ACT == ACT_ELU ? elu_fwd(v[j]) : v[j]) * s, h[j], l[j]);
     *reinterpret_cast<uint4*>(hi + r * ldp + c0) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + r * ldp + c0) = *reinterpret_cast<const uint4*>(l);
   }
@@ -544,17 +511,25 @@ static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int64_t co
   return 0;
 }
 
-static int launch_split(const float* src, int64_t ld, const Blob& b, cudaStream_t stream) {
-  cudaError_t ce = cudaMemsetAsync(b.base, 0, 8, stream);
-  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "proj_tc: memset: %s", cudaGetErrorString(ce));
+// split `src` (through the activation `act`) into blob b; amax_hint: device bound of max|src| (skips the amax pass)
+static int launch_split(const float* src, int64_t ld, const Blob& b, cudaStream_t stream, int act = ACT_NONE,
+                        const uint32_t* amax_hint = nullptr) {
   const int64_t cap = int64_t(sm_count()) * 8;
-  const int64_t want_a = ceil_div(b.rows * b.cols, 256 * 4);
-  amax_kernel<<<static_cast<int>(want_a < cap ? (want_a > 0 ? want_a : 1) : cap), 256, 0, stream>>>(src, ld, b.rows, b.cols, b.amax_bits());
-  int rc = check_launch("amax_kernel");
-  if (rc) return rc;
+  int rc;
+  if (!amax_hint) {
+    cudaError_t ce = cudaMemsetAsync(b.base, 0, 8, stream);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "proj_tc: memset: %s", cudaGetErrorString(ce));
+    const int64_t want_a = ceil_div(b.rows * b.cols, 256 * 4);
+    amax_kernel<<<static_cast<int>(want_a < cap ? (want_a > 0 ? want_a : 1) : cap), 256, 0, stream>>>(src, ld, b.rows, b.cols, b.amax_bits());
+    if ((rc = check_launch("amax_kernel"))) return rc;
+    amax_hint = b.amax_bits();
+  }
   const int64_t want_s = ceil_div(b.rows * (b.ldp >> 3), 256);
-  split_kernel<<<static_cast<int>(want_s < 2 * cap ? (want_s > 0 ? want_s : 1) : 2 * cap), 256, 0, stream>>>(
-      src, ld, b.rows, b.cols, b.hi(), b.lo(), b.ldp, b.amax_bits(), b.inv_scale());
+  const int blocks = static_cast<int>(want_s < 2 * cap ? (want_s > 0 ? want_s : 1) : 2 * cap);
+  if (act == ACT_ELU)
+    split_kernel<ACT_ELU><<<blocks, 256, 0, stream>>>(src, ld, b.rows, b.cols, b.hi(), b.lo(), b.ldp, amax_hint, b.inv_scale());
+  else
+    split_kernel<ACT_NONE><<<blocks, 256, 0, stream>>>(src, ld, b.rows, b.cols, b.hi(), b.lo(), b.ldp, amax_hint, b.inv_scale());
   return check_launch("split_kernel");
 }
 
@@ -647,7 +622,7 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   char* base = static_cast<char*>(a.workspace);
   const Blob X = make_blob(keep ? a.x_split : static_cast<void*>(base), N, F);
   const Blob W = make_blob(base + (keep ? 0 : xb), Dp, F);
-  if ((rc = launch_split(a.x, a.ldx, X, stream))) return rc;
+  if ((rc = launch_split(a.x, a.ldx, X, stream, a.x_activation, a.x_amax))) return rc;
   if ((rc = launch_split(a.w, F, W, stream))) return rc;
   TcGemmParams p{};
   p.C = a.wh; p.ldc = Dp; p.bias = a.bw;
@@ -676,14 +651,21 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
     B200GAT_REQUIRE(a.x_split_bytes >= xb, B200GAT_E_WORKSPACE, "proj_bwd: x_split %zu < %zu bytes", a.x_split_bytes, xb);
     B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.x_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_bwd: x_split must be 256-byte aligned");
   }
+  const bool have_g = a.g_t_split != nullptr;
+  if (have_g) {
+    B200GAT_REQUIRE(a.g_t_split_bytes >= gb, B200GAT_E_WORKSPACE, "proj_bwd: g_t_split %zu < %zu bytes", a.g_t_split_bytes, gb);
+    B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.g_t_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_bwd: g_t_split must be 256-byte aligned");
+  }
+  B200GAT_REQUIRE((have_g || a.g_t) && (have_x || a.x), B200GAT_E_NULL, "proj_bwd: NULL pointer");
   int rc;
-  if ((rc = check_ws(a.workspace, a.workspace_bytes, gb + wb + (have_x ? 0 : xb), "proj_bwd"))) return rc;
+  // workspace layout: [W blob][gT blob unless g_t_split][x blob unless x_split]
+  if ((rc = check_ws(a.workspace, a.workspace_bytes, wb + (have_g ? 0 : gb) + (have_x ? 0 : xb), "proj_bwd"))) return rc;
   char* base = static_cast<char*>(a.workspace);
-  const Blob G = make_blob(base, N, Dp);
-  const Blob W = make_blob(base + gb, Dp, F);
-  const Blob X = make_blob(have_x ? const_cast<void*>(a.x_split) : static_cast<void*>(base + gb + wb), N, F);
-  if ((rc = launch_split(a.g_t, Dp, G, stream))) return rc;
-  if (!have_x && (rc = launch_split(a.x, a.ldx, X, stream))) return rc;
+  const Blob W = make_blob(base, Dp, F);
+  const Blob G = make_blob(have_g ? const_cast<void*>(a.g_t_split) : static_cast<void*>(base + wb), N, Dp);
+  const Blob X = make_blob(have_x ? const_cast<void*>(a.x_split) : static_cast<void*>(base + wb + (have_g ? 0 : gb)), N, F);
+  if (!have_g && (rc = launch_split(a.g_t, Dp, G, stream))) return rc;
+  if (!have_x && (rc = launch_split(a.x, a.ldx, X, stream, a.x_activation))) return rc;
   if (a.g_x) {
     // gX[N,F] = gT[N,Dp] · W[Dp,F] : K = Dp; B = the W planes read MN-major (F contiguous)
     if ((rc = launch_split(a.w, F, W, stream))) return rc;

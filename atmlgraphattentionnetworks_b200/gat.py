@@ -41,11 +41,21 @@ def _workspace(nbytes, device):
 
 
 class GATLayerFunction(torch.autograd.Function):
-    """x [N,F], packed padded parameters (W [Dp,F], bw/a1/a2 [Dp], b1/b2 [H], bias [D_out]) -> out [N, D_out]."""
+    """x [N,F], packed padded parameters (W [Dp,F], bw/a1/a2 [Dp], b1/b2 [H], bias [D_out]) -> (out [N, D_out], out_amax).
+
+    fuse = (act_in, act_out, x_amax) describes the layer boundary fusions (include/b200gat.h, B200GAT_ACT_*):
+      act_in   the layer consumes ELU(x): x is the PRE-activation output of the previous layer
+      act_out  the returned `out` is pre-activation and its consumer applies ELU while loading it; the gradient that
+               comes back is therefore d/d ELU(out) and the backward multiplies it by ELU'(out).  Only the internal
+               compositions (GATStack, GATNet) set this, and they hand the tensor to nothing but an act_in layer.
+      x_amax   int32[1] device word: bound of max|x| from the producing layer (skips one pass over x)
+    out_amax (int32[1], bit pattern of max|out|) is returned for the next layer's x_amax.
+    """
 
     @staticmethod
-    def forward(ctx, x, w, bw, a1, a2, b1, b2, bias, graph, geom, mask):
+    def forward(ctx, x, w, bw, a1, a2, b1, b2, bias, graph, geom, mask, fuse):
         f_in, c, h, concat = geom
+        act_in, act_out, x_amax = fuse
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
@@ -64,6 +74,7 @@ class GATLayerFunction(torch.autograd.Function):
         rowmax = torch.empty((n, h), **f32)
         rowsum = torch.empty((n, h), **f32)
         o_heads = torch.empty((n, dp), **f32) if heads_mode else None
+        out_amax = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
@@ -74,22 +85,24 @@ class GATLayerFunction(torch.autograd.Function):
             pa = _abi.ProjFwdArgs(layer, n, x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
                                   a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
                                   s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes,
-                                  _ptr(x_split), split_bytes)
+                                  _ptr(x_split), split_bytes, _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(x_amax))
             _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
             ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
                                   bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
-                                  rowsum.data_ptr(), _ptr(o_heads))
+                                  rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr())
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
-        ctx.graph, ctx.geom, ctx.mask = graph, geom, mask
+        ctx.graph, ctx.geom, ctx.mask, ctx.act = graph, geom, mask, (bool(act_in), bool(act_out))
         ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads,
                               x_split)
-        return out
+        ctx.mark_non_differentiable(out_amax)
+        return out, out_amax
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _g_amax):
         x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, fwd_out, x_split = ctx.saved_tensors
         graph, (f_in, c, h, concat), mask = ctx.graph, ctx.geom, ctx.mask
+        act_in, act_out = ctx.act
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
@@ -114,22 +127,27 @@ class GATLayerFunction(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws_bytes = int(lib.b200gat_edge_bwd_workspace_bytes(ctypes.byref(layer), n))
             ws = _workspace(ws_bytes, dev)
+            # gT goes straight into the tensor-core operand format when the projection backward runs there
+            gs_bytes = int(lib.b200gat_edge_bwd_split_bytes(ctypes.byref(layer), n))
+            g_split = _workspace(gs_bytes, dev) if gs_bytes else None
             ea = _abi.EdgeBwdArgs(layer, graph.c_struct(), gout.data_ptr(), d_out,
                                   None if heads_mode else fwd_out.data_ptr(), d_out,
                                   fwd_out.data_ptr() if heads_mode else None, bias.data_ptr(),
                                   wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(), rowmax.data_ptr(),
                                   rowsum.data_ptr(), _ptr(mask), a1.data_ptr(), a2.data_ptr(),
                                   g_t.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(), g_a2.data_ptr(),
-                                  g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes)
+                                  g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes,
+                                  _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g_split), gs_bytes)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
             ws2 = _workspace(ws2_bytes, dev)
             pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
                                   _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes,
-                                  _ptr(x_split), x_split.numel() if x_split is not None else 0)
+                                  _ptr(x_split), x_split.numel() if x_split is not None else 0,
+                                  _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes)
             _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, ctx.geom)
             _abi.launches += 2
-        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None
+        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None
 
 
 class GraphAttentionLayer(torch.nn.Module):
@@ -190,6 +208,19 @@ class GraphAttentionLayer(torch.nn.Module):
         return keep.to(torch.float32).mul_(1.0 / (1.0 - p))
 
     def forward(self, x, edge_index, graph=None):
+        """GAT.py:37 — forward(x, edge_index) -> [N, H*C] (concat) or [N, C]."""
+        return self.forward_fused(x, edge_index, graph=graph)[0]
+
+    def can_fuse_activation_out(self):
+        """the ELU that follows this layer can be deferred to its consumer (concat-like layers only, edge_bwd contract)"""
+        return bool(self.concat) or self.num_heads == 1
+
+    def forward_fused(self, x, edge_index, graph=None, act_in=False, act_out=False, x_amax=None):
+        """Internal composition entry (GATStack / GATNet): -> (out, out_amax).  act_in: x is a pre-activation tensor
+        produced by a layer called with act_out, and ELU(x) is what is projected; act_out: return the pre-activation
+        output (see GATLayerFunction).  Never hand an act_out tensor to anything but an act_in layer."""
+        if act_out and not self.can_fuse_activation_out():
+            raise ValueError("act_out needs a concat-like layer")
         if not x.is_cuda:
             raise _abi.B200GatError("GraphAttentionLayer runs on CUDA tensors only (B200-native path, no CPU fallback)")
         if x.dtype != torch.float32:
@@ -204,4 +235,5 @@ class GraphAttentionLayer(torch.nn.Module):
         mask = self._dropout_mask(graph.num_edges, x.device)
         w, bw, a1, a2, b1, b2 = self._packed()
         geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
-        return GATLayerFunction.apply(x, w, bw, a1, a2, b1, b2, self.bias, graph, geom, mask)
+        return GATLayerFunction.apply(x, w, bw, a1, a2, b1, b2, self.bias, graph, geom, mask,
+                                      (bool(act_in), bool(act_out), x_amax))

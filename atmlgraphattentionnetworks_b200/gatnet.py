@@ -1,11 +1,15 @@
 """Drop-in `GATNet` (reference: GATNet.py:13-87), GAT branch on the B200-native layer.
 
 Constructor table and forward glue follow GATNet.py:17-37 / :60-87 exactly (same attribute names => same
-state_dict keys).  The glue ops (feature dropout, ELU, per-graph mean readout, lin1/lin2, log_softmax) stay PyTorch
-CUDA ops in this round (SURVEY.md §8f row 2 lists their fusion as a next row); the layer is the hot path.
+state_dict keys).  The ELU between two GAT layers is fused into the layer boundary (the producer keeps its
+pre-activation output, the consumer applies ELU while loading its operand, the producer's backward applies ELU' — see
+include/b200gat.h B200GAT_ACT_*) whenever no feature dropout sits between them; the other glue ops (feature dropout,
+per-graph mean readout, lin1/lin2, log_softmax) are PyTorch CUDA ops.
 The GCN branch (GATNet.py:38-58) is a third-party comparison baseline (torch_geometric.nn.GCNConv) and is only
 available when torch_geometric is installed.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -66,12 +70,20 @@ class GATNet(torch.nn.Module):
         x, edge_index = data.x, data.edge_index
         act = F.relu if self.model_name == "GCN" else F.elu
         if self.dataset_name == "CIFAR10":                     # GATNet.py:62-76
-            x = act(self.conv1(x, edge_index))
-            x = act(self.conv2(x, edge_index))
+            if self.model_name == "GAT":                       # elu(conv1) fused into the conv1 -> conv2 boundary
+                x, amax = self.conv1.forward_fused(x, edge_index, act_out=True)
+                x = act(self.conv2.forward_fused(x, edge_index, act_in=True, x_amax=amax)[0])
+            else:
+                x = act(self.conv1(x, edge_index))
+                x = act(self.conv2(x, edge_index))
             x = segment_mean(x, data.batch)
             x = F.relu(self.lin1(x))
             return F.log_softmax(self.lin2(x), dim=1)
         x = F.dropout(x, p=0.6, training=self.training)        # GATNet.py:78
+        if self.model_name == "GAT" and not self.training:     # no feature dropout in between: fuse elu(conv1)
+            x, amax = self.conv1.forward_fused(x, edge_index, act_out=True)
+            x = self.conv2.forward_fused(x, edge_index, act_in=True, x_amax=amax)[0]
+            return F.log_softmax(x, dim=1)
         x = act(self.conv1(x, edge_index))
         x = F.dropout(x, p=0.6, training=self.training)
         x = self.conv2(x, edge_index)
@@ -88,8 +100,12 @@ class GATStack(torch.nn.Module):
             [GraphAttentionLayer(i, o, num_heads=h, concat=c, dropout=dropout) for (i, o, h, c) in spec])
 
     def forward(self, x, edge_index):
+        pending, amax = False, None      # pending: x is a pre-activation tensor whose ELU the next layer applies
+        last = len(self.convs) - 1
         for k, conv in enumerate(self.convs):
-            x = conv(x, edge_index)
-            if k + 1 < len(self.convs):
+            fuse_out = k < last and conv.can_fuse_activation_out() and not os.environ.get("B200GAT_NO_FUSE_ACT")
+            x, amax = conv.forward_fused(x, edge_index, act_in=pending, act_out=fuse_out, x_amax=amax if pending else None)
+            pending = fuse_out
+            if k < last and not fuse_out:
                 x = F.elu(x)
         return x

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 5
+#define B200GAT_ABI_VERSION 6
 
 enum {
   B200GAT_OK = 0,
@@ -42,6 +42,12 @@ enum {
   B200GAT_E_WORKSPACE = -4,  /* workspace too small */
   B200GAT_E_UNSUPPORTED = -5
 };
+
+/* Activations between layers (GATNet.py:63-75 applies F.elu to every hidden layer's output) can be fused into the
+ * layer boundary: the PRODUCING layer keeps its pre-activation output (out_activation in b200gat_edge_bwd: the upstream
+ * gradient is d/d act(out) and is multiplied by act'(out) on the fly), the CONSUMING layer applies the activation
+ * while it loads x (x_activation in b200gat_proj_fwd / b200gat_proj_bwd).  act(out) is never written to memory. */
+enum { B200GAT_ACT_NONE = 0, B200GAT_ACT_ELU = 1 };
 
 /* Destination-sorted CSR (+ source-sorted CSC) of [edge_index ; self loops].  All arrays int32 on device. */
 typedef struct {
@@ -95,6 +101,9 @@ typedef struct {
   void* x_split; size_t x_split_bytes;   /* optional out: the tensor-core operand split of x (two fp16 planes + scale),
                                             kept by the caller for b200gat_proj_bwd; b200gat_proj_split_bytes() bytes,
                                             256-byte aligned.  NULL: the split lives in workspace and is redone in backward */
+  int32_t x_activation;                  /* B200GAT_ACT_*: the projection consumes act(x) */
+  const uint32_t* x_amax;                /* optional: device word holding the bit pattern of an upper bound of max|x|
+                                            (b200gat_edge_fwd's out_amax of the producing layer); saves one pass over x */
 } b200gat_proj_fwd_args;
 size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of an x_split buffer for this geometry; 0 when the shape runs on the CUDA-core path (pass x_split = NULL) */
@@ -112,6 +121,7 @@ typedef struct {
   float* out;  int64_t ldo;       /* [N, D_out] */
   float* rowmax; float* rowsum;   /* out [N, H]: softmax statistics kept for the recomputing backward */
   float* o_heads;                 /* out [N, Dp]; required iff !concat && H > 1 (per-head aggregate) */
+  uint32_t* out_amax;             /* optional out: device word <- bit pattern of max|out| (for the next layer's x_amax) */
 } b200gat_edge_fwd_args;
 int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream);
 
@@ -132,8 +142,15 @@ typedef struct {
   float* g_b1; float* g_b2;           /* out [H] */
   float* g_bias;                      /* out [D_out] */
   void* workspace; size_t workspace_bytes;
+  int32_t out_activation;             /* B200GAT_ACT_*: gout is the gradient w.r.t. act(out); `out` is pre-activation.
+                                         Needs a concat-like layer (concat || H == 1) */
+  void* g_t_split; size_t g_t_split_bytes;   /* optional out: gT as the tensor-core operand split consumed by
+                                         b200gat_proj_bwd (b200gat_edge_bwd_split_bytes() bytes, 256-byte aligned).
+                                         When given, g_t is scratch (it holds the un-finished gWh on return) */
 } b200gat_edge_bwd_args;
 size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
+/* bytes of a g_t_split buffer; 0 when the projection backward of this geometry runs on the CUDA-core path */
+size_t b200gat_edge_bwd_split_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream);
 
 /* ---- K3 staged: the three passes of b200gat_edge_bwd as separate calls, for destination-row partitioned multi-GPU
@@ -194,6 +211,8 @@ typedef struct {
   float* g_w;                         /* out [Dp, F_in] */
   void* workspace; size_t workspace_bytes;
   const void* x_split; size_t x_split_bytes;   /* optional in: the split of x written by b200gat_proj_fwd */
+  int32_t x_activation;               /* as in the forward (used when x_split is absent) */
+  const void* g_t_split; size_t g_t_split_bytes;   /* optional in: gT as written by b200gat_edge_bwd (g_t may be NULL) */
 } b200gat_proj_bwd_args;
 size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);
