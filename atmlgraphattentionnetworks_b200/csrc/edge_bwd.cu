@@ -189,6 +189,85 @@ __global__ void __launch_bounds__(256, 2) bwd_prep_rows_kernel(const PrepRowsPar
   }
 }
 
+// ---- fast prep for mean-over-heads layers (!concat, H > 1): one warp per destination row.  The row of the upstream
+// gradient (C values, shared by all heads, scaled 1/H) is loaded once, written to the gatherable copy gp [N, Cp] and
+// dotted with each head's aggregate O[i,h,:]; the g_bias column sums ride along. --------------------------------------
+struct PrepMeanParams {
+  int64_t N;
+  int H, C, Cp;
+  const float* gout; int64_t ldgo;
+  const float* o_heads;               // [N, H, Cp], 16-byte aligned
+  const float* s_dst; const float* rowmax; const float* rowsum;
+  float* gp;                          // [N, Cp]
+  float4* rowrec;
+  float* g_bias;                      // [C], zero-initialised, accumulated atomically
+};
+
+__global__ void __launch_bounds__(256) bwd_prep_mean_rows_kernel(const PrepMeanParams p) {
+  constexpr int T = 4;                                    // float4 slots per lane: Cp <= 512
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = p.Cp >> 2;
+  const float gscale = 1.f / static_cast<float>(p.H);
+  float4 cs[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) cs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = warp; i < p.N; i += nwarps) {
+    const float* g = p.gout + i * p.ldgo;
+    float4 gv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int q = lane + 32 * t, c = 4 * q;
+      gv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < Q) {
+        if (c + 0 < p.C) gv[t].x = __ldg(g + c + 0);
+        if (c + 1 < p.C) gv[t].y = __ldg(g + c + 1);
+        if (c + 2 < p.C) gv[t].z = __ldg(g + c + 2);
+        if (c + 3 < p.C) gv[t].w = __ldg(g + c + 3);
+        cs[t].x += gv[t].x; cs[t].y += gv[t].y; cs[t].z += gv[t].z; cs[t].w += gv[t].w;
+        gv[t].x *= gscale; gv[t].y *= gscale; gv[t].z *= gscale; gv[t].w *= gscale;
+        *reinterpret_cast<float4*>(p.gp + i * int64_t(p.Cp) + c) = gv[t];
+      }
+    }
+    const float* o = p.o_heads + i * int64_t(p.H) * p.Cp;
+    for (int h = 0; h < p.H; ++h) {
+      float d = 0.f;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int q = lane + 32 * t;
+        if (q < Q) {
+          const float4 ov = ldg4(o + h * p.Cp + 4 * q);
+          d += gv[t].x * ov.x + gv[t].y * ov.y + gv[t].z * ov.z + gv[t].w * ov.w;
+        }
+      }
+      d = group_sum<32>(d);
+      if (lane == 0) {
+        const int64_t item = i * p.H + h;
+        p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
+      }
+    }
+  }
+  __shared__ float4 red[8][32];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (32 * t >= Q) break;
+    __syncthreads();
+    red[threadIdx.x >> 5][lane] = cs[t];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float4 s4 = red[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { s4.x += red[w][lane].x; s4.y += red[w][lane].y; s4.z += red[w][lane].z; s4.w += red[w][lane].w; }
+      const int c = 4 * (lane + 32 * t);
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u < p.C) atomicAdd(p.g_bias + c + u, sv[u]);
+    }
+  }
+}
+
 // ---- column sums of a [N, ncols] matrix (g_bias = sum_n gout[n,:]) ------------------------------------------------
 // (C, Cp): output column c reads input column (c / C) * Cp + c % C — the head-padded copy gp; C == Cp: identity
 __global__ void __launch_bounds__(256)
@@ -574,6 +653,16 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
     if (act) bwd_prep_rows_kernel<true><<<blocks, 256, 0, stream>>>(pr);
     else bwd_prep_rows_kernel<false><<<blocks, 256, 0, stream>>>(pr);
     return check_launch("bwd_prep_rows_kernel");
+  }
+  if (!g.concat_like && gp && aligned16(o_heads) && aligned16(gp)) {
+    PrepMeanParams pm;
+    pm.N = rows; pm.H = g.H; pm.C = g.C; pm.Cp = g.Cp;
+    pm.gout = gout; pm.ldgo = ldgo; pm.o_heads = o_heads; pm.s_dst = s_dst; pm.rowmax = rowmax; pm.rowsum = rowsum;
+    pm.gp = gp; pm.rowrec = rowrec; pm.g_bias = g_bias;
+    const int64_t want = ceil_div(rows, 8);
+    const int64_t cap_rows = int64_t(sm_count()) * 8;
+    bwd_prep_mean_rows_kernel<<<static_cast<int>(want < cap_rows ? want : cap_rows), 256, 0, stream>>>(pm);
+    return check_launch("bwd_prep_mean_rows_kernel");
   }
   PrepParams dp;
   dp.N = rows; dp.H = g.H; dp.C = g.C; dp.Cp = g.Cp; dp.concat_like = g.concat_like ? 1 : 0;

@@ -41,7 +41,9 @@ def _workspace(nbytes, device):
 
 
 class GATLayerFunction(torch.autograd.Function):
-    """x [N,F], packed padded parameters (W [Dp,F], bw/a1/a2 [Dp], b1/b2 [H], bias [D_out]) -> (out [N, D_out], out_amax).
+    """x [N,F], bias [D_out], the layer's persistent packed parameter storage `packed` = (W [Dp,F], bw/a1/a2 [Dp],
+    b1/b2 [H]; the per-head parameters are views of it) and the 6H per-head parameters themselves (*params, in the
+    order of GraphAttentionLayer._head_parameters: they only route the gradients) -> (out [N, D_out], out_amax).
 
     fuse = (act_in, act_out, x_amax) describes the layer boundary fusions (include/b200gat.h, B200GAT_ACT_*):
       act_in   the layer consumes ELU(x): x is the PRE-activation output of the previous layer
@@ -53,7 +55,8 @@ class GATLayerFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, bw, a1, a2, b1, b2, bias, graph, geom, mask, fuse):
+    def forward(ctx, x, bias, graph, geom, mask, fuse, packed, *params):
+        w, bw, a1, a2, b1, b2 = packed
         f_in, c, h, concat = geom
         act_in, act_out, x_amax = fuse
         lib = _abi.lib()
@@ -65,7 +68,7 @@ class GATLayerFunction(torch.autograd.Function):
         d_out = h * c if concat else c
         heads_mode = (not concat) and h > 1
         x = x.contiguous()
-        w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
+        bias = bias.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         wh = torch.empty((n, dp), **f32)
         s_src = torch.empty((n, h), **f32)
@@ -147,7 +150,13 @@ class GATLayerFunction(torch.autograd.Function):
                                   _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes)
             _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, ctx.geom)
             _abi.launches += 2
-        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None
+        # per-head gradients are views of the packed buffers, in the order of _head_parameters (autograd takes them as
+        # the parameters' .grad without a copy when no gradient is accumulated yet)
+        gw3, gbw2, ga12, ga22 = g_w.view(h, cp, f_in), g_bw.view(h, cp), g_a1.view(h, cp), g_a2.view(h, cp)
+        per_head = []
+        for k in range(h):
+            per_head += [gw3[k, :c], gbw2[k, :c], ga12[k:k + 1, :c], g_b1[k:k + 1], ga22[k:k + 1, :c], g_b2[k:k + 1]]
+        return (g_x, g_bias, None, None, None, None, None, *per_head)
 
 
 class GraphAttentionLayer(torch.nn.Module):
@@ -179,8 +188,61 @@ class GraphAttentionLayer(torch.nn.Module):
             self.bias = torch.nn.Parameter(torch.zeros(output_channels * num_heads))
         self.graph_cache = GLOBAL_CACHE
         self.mask_hook = None   # parity tests: callable (E', H) -> keep-multiplier [E', H] in ORIGINAL edge order
+        self._store = None      # persistent packed parameter storage (see _packed_storage)
 
-    # ---- parameter packing: [Dp, F] / [Dp] / [H] views of the per-head Linear modules (autograd splits the grads back)
+    # ---- persistent packed storage: the kernels read ONE [Dp, F] / [Dp] / [H] set of arrays per layer (head-major, rows
+    # padded to c_pad with zeros).  The per-head Linear parameters of GAT.py:19-25 (and the state_dict keys that come with
+    # them) are VIEWS of that storage, so optimizers and load_state_dict update it in place and no per-step packing or
+    # gradient un-packing kernels run.  Anything that re-creates the parameter tensors (.to(), .cuda(), assignment) is
+    # detected by the pointer check and the storage is rebuilt from the current values.
+    def _head_parameters(self):
+        out = []
+        for k in range(self.num_heads):
+            out += [self.ws[k].weight, self.ws[k].bias, self.attentions1[k].weight, self.attentions1[k].bias,
+                    self.attentions2[k].weight, self.attentions2[k].bias]
+        return out
+
+    def _packed_storage(self):
+        c, h, f = self.output_channels, self.num_heads, self.input_channels
+        cp = (c + 3) // 4 * 4
+        st = self._store
+        ok = st is not None and st[0].device == self.bias.device
+        if ok:
+            w3, bw2, a12, a22, b1, b2 = st[1]
+            for k in range(h):
+                if (self.ws[k].weight.data_ptr() != w3[k].data_ptr() or self.ws[k].bias.data_ptr() != bw2[k].data_ptr() or
+                        self.attentions1[k].weight.data_ptr() != a12[k].data_ptr() or
+                        self.attentions2[k].weight.data_ptr() != a22[k].data_ptr() or
+                        self.attentions1[k].bias.data_ptr() != b1[k:].data_ptr() or
+                        self.attentions2[k].bias.data_ptr() != b2[k:].data_ptr()):
+                    ok = False
+                    break
+        if not ok:
+            dev = self.bias.device
+            f32 = dict(dtype=torch.float32, device=dev)
+            w3, bw2, a12, a22 = (torch.zeros((h, cp, f), **f32), torch.zeros((h, cp), **f32), torch.zeros((h, cp), **f32),
+                                 torch.zeros((h, cp), **f32))
+            b1, b2 = torch.zeros(h, **f32), torch.zeros(h, **f32)
+            with torch.no_grad():
+                for k in range(h):
+                    w3[k, :c].copy_(self.ws[k].weight)
+                    bw2[k, :c].copy_(self.ws[k].bias)
+                    a12[k, :c].copy_(self.attentions1[k].weight[0])
+                    a22[k, :c].copy_(self.attentions2[k].weight[0])
+                    b1[k:k + 1].copy_(self.attentions1[k].bias)
+                    b2[k:k + 1].copy_(self.attentions2[k].bias)
+                    self.ws[k].weight.data = w3[k, :c]
+                    self.ws[k].bias.data = bw2[k, :c]
+                    self.attentions1[k].weight.data = a12[k:k + 1, :c]
+                    self.attentions2[k].weight.data = a22[k:k + 1, :c]
+                    self.attentions1[k].bias.data = b1[k:k + 1]
+                    self.attentions2[k].bias.data = b2[k:k + 1]
+            st = (w3, (w3, bw2, a12, a22, b1, b2),
+                  (w3.view(h * cp, f), bw2.view(-1), a12.view(-1), a22.view(-1), b1, b2))
+            self._store = st
+        return st[2]
+
+    # ---- functional packing through autograd (torch.stack / pad): used by the row-partitioned multi-GPU path and tests
     def _packed(self):
         c, h = self.output_channels, self.num_heads
         pad = (c + 3) // 4 * 4 - c
@@ -233,7 +295,9 @@ class GraphAttentionLayer(torch.nn.Module):
         elif not isinstance(graph, GraphCSR) or graph.num_nodes != n:
             raise ValueError("graph does not match x")
         mask = self._dropout_mask(graph.num_edges, x.device)
-        w, bw, a1, a2, b1, b2 = self._packed()
+        if x.dtype != torch.float32 or self.bias.dtype != torch.float32 or not self.bias.is_cuda:
+            raise TypeError("GraphAttentionLayer parameters must be float32 CUDA tensors (move the module with .to(device))")
+        packed = self._packed_storage()
         geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
-        return GATLayerFunction.apply(x, w, bw, a1, a2, b1, b2, self.bias, graph, geom, mask,
-                                      (bool(act_in), bool(act_out), x_amax))
+        return GATLayerFunction.apply(x, self.bias, graph, geom, mask, (bool(act_in), bool(act_out), x_amax), packed,
+                                      *self._head_parameters())

@@ -254,7 +254,9 @@ def main():
     n = data.x.shape[0]
     torch.manual_seed(0)
     model = GATStack(spec, dropout=0.0).to(dev)
-    bucket = GradBucket(model.parameters())
+    # N > 1: all gradients live in one flat buffer (one NCCL all-reduce per step); N = 1: gradients are set to None and
+    # autograd adopts the kernels' output buffers as .grad without a copy
+    bucket = GradBucket(model.parameters()) if world > 1 else None
     opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True)   # run_inductive.py:18-19,65
     part = None
     if partitioned:
@@ -269,7 +271,10 @@ def main():
     x_d, ei_d, y_d = x_h.to(dev), ei_h.to(dev), y_h.to(dev)
 
     def train_step(x, ei, y):
-        bucket.zero()
+        if bucket is not None:
+            bucket.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         if partitioned:
             out = pmodel(x, part)
             # global mean loss = sum over ranks of (own sum / N); parameter gradients are then SUMMED over ranks
@@ -280,7 +285,8 @@ def main():
             out = model(x, ei)
             loss = loss_fn(out, y)
             loss.backward()
-            bucket.all_reduce_mean()
+            if bucket is not None:
+                bucket.all_reduce_mean()
         opt.step()
         return loss
 

@@ -119,6 +119,32 @@ def test_packed_parameters_round_trip():
     assert torch.all(layer.ws[1].weight.grad == 1)
 
 
+def test_persistent_packed_storage_tracks_the_per_head_parameters():
+    """The kernels read one packed [Dp, F] / [Dp] / [H] set of arrays; the per-head Linear parameters are views of it."""
+    import GAT
+    torch.manual_seed(0)
+    layer = GAT.GraphAttentionLayer(5, 3, num_heads=2, concat=True, dropout=0.0)
+    before = {k: v.clone() for k, v in layer.state_dict().items()}
+    w, bw, a1, a2, b1, b2 = layer._packed_storage()
+    assert w.shape == (8, 5) and bw.shape == (8,) and b1.shape == (2,)
+    for k, v in layer.state_dict().items():
+        assert torch.equal(v, before[k]), k                               # tying does not change any value
+    assert torch.equal(w[4:7], layer.ws[1].weight) and torch.all(w[3] == 0) and torch.all(w[7] == 0)
+    with torch.no_grad():                                                  # an optimizer's in-place update is seen
+        layer.ws[1].weight.add_(1.0)
+        layer.attentions2[0].bias.fill_(7.0)
+    w2, *_, b2b = layer._packed_storage()
+    assert w2.data_ptr() == w.data_ptr()                                   # no rebuild
+    assert torch.equal(w2[4:7], before["ws.1.weight"] + 1.0) and float(b2b[0]) == 7.0
+    sd = {k: torch.full_like(v, 0.25) for k, v in layer.state_dict().items()}
+    layer.load_state_dict(sd)                                              # load_state_dict copies in place
+    assert torch.all(layer._packed_storage()[0][0:3] == 0.25) and torch.all(layer._packed_storage()[0][3] == 0)
+    layer.ws[0].weight.data = torch.ones(3, 5)                             # what .to() / .cuda() do: new tensors
+    w3 = layer._packed_storage()[0]
+    assert w3.data_ptr() != w.data_ptr() and torch.all(w3[0:3] == 1.0) and torch.all(w3[4:7] == 0.25)
+    assert layer.ws[0].weight.data_ptr() == w3.data_ptr()
+
+
 def test_no_cpu_fallback():
     import GAT
     layer = GAT.GraphAttentionLayer(4, 4, num_heads=2, concat=True, dropout=0.0)
