@@ -67,66 +67,127 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     float m = -INFINITY, l = 0.f;
     const float* whh = p.wh + h * Cp;
-    for (int k0 = 0; k0 < maxdeg; k0 += G) {
-      const int k = beg + k0 + gl;
-      const bool ok = k < end;
-      int j = static_cast<int>(i);
-      float e = -INFINITY;
-      if (ok) {
-        j = __ldg(p.col + k);
-        e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
-      }
-      const float m_new = fmaxf(m, group_max<G>(e));
-      if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
-        const float scale = expf(m - m_new);
-        l *= scale;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale;
-        }
-      }
-      m = m_new;
-      float pp = 0.f, pm = 0.f;
-      if (ok) {
-        pp = expf(e - m);
-        pm = pp;
-        if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
-      }
-      l += pp;
-      const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
-      // U edges per step: all U*NV 128-bit gathers are issued before the first FMA consumes one (memory-level
-      // parallelism; a per-edge branch here serialises load -> FMA -> next load and leaves the kernel latency-bound)
-      constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
-      for (int t = 0; t < cnt; t += U) {
-        int jt[U];
-        float pt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          jt[u] = __shfl_sync(FULL, j, t + u, G);
-          pt[u] = __shfl_sync(FULL, pm, t + u, G);
-          if (t + u >= cnt) pt[u] = 0.f;
-        }
+    // For 256-wide heads (NV = 2) the FIRST gather batch of a chunk is issued as soon as col[] is known — before the
+    // dependent s_src gather, the exp and the softmax bookkeeping, none of which the Wh gathers need.  Tuned with
+    // tools/microbench/gather_bench.cu (PPI-shaped batch, same loop): NV=2: weights-first U=4 0.279 ms, early U=4 0.317,
+    // early U=2 0.233 (a bare gather loop: 0.204); NV=1: weights-first U=8 is the best on the streaming graph.
+    // Double-buffering the batches in registers was measured slower (80 registers: 3 instead of 4 CTAs per SM).
+    if constexpr (!HAS_MASK && NV == 2) {
+      constexpr int U = 2;
+      for (int k0 = 0; k0 < maxdeg; k0 += G) {
+        const int k = beg + k0 + gl;
+        const bool ok = k < end;
+        int j = static_cast<int>(i);
+        if (ok) j = __ldg(p.col + k);
+        const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
         float4 w[U][NV];
+        auto load_batch = [&](int t) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float* src = whh + int64_t(jt[u]) * Dp;
+          for (int u = 0; u < U; ++u) {
+            // slots past the chunk's edge count read a valid row (lane t+u's own j, or the destination itself), weight 0
+            const int jt = __shfl_sync(FULL, j, t + u, G);
+            const float* src = whh + int64_t(jt) * Dp;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) w[u][v] = ldg4(src + off[v]);
+          }
+        };
+        load_batch(0);
+        float e = -INFINITY;
+        if (ok) e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
+        const float m_new = fmaxf(m, group_max<G>(e));
+        if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
+          const float scale = expf(m - m_new);
+          l *= scale;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6) contribute nothing: skip the gather
-              w[u][v] = pt[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {          // no predicate, no branch: padded slots gather the row's own (valid) Wh and weigh it by 0
-              w[u][v] = ldg4(src + off[v]);
+            acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale;
+          }
+        }
+        m = m_new;
+        const float pp = ok ? expf(e - m) : 0.f;
+        l += pp;
+        for (int t = 0; t < cnt; t += U) {
+          float pt[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            pt[u] = __shfl_sync(FULL, pp, t + u, G);
+            if (t + u >= cnt) pt[u] = 0.f;
+          }
+          if (t > 0) load_batch(t);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              acc[v].x = fmaf(pt[u], w[u][v].x, acc[v].x);
+              acc[v].y = fmaf(pt[u], w[u][v].y, acc[v].y);
+              acc[v].z = fmaf(pt[u], w[u][v].z, acc[v].z);
+              acc[v].w = fmaf(pt[u], w[u][v].w, acc[v].w);
             }
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-#pragma unroll
+      }
+    } else {
+      for (int k0 = 0; k0 < maxdeg; k0 += G) {
+        const int k = beg + k0 + gl;
+        const bool ok = k < end;
+        int j = static_cast<int>(i);
+        float e = -INFINITY;
+        if (ok) {
+          j = __ldg(p.col + k);
+          e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
+        }
+        const float m_new = fmaxf(m, group_max<G>(e));
+        if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
+          const float scale = expf(m - m_new);
+          l *= scale;
+  #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            acc[v].x = fmaf(pt[u], w[u][v].x, acc[v].x);
-            acc[v].y = fmaf(pt[u], w[u][v].y, acc[v].y);
-            acc[v].z = fmaf(pt[u], w[u][v].z, acc[v].z);
-            acc[v].w = fmaf(pt[u], w[u][v].w, acc[v].w);
+            acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale;
+          }
+        }
+        m = m_new;
+        float pp = 0.f, pm = 0.f;
+        if (ok) {
+          pp = expf(e - m);
+          pm = pp;
+          if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
+        }
+        l += pp;
+        const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
+        // U edges per step: all U*NV 128-bit gathers are issued before the first FMA consumes one (memory-level
+        // parallelism; a per-edge branch here serialises load -> FMA -> next load and leaves the kernel latency-bound)
+        constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
+        for (int t = 0; t < cnt; t += U) {
+          int jt[U];
+          float pt[U];
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            jt[u] = __shfl_sync(FULL, j, t + u, G);
+            pt[u] = __shfl_sync(FULL, pm, t + u, G);
+            if (t + u >= cnt) pt[u] = 0.f;
+          }
+          float4 w[U][NV];
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float* src = whh + int64_t(jt[u]) * Dp;
+  #pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6) contribute nothing: skip the gather
+                w[u][v] = pt[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {          // no predicate, no branch: padded slots gather the row's own (valid) Wh and weigh it by 0
+                w[u][v] = ldg4(src + off[v]);
+              }
+            }
+          }
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+  #pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              acc[v].x = fmaf(pt[u], w[u][v].x, acc[v].x);
+              acc[v].y = fmaf(pt[u], w[u][v].y, acc[v].y);
+              acc[v].z = fmaf(pt[u], w[u][v].z, acc[v].z);
+              acc[v].w = fmaf(pt[u], w[u][v].w, acc[v].w);
+            }
           }
         }
       }
