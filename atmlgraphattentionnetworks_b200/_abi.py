@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -18,7 +18,7 @@ _i64p = C.POINTER(C.c_int64)
 class Graph(C.Structure):
     _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("eid", C.c_void_p),
-                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p)]
+                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p), ("span", C.c_int64)]
 
 
 class Layer(C.Structure):
@@ -72,7 +72,7 @@ class EdgeBwdCscArgs(C.Structure):
                 ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p),
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("rowrec", C.c_void_p), ("mask", C.c_void_p),
                 ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
-                ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p)]
+                ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64)]
 
 
 class EdgeBwdFinishArgs(C.Structure):

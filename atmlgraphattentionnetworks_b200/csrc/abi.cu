@@ -1,6 +1,7 @@
 // ABI plumbing: version, thread-local error message, device attribute cache.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace b200gat {
 
@@ -42,6 +43,31 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+int64_t l2_bytes() {
+  static thread_local int cached_dev = -1;
+  static thread_local int64_t cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return int64_t(126) << 20;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev) != cudaSuccess || n <= 0) n = 126 << 20;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+bool edge_schedule_streaming(int64_t span, int64_t row_bytes) {
+  static int forced = -1;   // 0: by span, 1: cached, 2: stream
+  if (forced < 0) {
+    const char* e = getenv("B200GAT_EDGE_SCHEDULE");
+    forced = (e && e[0] == 'c') ? 1 : ((e && e[0] == 's') ? 2 : 0);
+  }
+  if (forced) return forced == 2;
+  if (span < 0) return false;                       // unknown locality: the occupancy-first schedule
+  return (span + 1) * row_bytes > l2_bytes() / 2;
 }
 
 }  // namespace b200gat

@@ -20,6 +20,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();   // cached multiprocessor count of the current device (148 on B200)
+int64_t l2_bytes();   // cached L2 size of the current device (126 MB on B200)
+
+// Edge-kernel schedule (see b200gat_graph.span): `row_bytes` = bytes of one gathered row.  Streaming when the rows an
+// edge can reach from the row being processed do not fit half of L2; B200GAT_EDGE_SCHEDULE=cached|stream overrides.
+bool edge_schedule_streaming(int64_t span, int64_t row_bytes);
 
 inline int validate_layer(const b200gat_layer& L) {
   B200GAT_REQUIRE(L.in_channels > 0 && L.out_channels > 0 && L.heads > 0, B200GAT_E_SHAPE,

@@ -23,15 +23,20 @@ static int key_bits(int64_t n) {
 __global__ void csr_fill_keys(const int64_t* __restrict__ ei, int64_t E, int64_t N, int32_t* __restrict__ keys,
                               int32_t* __restrict__ iota, int32_t* __restrict__ status) {
   int64_t EP = E + N;
-  int bad = 0;
+  int bad = 0, span = 0;
   for (int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; p < EP; p += int64_t(gridDim.x) * blockDim.x) {
     int64_t d, s;
     if (p < E) { s = ei[p]; d = ei[E + p]; } else { s = d = p - E; }
     if (d < 0 || d >= N || s < 0 || s >= N) { ++bad; d = d < 0 ? 0 : (d >= N ? N - 1 : d); }
+    else { const int64_t w = s > d ? s - d : d - s; span = w > span ? static_cast<int>(w) : span; }
     keys[p] = static_cast<int32_t>(d);
     iota[p] = static_cast<int32_t>(p);
   }
   if (bad) atomicAdd(status, bad);
+  // status[1] = max |source - destination|: how far apart (in node rows) an edge's gather can be from the row that
+  // is being processed — block-diagonal graph batches have a small span (their gathered operand stays L2-resident)
+  span = __reduce_max_sync(0xffffffffu, span);
+  if ((threadIdx.x & 31) == 0 && span) atomicMax(status + 1, span);
 }
 
 // After the destination sort: col[pos] = source of entry eid[pos]; rowptr from key boundaries.

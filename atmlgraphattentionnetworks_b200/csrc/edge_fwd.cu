@@ -31,8 +31,12 @@ struct EdgeFwdParams {
   uint32_t* out_amax;   // optional: bit pattern of max|out| (atomicMax; zeroed by the host)
 };
 
-template <int G, int NV, bool HAS_MASK>
-__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
+// STREAM: the schedule for graphs whose gathered rows come from HBM (b200gat_graph.span): __launch_bounds__(256, 3)
+// makes ptxas issue ALL U*NV gathers of a batch back to back (76 registers) — 3x the bytes in flight per warp at 3/4
+// of the occupancy.  Measured (tools/microbench/gather_bench.cu, power-law graph): 5.3 vs 3.7 TB/s gathered.  On the
+// L2-resident PPI-shaped batch the same build is 13 % SLOWER than the occupancy-first one, hence two instantiations.
+template <int G, int NV, bool HAS_MASK, bool STREAM>
+__device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
     // tools/microbench/gather_bench.cu (PPI-shaped batch, same loop): NV=2: weights-first U=4 0.279 ms, early U=4 0.317,
     // early U=2 0.233 (a bare gather loop: 0.204); NV=1: weights-first U=8 is the best on the streaming graph.
     // Double-buffering the batches in registers was measured slower (80 registers: 3 instead of 4 CTAs per SM).
-    if constexpr (!HAS_MASK && NV == 2) {
+    if constexpr (!HAS_MASK && NV == 2 && !STREAM) {
       constexpr int U = 2;
       for (int k0 = 0; k0 < maxdeg; k0 += G) {
         const int k = beg + k0 + gl;
@@ -231,6 +235,14 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) {
   if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
 }
 
+// two entry points: __launch_bounds__(256) (no minimum: ptxas's own occupancy-first choice, 60-64 registers) and
+// __launch_bounds__(256, 3) for the streaming schedule (a minimum of 1 is NOT the same as none: it raises the register
+// budget and changed the code of the occupancy-first variant for the worse)
+template <int G, int NV, bool HAS_MASK>
+__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, HAS_MASK, false>(p); }
+template <int G, int NV>
+__global__ void __launch_bounds__(256, 3) edge_fwd_stream_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, false, true>(p); }
+
 // concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c]
 __global__ void __launch_bounds__(256)
 head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bias, float* __restrict__ out,
@@ -251,13 +263,14 @@ head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bi
 }
 
 template <int G, int NV>
-static int launch_edge_fwd(const EdgeFwdParams& p, cudaStream_t stream) {
+static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t stream) {
   constexpr int GPW = 32 / G;
   const int threads = 256;
   const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   if (p.mask) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  else if (streaming && G >= 16) edge_fwd_stream_kernel<(G >= 16 ? G : 32), (G >= 16 ? NV : 1)><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_kernel");
 }
@@ -303,14 +316,15 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   }
 
   const int Q = Cp / 4;
-  if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, stream);
-  else if (Q <= 2) rc = launch_edge_fwd<2, 1>(p, stream);
-  else if (Q <= 4) rc = launch_edge_fwd<4, 1>(p, stream);
-  else if (Q <= 8) rc = launch_edge_fwd<8, 1>(p, stream);
-  else if (Q <= 16) rc = launch_edge_fwd<16, 1>(p, stream);
-  else if (Q <= 32) rc = launch_edge_fwd<32, 1>(p, stream);
-  else if (Q <= 64) rc = launch_edge_fwd<32, 2>(p, stream);
-  else rc = launch_edge_fwd<32, 4>(p, stream);
+  const bool streaming = edge_schedule_streaming(a->graph.span, int64_t(H) * Cp * 4);
+  if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, streaming, stream);
+  else if (Q <= 2) rc = launch_edge_fwd<2, 1>(p, streaming, stream);
+  else if (Q <= 4) rc = launch_edge_fwd<4, 1>(p, streaming, stream);
+  else if (Q <= 8) rc = launch_edge_fwd<8, 1>(p, streaming, stream);
+  else if (Q <= 16) rc = launch_edge_fwd<16, 1>(p, streaming, stream);
+  else if (Q <= 32) rc = launch_edge_fwd<32, 1>(p, streaming, stream);
+  else if (Q <= 64) rc = launch_edge_fwd<32, 2>(p, streaming, stream);
+  else rc = launch_edge_fwd<32, 4>(p, streaming, stream);
   if (rc) return rc;
   if (heads_mode) {
     const int64_t total = N * C;

@@ -180,7 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   using S = TcCfg<BN>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: an integer round trip would
+  // lose the address space and turn every epilogue read of vec[] / red[] into a generic LD (ncu: 39 % of all stalls)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   float* vec = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
   float* red = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::VEC_BYTES);
@@ -357,15 +359,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         if (EPI == EPI_LOGITS) {
           float d1 = 0.f, d2 = 0.f;
           if (p.Cp <= 128) {
-            // heads tile this thread's 128 columns (128 % Cp == 0, checked on the host)
+            // heads tile this thread's 128 columns: Cp divides 128 (checked on the host), hence is a power of two
+            const int cmask = p.Cp - 1, cshift = 31 - __clz(p.Cp);
 #pragma unroll
             for (int j = 0; j < 128; ++j) {
               d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
               d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
-              if ((j + 1) % p.Cp == 0) {
+              if (((j + 1) & cmask) == 0) {
                 const int64_t col = col0 + j;
                 if (row_ok && col < p.N) {
-                  const int h = static_cast<int>(col / p.Cp);
+                  const int h = static_cast<int>(col >> cshift);
                   p.s_src[row * p.H + h] = d1 + __ldg(p.b1 + h);
                   p.s_dst[row * p.H + h] = d2 + __ldg(p.b2 + h);
                 }
@@ -394,10 +397,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           }
         }
         if (row_ok) {
+          const bool al_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
           if (vec_ok) {
 #pragma unroll
             for (int j = 0; j < 128; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          } else if (al_ok) {      // N tail inside this thread's columns: whole float4 groups, then the ragged rest
+#pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+              if (col0 + j + 4 <= p.N) {
+                *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (col0 + j + u < p.N) dst[j + u] = acc[j + u];
+              }
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 128; ++j)

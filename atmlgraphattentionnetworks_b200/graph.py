@@ -15,7 +15,7 @@ class GraphCSR:
     """int32 device arrays of [edge_index ; self loops] (see include/b200gat.h: b200gat_graph)."""
 
     __slots__ = ("num_nodes", "num_input_edges", "num_edges", "rowptr", "col", "eid", "colptr", "crow", "ceid",
-                 "device", "_struct", "__weakref__")
+                 "device", "span", "_struct", "__weakref__")
 
     def c_struct(self):
         return self._struct
@@ -57,12 +57,14 @@ def build_csr(edge_index, num_nodes, validate=True):
                                    ws.data_ptr(), ws_bytes, stream)
         _abi.check(rc, "b200gat_csr_build")
         _abi.launches += 5 if ep else 0
+        g.span = -1
         if validate:
-            bad = int(status[0].item())
+            bad, span = (int(v) for v in status.tolist())      # one D2H read: index check + the locality statistic
             if bad:
                 raise IndexError(f"edge_index has {bad} entries outside [0, {n})")
+            g.span = span
     g._struct = _abi.Graph(n, ep, g.rowptr.data_ptr(), g.col.data_ptr(), g.eid.data_ptr(), g.colptr.data_ptr(),
-                           g.crow.data_ptr(), g.ceid.data_ptr())
+                           g.crow.data_ptr(), g.ceid.data_ptr(), g.span)
     return g
 
 

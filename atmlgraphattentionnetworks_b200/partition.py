@@ -79,7 +79,7 @@ def build_row_partition(edge_index, num_nodes, world, rank):
     p._struct = None
     if rowptr.is_cuda:
         p._struct = _abi.Graph(hi - lo, int(col.numel()), rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
-                               colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr())
+                               colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr(), n)   # span: one big graph
     return p
 
 
@@ -182,7 +182,8 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
     stream = torch.cuda.current_stream(dev).cuda_stream
     ca = _abi.EdgeBwdCscArgs(layer, n, part.colptr.data_ptr(), part.crow.data_ptr(), part.ceid.data_ptr(),
                              wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
-                             g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr())
+                             g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
+                             part.num_nodes)
     _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
     return g_wh, g_s_src, g_s_dst_full
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 6
+#define B200GAT_ABI_VERSION 7
 
 enum {
   B200GAT_OK = 0,
@@ -59,6 +59,10 @@ typedef struct {
   const int32_t* colptr;   /* [N+1]  CSC by source (stable w.r.t. CSR order) */
   const int32_t* crow;     /* [E']   destination of each CSC entry */
   const int32_t* ceid;     /* [E']   original position of each CSC entry */
+  int64_t span;            /* max |source - destination| over the edges (status[1] of b200gat_csr_build), or < 0 if
+                              unknown.  The edge kernels use it to pick their schedule: a small span (block-diagonal
+                              graph batches) keeps the gathered rows L2-resident and favours occupancy; a large one
+                              (one big graph) streams them from HBM and favours more gathers in flight per warp */
 } b200gat_graph;
 
 /* Layer geometry, GAT.py:8 (input_channels, output_channels, num_heads, concat). */
@@ -80,7 +84,7 @@ int b200gat_last_error(char* buf, size_t buf_len);
 /* ---- K0: graph ingestion (GAT.py:38) ------------------------------------------------------------------- */
 size_t b200gat_csr_workspace_bytes(int64_t num_nodes, int64_t num_input_edges);
 /* edge_index: int64 [2, E] contiguous (row 0 = source, row 1 = target).  status: device int32[2], set to
- * {number of out-of-range indices, reserved}; the arrays are still well-formed (indices clamped) if non-zero. */
+ * {number of out-of-range indices, max |source - destination| (b200gat_graph.span)}; the arrays are still well-formed (indices clamped) if non-zero. */
 int b200gat_csr_build(const int64_t* edge_index, int64_t num_input_edges, int64_t num_nodes,
                       int32_t* rowptr, int32_t* col, int32_t* eid,
                       int32_t* colptr, int32_t* crow, int32_t* ceid,
@@ -185,6 +189,7 @@ typedef struct {
   float* g_wh;                        /* out [rows, Dp] */
   float* g_s_src;                     /* out [rows, H] */
   float* g_s_dst;                     /* in/out ALL nodes [N, H]: zero-initialised by the caller, accumulated atomically */
+  int64_t span;                       /* as b200gat_graph.span for the gathered rows `g` (< 0: unknown) */
 } b200gat_edge_bwd_csc_args;
 int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
 

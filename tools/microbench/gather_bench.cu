@@ -213,6 +213,30 @@ static Graph make_graph(int64_t N, int blocks, int deg, unsigned seed) {
   return g;
 }
 
+// both endpoints = perm[floor(N * U^2)] (the BASELINE power-law graph: in-degree max ~40k, median 19), dst-sorted CSR
+static Graph make_powerlaw(int64_t N, int64_t E, unsigned seed) {
+  Graph g; g.N = N;
+  uint64_t x = 88172645463325252ull + seed;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  std::vector<int> perm(N);
+  for (int64_t i = 0; i < N; ++i) perm[i] = (int)i;
+  for (int64_t i = N - 1; i > 0; --i) std::swap(perm[i], perm[rnd() % (i + 1)]);
+  auto pick = [&]() { double u = (rnd() >> 11) * (1.0 / 9007199254740992.0); int64_t k = (int64_t)(u * u * N); return perm[k < N ? k : N - 1]; };
+  std::vector<int> src(E), dst(E);
+  std::vector<int> cnt(N + 1, 0);
+  for (int64_t e = 0; e < E; ++e) { src[e] = pick(); dst[e] = pick(); cnt[dst[e] + 1]++; }
+  for (int64_t i = 0; i < N; ++i) cnt[i + 1] += 1;          // self loops
+  g.rowptr.assign(N + 1, 0);
+  for (int64_t i = 0; i < N; ++i) g.rowptr[i + 1] = g.rowptr[i] + cnt[i + 1];
+  g.col.resize(g.rowptr[N]);
+  std::vector<int> fill(g.rowptr.begin(), g.rowptr.end() - 1);
+  for (int64_t e = 0; e < E; ++e) g.col[fill[dst[e]]++] = src[e];
+  for (int64_t i = 0; i < N; ++i) g.col[fill[i]++] = (int)i;
+  int mx = 0; for (int64_t i = 0; i < N; ++i) mx = std::max(mx, g.rowptr[i + 1] - g.rowptr[i]);
+  printf("power-law graph: max in-degree %d\n", mx);
+  return g;
+}
+
 template <typename F> static float time_ms(F f, int reps) {
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
   f(); CK(cudaDeviceSynchronize());
@@ -222,9 +246,9 @@ template <typename F> static float time_ms(F f, int reps) {
   float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms / reps;
 }
 
-template <int DV> static void run_case(const char* name, int64_t N, int blocks, int deg, int reps) {
+template <int DV> static void run_case(const char* name, int64_t N, int blocks, int deg, int reps, int64_t powerlaw_edges = 0) {
   const int D = DV * 128;
-  Graph g = make_graph(N, blocks, deg, 1);
+  Graph g = powerlaw_edges ? make_powerlaw(N, powerlaw_edges, 1) : make_graph(N, blocks, deg, 1);
   const int64_t E = g.col.size();
   int *rowptr, *col; float *T, *out;
   CK(cudaMalloc(&rowptr, (N + 1) * 4)); CK(cudaMalloc(&col, E * 4));
@@ -281,5 +305,6 @@ template <int DV> static void run_case(const char* name, int64_t N, int blocks, 
 int main() {
   run_case<8>("PPI-shaped (24 blocks, cached regime), D=1024", 56944, 24, 14, 20);
   run_case<4>("large random (streaming regime), D=512", 1200000, 1, 26, 3);
+  run_case<4>("power-law 2.4M nodes / 62M edges (streaming regime, skewed degrees), D=512", 2400000, 1, 0, 2, 62000000);
   return 0;
 }
