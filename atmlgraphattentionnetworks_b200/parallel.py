@@ -66,3 +66,43 @@ class GradBucket:
 
     def _slot(self, p):
         return self._slots[id(p)]
+
+
+def all_reduce_packed_grads(params, group=None, weight=None):
+    """Data-parallel gradient exchange without a staging copy: the layer's backward hands every per-head gradient back
+    as a VIEW of its packed output buffers (gat.py), so with `zero_grad(set_to_none=True)` the .grad tensors of a step
+    are views of a handful of base buffers (7 per GAT layer).  Those bases are scaled with one multi-tensor kernel and
+    all-reduced inside one NCCL group (one fused launch) — no flat bucket, no accumulate-into-bucket kernels.
+    Average over ranks by default; `weight` = n_r / N for node-level mean losses.  Returns the number of buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    # group the gradients by STORAGE (autograd detaches the views it adopts, so ._base is gone): every storage a .grad
+    # lives in is one of the backward's dedicated packed buffers (or a plain parameter's own gradient) and is reduced whole
+    bases, seen = [], set()
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
+        st = g.untyped_storage()
+        if st.data_ptr() in seen:
+            continue
+        seen.add(st.data_ptr())
+        bases.append(torch.empty(0, dtype=g.dtype, device=g.device).set_(st))
+    if not bases:
+        return 0
+    scale = (1.0 / dist.get_world_size(group)) if weight is None else float(weight)
+    torch._foreach_mul_(bases, scale)
+    coalesce = None
+    if dist.get_backend(group) == "nccl":             # gloo (the CPU tests) has no coalescing: plain loop there
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager as coalesce
+        except ImportError:
+            coalesce = None
+    if coalesce is not None:
+        with coalesce(group=group, device=bases[0].device, async_ops=False):
+            for b in bases:
+                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+    else:
+        for b in bases:
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+    return len(bases)

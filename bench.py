@@ -237,7 +237,7 @@ def main():
     from atmlgraphattentionnetworks_b200 import _abi
     from atmlgraphattentionnetworks_b200.gatnet import GATStack
     from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
-    from atmlgraphattentionnetworks_b200.parallel import GradBucket
+    from atmlgraphattentionnetworks_b200.parallel import GradBucket, all_reduce_packed_grads
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -254,9 +254,11 @@ def main():
     n = data.x.shape[0]
     torch.manual_seed(0)
     model = GATStack(spec, dropout=0.0).to(dev)
-    # N > 1: all gradients live in one flat buffer (one NCCL all-reduce per step); N = 1: gradients are set to None and
-    # autograd adopts the kernels' output buffers as .grad without a copy
-    bucket = GradBucket(model.parameters()) if world > 1 else None
+    # gradients are set to None every step and autograd adopts the kernels' packed output buffers as .grad without a copy;
+    # N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (parallel.all_reduce_packed_grads).
+    # The row-partitioned large graph keeps the flat bucket (its stage functions build gradients through torch ops).
+    bucket = GradBucket(model.parameters()) if (world > 1 and args.workload == "large") else None
+    params = list(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True)   # run_inductive.py:18-19,65
     part = None
     if partitioned:
@@ -285,8 +287,8 @@ def main():
             out = model(x, ei)
             loss = loss_fn(out, y)
             loss.backward()
-            if bucket is not None:
-                bucket.all_reduce_mean()
+            if world > 1:
+                all_reduce_packed_grads(params)
         opt.step()
         return loss
 
@@ -369,14 +371,24 @@ def main():
                 rec["TFLOPs"] = fl / ms / 1e9
             kernels.append(rec)
     dom = max(kernels, key=lambda r: r["ms"]) if kernels else None
+    # measured DRAM traffic of each op (one committed `ncu --set full` capture of this workload, tools/ncu_traffic.py)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.isfile(tpath) and not partitioned:
+        traffic = json.load(open(tpath)).get("ops", {})
+    for rec in kernels:
+        t = traffic.get(f"{rec['op']}:{rec['layer']}")
+        rec["dram_traffic_bytes"] = t["dram_bytes"] if t else None
     roofline = None
     if dom is not None:
         if dom["op"].startswith("b200gat_edge"):
             roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": dom["GBps"] / peaks["hbm"], "traffic": None}
+                        "frac": dom["GBps"] / peaks["hbm"], "traffic": dom["dram_traffic_bytes"],
+                        "alg_bytes": dom["alg_bytes"]}
         else:
             roofline = {"bound": "tensor", "achieved": dom.get("TFLOPs", 0.0), "peak": peaks["bf16_sustained"],
-                        "unit": "TFLOP/s", "frac": dom.get("TFLOPs", 0.0) / peaks["bf16_sustained"], "traffic": None}
+                        "unit": "TFLOP/s", "frac": dom.get("TFLOPs", 0.0) / peaks["bf16_sustained"],
+                        "traffic": dom["dram_traffic_bytes"], "alg_bytes": dom["alg_bytes"]}
         roofline.update({"kernel": f"{dom['op']} layer {dom['layer']} ({dom['geom']})", "ms": dom["ms"],
                          "peak_source": peaks["source"] + " (of measured)"})
     edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
@@ -403,7 +415,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wdesc,
                    "parallelism": (f"row{world} (destination-row partition, NCCL all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
-                                   if partitioned else f"dp{world} (independent graph batches per rank, flat NCCL grad all-reduce)"),
+                                   if partitioned else f"dp{world} (independent graph batches per rank, one-group NCCL all-reduce of the packed gradient buffers)"),
                    "edges_per_layer_incl_self_loops": ep, "input_edges": int(data.edge_index.shape[1]), "nodes": n,
                    "layers": len(spec), "step": "zero_grad + fwd + BCE loss + bwd + grad all-reduce + fused Adam",
                    "l2": "inputs larger than L2 (per-step working set ~2 GB vs 126 MB L2); no explicit flush"},

@@ -75,6 +75,7 @@ def _run(n, f, c, h, x_scale=1.0, g_scale=1.0, keep_split=True, need_gx=True, se
 CASES = [
     # n, f, c, h, kwargs                                      what it reaches
     (512, 64, 32, 4, {}),                                   # BN=128, fused logits (Cp | 128), one k-block
+    (1024, 64, 8, 8, {}),                                   # the smoke() geometry: Dp = 64 (half an n-tile), 8 heads per thread
     (3000, 50, 256, 4, {}),                                 # PPI layer 1: K tail 50, Cp = 256 logits across two warps
     (2048, 256, 64, 4, {}),                                 # BN=256, several heads per epilogue thread
     (1000, 1024, 256, 4, {}),                               # PPI layer 2: K = 1024, gX through MN-major W planes

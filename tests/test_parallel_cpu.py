@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from atmlgraphattentionnetworks_b200.parallel import GradBucket, row_partition, shard_graphs
+from atmlgraphattentionnetworks_b200.parallel import GradBucket, all_reduce_packed_grads, row_partition, shard_graphs
 
 
 def _free_port():
@@ -52,6 +52,62 @@ def test_grad_bucket_all_reduce_matches_single_process():
     want = torch.cat([p.grad.flatten() for p in model.parameters()])
     assert torch.allclose(out[0], out[1])
     assert torch.allclose(out[0], want, rtol=1e-5, atol=1e-7)
+
+
+class _PackedGrad(torch.autograd.Function):
+    """y = x @ w1.T + x @ w2.T with the two weight gradients returned as views of ONE packed buffer (what the GAT layer's
+    backward does for its per-head parameters)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2):
+        ctx.save_for_backward(x)
+        return x @ w1.t() + x @ w2.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        packed = torch.empty(2, g.shape[1], x.shape[1])
+        packed[0] = g.t() @ x
+        packed[1] = g.t() @ x
+        return None, packed[0], packed[1]
+
+
+def _packed_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w1, w2 = torch.randn(3, 6, requires_grad=True), torch.randn(3, 6, requires_grad=True)
+    lin = torch.nn.Linear(3, 2)                              # an ordinary parameter next to the packed ones
+    gen = torch.Generator().manual_seed(100)
+    x_all, y_all = torch.randn(8, 6, generator=gen), torch.randn(8, 2, generator=gen)
+    mine = shard_graphs(8, world, rank)
+    params = [w1, w2, *lin.parameters()]
+    for _ in range(2):
+        for p in params:
+            p.grad = None
+        torch.nn.functional.mse_loss(lin(_PackedGrad.apply(x_all[mine], w1, w2)), y_all[mine]).backward()
+        n_buffers = all_reduce_packed_grads(params)
+    assert w1.grad.untyped_storage().data_ptr() == w2.grad.untyped_storage().data_ptr()   # adopted as views, no copy
+    out[rank] = (n_buffers, torch.cat([p.grad.flatten() for p in params]).clone())
+    dist.destroy_process_group()
+
+
+def test_packed_grad_all_reduce_matches_single_process():
+    world = 2
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_packed_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    w1, w2 = torch.randn(3, 6, requires_grad=True), torch.randn(3, 6, requires_grad=True)
+    lin = torch.nn.Linear(3, 2)
+    gen = torch.Generator().manual_seed(100)
+    x_all, y_all = torch.randn(8, 6, generator=gen), torch.randn(8, 2, generator=gen)
+    torch.nn.functional.mse_loss(lin(_PackedGrad.apply(x_all, w1, w2)), y_all).backward()
+    want = torch.cat([p.grad.flatten() for p in [w1, w2, *lin.parameters()]])
+    assert out[0][0] == 3                                    # one packed base + lin.weight + lin.bias
+    assert torch.allclose(out[0][1], out[1][1])
+    assert torch.allclose(out[0][1], want, rtol=1e-5, atol=1e-7)
 
 
 def test_partition_helpers():
