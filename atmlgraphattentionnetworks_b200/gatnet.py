@@ -27,9 +27,13 @@ _GAT_TABLE = {
 _GCN_OUT = {"CIFAR10": 64, "Cora": 7, "Citeseer": 6, "Pubmed": 3, "AmazonComp": 10, "AmazonPhotos": 8}
 
 
-def segment_mean(x, batch):
-    """torch_scatter.scatter_mean(x, batch, dim=0) (GATNet.py:73): per-graph mean, empty groups -> 0."""
-    groups = int(batch.max().item()) + 1 if batch.numel() else 0
+def segment_mean(x, batch, num_graphs=None):
+    """torch_scatter.scatter_mean(x, batch, dim=0) (GATNet.py:73): per-graph mean, empty groups -> 0.  `num_graphs` (PyG
+    batches carry it as data.num_graphs) avoids the host synchronisation of batch.max().item()."""
+    if num_graphs is not None:
+        groups = int(num_graphs)
+    else:
+        groups = int(batch.max().item()) + 1 if batch.numel() else 0
     total = torch.zeros((groups, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
     count = torch.zeros(groups, dtype=x.dtype, device=x.device).index_add_(
         0, batch, torch.ones(batch.numel(), dtype=x.dtype, device=x.device)).clamp_(min=1)
@@ -76,7 +80,7 @@ class GATNet(torch.nn.Module):
             else:
                 x = act(self.conv1(x, edge_index))
                 x = act(self.conv2(x, edge_index))
-            x = segment_mean(x, data.batch)
+            x = segment_mean(x, data.batch, getattr(data, "num_graphs", None))
             x = F.relu(self.lin1(x))
             return F.log_softmax(self.lin2(x), dim=1)
         x = F.dropout(x, p=0.6, training=self.training)        # GATNet.py:78

@@ -55,6 +55,20 @@ def make_workload(name, seed, sample=None):
         spec = [(50, 64, 8, True)]
         loss_fn = lambda out, y: out.sum()                                     # noqa: E731
         desc = "heads sweep point: one layer 50 -> 8 heads x 64 on the PPI-shaped batch"
+    elif name == "cifar":
+        # BASELINE configs[2]: run_gnn_benchmark.py:35-66 — GATNet('GAT','CIFAR10',F): conv1 -> elu -> conv2 -> elu ->
+        # per-graph mean -> lin1 -> relu -> lin2 -> log_softmax, nll_loss per graph; dropout 0.0 (GATNet.py:19-20)
+        data = synth.cifar_shaped(seed=seed, num_graphs=128 if sample is None else 16)
+        spec = [(5, 8, 8, True), (64, 8, 8, True)]
+        loss_fn = lambda out, y: F.nll_loss(out, y)                            # noqa: E731
+        desc = "CIFAR10-superpixel-shaped batch (128 graphs x ~117 nodes, kNN k=8, 5 feats, 10 classes), GATNet('GAT','CIFAR10',5)"
+    elif name == "cora":
+        # BASELINE configs[0]: run_inductive.py:75-85 — GATNet('GAT','Cora',1433) in training mode (feature dropout 0.6 and
+        # attention dropout 0.6 are active, as in the reference's train step), nll_loss over all nodes
+        data = synth.cora_shaped(seed=seed)
+        spec = [(1433, 8, 8, True), (64, 7, 1, False)]
+        loss_fn = lambda out, y: F.nll_loss(out, y)                            # noqa: E731
+        desc = "Cora-shaped graph (2708 nodes, 10556 edges, 1433 feats, 7 classes), GATNet('GAT','Cora',1433), dropout 0.6 active"
     else:
         raise ValueError(name)
     return data, spec, loss_fn, desc
@@ -159,12 +173,17 @@ class ClockSampler:
 def cpu_reference_leg(workload, steps, warmup, sample):
     """The reference's CPU PyTorch path (oracle port of GAT.py, same op sequence, autograd backward) on all host
     cores, on a bounded sample of the workload.  -> (edges/s, seconds per step, description)."""
-    from oracle.gat_port import PortStack
+    from oracle.gat_port import PortGATNet, PortStack
     torch.set_num_threads(os.cpu_count() or 1)
     data, spec, loss_fn, _ = make_workload(workload, 0, sample=sample)
     torch.manual_seed(0)
-    model = PortStack(spec, dropout=0.0)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4)
+    if workload in ("cifar", "cora"):
+        net = PortGATNet("GAT", "CIFAR10" if workload == "cifar" else "Cora", data.x.shape[1]).train()
+        model = lambda x, ei: net(data)                                        # noqa: E731
+        opt = torch.optim.Adam(net.parameters(), lr=5e-3, weight_decay=5e-4)
+    else:
+        model = PortStack(spec, dropout=0.0)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4)
     ep = layer_edges(data)
 
     def step():
@@ -180,6 +199,8 @@ def cpu_reference_leg(workload, steps, warmup, sample):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
     what = (f"{data.num_graphs} of 24 graphs of the PPI-shaped batch" if workload in ("ppi", "heads") else
+            f"{data.num_graphs} of 128 graphs of the CIFAR-shaped batch" if workload == "cifar" else
+            "the whole Cora-shaped graph" if workload == "cora" else
             "1/32-scale graph from the same power-law generator")
     desc = f"{what}: {data.x.shape[0]} nodes, {ep} edges incl. self loops, {len(spec)} layers, {steps} steps after {warmup} warm-up"
     return len(spec) * ep / dt, dt, desc
@@ -205,7 +226,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ppi", choices=["ppi", "heads", "large"])
+    ap.add_argument("--workload", default="ppi", choices=["ppi", "heads", "large", "cifar", "cora"])
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the resident train step in a CUDA graph and time replays (launch-bound workloads)")
     ap.add_argument("--cpu-sample-graphs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu runs): warm-up + steps, minimal JSON")
@@ -235,7 +258,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the GAT hot path has no CPU fallback); use --impl reference for the CPU leg")
     import torch.distributed as dist
     from atmlgraphattentionnetworks_b200 import _abi
-    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    from atmlgraphattentionnetworks_b200.gatnet import GATNet, GATStack
     from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
     from atmlgraphattentionnetworks_b200.parallel import GradBucket, all_reduce_packed_grads
 
@@ -253,13 +276,22 @@ def main():
     ep = layer_edges(data)
     n = data.x.shape[0]
     torch.manual_seed(0)
-    model = GATStack(spec, dropout=0.0).to(dev)
+    is_net = args.workload in ("cifar", "cora")
+    if is_net:
+        from types import SimpleNamespace
+        net = GATNet("GAT", "CIFAR10" if args.workload == "cifar" else "Cora", data.x.shape[1]).to(dev).train()
+        batch_d = data.batch.to(dev) if hasattr(data, "batch") else None
+        model = lambda x, ei: net(SimpleNamespace(x=x, edge_index=ei, batch=batch_d, num_graphs=data.num_graphs))   # noqa: E731
+        model.parameters = net.parameters
+    else:
+        model = GATStack(spec, dropout=0.0).to(dev)
     # gradients are set to None every step and autograd adopts the kernels' packed output buffers as .grad without a copy;
     # N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (parallel.all_reduce_packed_grads).
     # The row-partitioned large graph keeps the flat bucket (its stage functions build gradients through torch ops).
     bucket = GradBucket(model.parameters()) if (world > 1 and args.workload == "large") else None
     params = list(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True)   # run_inductive.py:18-19,65
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True,   # run_inductive.py:18-19,65
+                           capturable=args.cuda_graph)
     part = None
     if partitioned:
         from atmlgraphattentionnetworks_b200.partition import PartitionedGATStack, build_row_partition
@@ -314,10 +346,33 @@ def main():
     # ---- resident leg ----
     for _ in range(warmup):
         train_step(x_d, ei_d, y_d)
+    resident = lambda: train_step(x_d, ei_d, y_d)                               # noqa: E731
+    launches_per_replay = None
+    if args.cuda_graph:
+        # whole-step capture: zero_grad + forward + loss + backward + fused Adam of the resident
+        # batch become ONE graph launch; the CSR is cached (no host sync inside), every buffer comes from the graph's pool
+        assert world == 1, "--cuda-graph is a single-GPU mode"
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                train_step(x_d, ei_d, y_d)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        l0 = _abi.launch_count()
+        with torch.cuda.graph(graph):
+            static_loss = train_step(x_d, ei_d, y_d)
+        launches_per_replay = _abi.launch_count() - l0
+        resident = graph.replay
+        for _ in range(3):
+            resident()
     launches0 = _abi.launch_count()
     with ClockSampler(local_rank) as clocks:
-        ms_step = timed(lambda: train_step(x_d, ei_d, y_d), args.steps)
+        ms_step = timed(resident, args.steps)
     launches = _abi.launch_count() - launches0
+    if launches_per_replay is not None:
+        launches = launches_per_replay * args.steps
     if args.profile:
         if rank == 0:
             _emit({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches})
@@ -417,7 +472,8 @@ def main():
                    "parallelism": (f"row{world} (destination-row partition, NCCL all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
                                    if partitioned else f"dp{world} (independent graph batches per rank, one-group NCCL all-reduce of the packed gradient buffers)"),
                    "edges_per_layer_incl_self_loops": ep, "input_edges": int(data.edge_index.shape[1]), "nodes": n,
-                   "layers": len(spec), "step": "zero_grad + fwd + BCE loss + bwd + grad all-reduce + fused Adam",
+                   "layers": len(spec), "step": "zero_grad + fwd + loss + bwd + grad all-reduce + fused Adam",
+                   "cuda_graph": bool(args.cuda_graph),
                    "l2": "inputs larger than L2 (per-step working set ~2 GB vs 126 MB L2); no explicit flush"},
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "includes": "H2D from pinned host, CSR build (2 radix sorts), train step, loss D2H"},
