@@ -75,14 +75,53 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int COLS>
+template <int COLS, int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
-template <int COLS>
+template <int COLS, int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// ---- CTA-pair (cta_group::2) helpers.  Shared-memory addresses in the shared::cluster window carry the CTA rank in bit 24;
+// clearing it addresses the same offset in the pair's leader (even) CTA.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a pair member: the bytes land in the executing CTA, the transaction completes on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the pair leader's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(uint16_t(3)) : "memory");
 }
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -127,9 +166,10 @@ template <bool MN>
 __device__ __forceinline__ constexpr uint32_t kstep_bytes() { return MN ? 16 * 128 : 16 * 2; }
 
 // instruction descriptor: kind::f16 with fp16 A/B (format 0), fp32 accumulate (c format 1), M=128, N=BN
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+  return (1u << 4) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) | (uint32_t(BN >> 3) << 17) |
+         (uint32_t((TC_BM * CG) >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
@@ -147,13 +187,19 @@ struct TcGemmParams {
 
 enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2 };
 
-template <int BN>
+// CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA PAIR (cluster of two SMs) computes one 256 x BN
+// tile: each CTA stages its own 128 A rows and HALF of the B tile (BN/2 rows), one tcgen05.mma.cta_group::2 issued by the
+// leader multiplies both, and each CTA's TMEM receives its own 128 rows of the result.  B is fetched once per pair (the
+// 1-CTA kernel is bound by operand bytes entering the SM: 96 KB per 1536-cycle k-block) and a stage shrinks to 64 KB, so
+// three stages fit.
+template <int BN, int CG = 1>
 struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int STAGES = (BN == 256 && CG == 1) ? 2 : 3;
   static constexpr int EPI_WARPS = 4 * (BN / 128);
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;            // 16 KB per plane
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_ROWS = BN / CG;                       // B rows staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int VEC_BYTES = 3 * BN * 4;                 // bias / a1 / a2 slices of the current tile
   static constexpr int RED_BYTES = 2 * TC_BM * 4;              // cross-half logit partials (BN = 256, Cp = 256)
@@ -162,22 +208,29 @@ struct TcCfg {
 };
 
 // one operand plane of one k-block: K-major = one box {64 k, ROWS}; MN-major = ROWS/64 boxes {64 mn, 64 k}
-template <bool MN, int ROWS>
+template <bool MN, int ROWS, int CG>
 __device__ __forceinline__ void load_plane(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int k0, int mn0) {
   if (!MN) {
-    tma_load_2d(dst, map, bar, k0, mn0);
+    if (CG == 1) tma_load_2d(dst, map, bar, k0, mn0);
+    else tma_load_2d_pair(dst, map, bar, k0, mn0);
   } else {
 #pragma unroll
-    for (int c = 0; c < ROWS / 64; ++c) tma_load_2d(dst + c * TC_MN_CHUNK_BYTES, map, bar, mn0 + 64 * c, k0);
+    for (int c = 0; c < ROWS / 64; ++c) {
+      if (CG == 1) tma_load_2d(dst + c * TC_MN_CHUNK_BYTES, map, bar, mn0 + 64 * c, k0);
+      else tma_load_2d_pair(dst + c * TC_MN_CHUNK_BYTES, map, bar, mn0 + 64 * c, k0);
+    }
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
+__global__ void __launch_bounds__(TcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                const TcGemmParams p) {
-  using S = TcCfg<BN>;
+  using S = TcCfg<BN, CG>;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;      // position in the CTA pair; 0 = leader (issues the MMAs)
+  const int unit = CG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);          // the pair / CTA walking the item list
+  const int nunits = CG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: an integer round trip would
@@ -201,18 +254,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bl)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);                   // pair: only the leader's copy is used (both CTAs' TMA bytes land on it)
+      mbar_init(&empty_bar[s], 1);                  // one (multicast) tcgen05.commit per use
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], S::EPI_WARPS);
+      mbar_init(&tempty_bar[b], CG * S::EPI_WARPS); // pair: the leader's copy collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_ptr);
+  if (warp == 1) tmem_alloc<2 * BN, CG>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();                      // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -221,8 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   auto item_coords = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
     const int nt = w % p.n_tiles;
     const int r = w / p.n_tiles;
-    const int mt = r % p.m_tiles, sp = r / p.m_tiles;
-    m0 = mt * TC_BM;
+    const int mt = r % p.m_tiles, sp = r / p.m_tiles;   // m_tiles counts 128*CG-row tiles
+    m0 = mt * (TC_BM * CG) + int(rank) * TC_BM;          // this CTA's 128 rows
     n0 = nt * BN;
     kb0 = sp * p.k_blocks_per_split;
     const int kb1 = (kb0 + p.k_blocks_per_split < p.k_blocks) ? kb0 + p.k_blocks_per_split : p.k_blocks;
@@ -233,29 +287,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      for (int w = unit; w < total_items; w += nunits) {
         int m0, n0, kb0, nkb;
         item_coords(w, m0, n0, kb0, nkb);
+        const int nb0 = n0 + int(rank) * S::B_ROWS;     // pair: this CTA stages its half of the B tile
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t st = smem_u32(stage_base + s * S::STAGE_BYTES);
-          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], CG * S::STAGE_BYTES);   // the bytes of BOTH CTAs
           const int k0 = (kb0 + i) * TC_BK;
-          load_plane<A_MN, TC_BM>(st, &map_ah, &full_bar[s], k0, m0);
-          load_plane<A_MN, TC_BM>(st + S::A_BYTES, &map_al, &full_bar[s], k0, m0);
-          load_plane<B_MN, BN>(st + 2 * S::A_BYTES, &map_bh, &full_bar[s], k0, n0);
-          load_plane<B_MN, BN>(st + 2 * S::A_BYTES + S::B_BYTES, &map_bl, &full_bar[s], k0, n0);
+          load_plane<A_MN, TC_BM, CG>(st, &map_ah, &full_bar[s], k0, m0);
+          load_plane<A_MN, TC_BM, CG>(st + S::A_BYTES, &map_al, &full_bar[s], k0, m0);
+          load_plane<B_MN, S::B_ROWS, CG>(st + 2 * S::A_BYTES, &map_bh, &full_bar[s], k0, nb0);
+          load_plane<B_MN, S::B_ROWS, CG>(st + 2 * S::A_BYTES + S::B_BYTES, &map_bl, &full_bar[s], k0, nb0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN, CG>();
       uint32_t it = 0, chunk = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      for (int w = unit; w < total_items; w += nunits) {
         int m0, n0, kb0, nkb;
         item_coords(w, m0, n0, kb0, nkb);
         for (int i = 0; i < nkb; ++i, ++it) {
@@ -278,13 +333,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             const uint32_t ao = ks * kstep_bytes<A_MN>(), bo = ks * kstep_bytes<B_MN>();
             const uint64_t dah = make_sdesc<A_MN>(a_hi + ao), dal = make_sdesc<A_MN>(a_lo + ao);
             const uint64_t dbh = make_sdesc<B_MN>(b_hi + bo), dbl = make_sdesc<B_MN>(b_lo + bo);
-            mma_f16(d_tmem, dal, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
-            mma_f16(d_tmem, dah, dbl, idesc, 1u);
-            mma_f16(d_tmem, dah, dbh, idesc, 1u);
+            if (CG == 1) {
+              mma_f16(d_tmem, dal, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
+              mma_f16(d_tmem, dah, dbl, idesc, 1u);
+              mma_f16(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              mma_f16_pair(d_tmem, dal, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
+              mma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
+              mma_f16_pair(d_tmem, dah, dbh, idesc, 1u);
+            }
           }
-          mma_commit(&empty_bar[s]);                  // frees the stage once these MMAs have read it
-          if (chunk_last) {
-            mma_commit(&tfull_bar[b]);                // chunk complete in TMEM buffer b
+          // frees the stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 1) mma_commit(&empty_bar[s]); else mma_commit_pair(&empty_bar[s]);
+          if (chunk_last) {                           // chunk complete in TMEM buffer b (of both CTAs)
+            if (CG == 1) mma_commit(&tfull_bar[b]); else mma_commit_pair(&tfull_bar[b]);
             ++chunk;
           }
         }
@@ -298,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int cbase = half * 128;                   // first tile column of this thread
     const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
     uint32_t chunk = 0;
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    for (int w = unit; w < total_items; w += nunits) {
       int m0, n0, kb0, nkb;
       item_coords(w, m0, n0, kb0, nkb);
       const int nchunks = (nkb + TC_KC - 1) / TC_KC;
@@ -335,7 +397,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[b]);
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(&tempty_bar[b]); else mbar_arrive_leader(&tempty_bar[b]);
+        }
       }
 
       const int64_t col0 = int64_t(n0) + cbase;       // first global column of this thread
@@ -424,9 +488,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();                      // the peer may still be signalling this CTA's barriers / reading its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<2 * BN, CG>(tmem_base);
   }
 }
 
@@ -548,23 +613,74 @@ static int launch_split(const float* src, int64_t ld, const Blob& b, cudaStream_
   return check_launch("split_kernel");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      TcGemmParams p, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, CG>;
+  using S = TcCfg<BN, CG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::TOTAL);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "proj_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  p.m_tiles = static_cast<int>(ceil_div(p.M, TC_BM));
+  p.m_tiles = static_cast<int>(ceil_div(p.M, TC_BM * CG));
   p.n_tiles = static_cast<int>(ceil_div(p.N, BN));
   const int64_t items = int64_t(p.m_tiles) * p.n_tiles * p.splits;
-  const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-  kern<<<grid, TcCfg<BN>::THREADS, TcCfg<BN>::TOTAL, stream>>>(ah, al, bh, bl, p);
+  if (CG == 1) {
+    const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
+    kern<<<grid, S::THREADS, S::TOTAL, stream>>>(ah, al, bh, bl, p);
+  } else {
+    // persistent pairs: as many clusters as can be co-resident (GPCs with an odd SM count leave an SM without a partner)
+    static int max_pairs = 0;
+    static std::once_flag once2;
+    std::call_once(once2, [&] {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(2 * sm_count());
+      q.blockDim = dim3(S::THREADS);
+      q.dynamicSmemBytes = S::TOTAL;
+      cudaLaunchAttribute qa;
+      qa.id = cudaLaunchAttributeClusterDimension;
+      qa.val.clusterDim.x = 2; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+      q.attrs = &qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) n = sm_count() / 2 - 4;
+      max_pairs = n;
+      (void)cudaGetLastError();
+    });
+    const int64_t units = max_pairs;
+    const int grid = static_cast<int>((items < units ? items : units) * CG);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(S::THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, p);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "proj_tc: cluster launch: %s", cudaGetErrorString(e));
+  }
   return check_launch("gemm_tc_kernel");
+}
+
+// The CTA-pair kernel is OPT-IN (B200GAT_GEMM_PAIR=1): it passes every parity test, but measured on the PPI-shaped
+// GEMMs it is no faster than the single-CTA kernel (forward 229.9 vs 227 us, gX 298 vs 303, gW 271 vs 296) — at
+// ~1.56 PFLOP/s of fp16 MMA work those kernels already run at 92 % of the pool's measured cuBLAS bf16 burst rate
+// (1.69 PFLOP/s; the part is power-limited well below the nominal 2.25), so halving the operand bytes buys nothing.
+static bool use_pair(int64_t M, int bn) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200GAT_GEMM_PAIR");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on && bn == 256 && M >= 256;
 }
 
 // C[M,N] (=, +bias | +=) A · B^T.  A is the blob of a [M,K] (K-major) or [K,M] (A_MN) tensor, B of a [N,K] (K-major)
@@ -582,13 +698,15 @@ static int gemm_blobs(const Blob& A, const Blob& B, int64_t M, int64_t N, int64_
   const int bn = N > 128 ? 256 : 128;
   CUtensorMap ah, al, bh, bl;
   int rc;
-  const int a_box = A_MN ? 64 : TC_BM, b_box = B_MN ? 64 : bn;
+  const bool pair = use_pair(M, bn);
+  const int a_box = A_MN ? 64 : TC_BM, b_box = B_MN ? 64 : (pair ? bn / 2 : bn);
   if ((rc = make_map(&ah, A.hi(), A.rows, A.cols, A.ldp, a_box))) return rc;
   if ((rc = make_map(&al, A.lo(), A.rows, A.cols, A.ldp, a_box))) return rc;
   if ((rc = make_map(&bh, B.hi(), B.rows, B.cols, B.ldp, b_box))) return rc;
   if ((rc = make_map(&bl, B.lo(), B.rows, B.cols, B.ldp, b_box))) return rc;
-  if (bn == 256) return launch_tc<256, A_MN, B_MN, EPI>(ah, al, bh, bl, p, stream);
-  return launch_tc<128, A_MN, B_MN, EPI>(ah, al, bh, bl, p, stream);
+  if (pair) return launch_tc<256, A_MN, B_MN, EPI, 2>(ah, al, bh, bl, p, stream);
+  if (bn == 256) return launch_tc<256, A_MN, B_MN, EPI, 1>(ah, al, bh, bl, p, stream);
+  return launch_tc<128, A_MN, B_MN, EPI, 1>(ah, al, bh, bl, p, stream);
 }
 
 // ---- shape gates: the tensor-core path takes the projections that are worth a 128-row tile pipeline -----------------

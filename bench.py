@@ -381,14 +381,31 @@ def main():
         return 0
 
     # ---- end-to-end leg: pinned host buffers in, loss out, every step (new tensors => CSR rebuilt every step) ----
-    def e2e_step():
-        x = x_h.to(dev, non_blocking=True)
-        ei = ei_h.to(dev, non_blocking=True)
-        y = y_h.to(dev, non_blocking=True)
-        return float(train_step(x, ei, y).item())
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, max(args.steps // 2, 3))
+    # The host->device copy of step k+1 is issued on a copy stream while step k computes (what a data loader with a
+    # prefetch depth of one does): every step still copies its own inputs from pinned host memory inside the timed
+    # region, builds its CSR from the fresh edge_index, and reads its loss back.
+    copy_stream = torch.cuda.Stream()
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            bufs = (x_h.to(dev, non_blocking=True), ei_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True))
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return bufs, done
+
+    def e2e_run(steps):
+        nxt = upload()
+        for k in range(steps):
+            (x, ei, y), done = nxt
+            if k + 1 < steps:
+                nxt = upload()
+            torch.cuda.current_stream().wait_event(done)
+            for t in (x, ei, y):
+                t.record_stream(torch.cuda.current_stream())
+            float(train_step(x, ei, y).item())
+    e2e_run(2)
+    e2e_steps = max(args.steps // 2, 3)
+    ms_e2e = timed(lambda: e2e_run(e2e_steps), 1) / e2e_steps
     h2d = x_h.numel() * 4 + ei_h.numel() * 8 + y_h.numel() * y_h.element_size()
 
     # ---- per-op breakdown (CUDA events around each C-ABI call) ----
@@ -476,7 +493,7 @@ def main():
                    "cuda_graph": bool(args.cuda_graph),
                    "l2": "inputs larger than L2 (per-step working set ~2 GB vs 126 MB L2); no explicit flush"},
         "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "includes": "H2D from pinned host, CSR build (2 radix sorts), train step, loss D2H"},
+                "d2h_bytes_per_step": 4, "includes": "H2D from pinned host (prefetch depth 1 on a copy stream), CSR build (2 radix sorts), train step, loss D2H"},
         "gpu_launches": launches, "roofline": roofline, "edge_phase": edge_phase, "kernels": kernels,
         "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
