@@ -594,7 +594,9 @@ static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t 
   const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  (void)streaming;   // measured on the power-law graph: the batched (256, 2) build is slower here (48.2 vs 42.6 ms)
+  // measured on the power-law graph: the batched builds (launch_bounds (256, 2) and (256, 3)) are SLOWER here (48.2 /
+  // 48.3 vs 42.6 ms): the per-batch dot-product reduce chain wants warps, not loads in flight
+  (void)streaming;
   if (p.mask) edge_bwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
   else edge_bwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_kernel");
