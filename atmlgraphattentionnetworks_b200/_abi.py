@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -23,7 +23,8 @@ class Graph(C.Structure):
 
 class Layer(C.Structure):
     _fields_ = [("in_channels", C.c_int64), ("out_channels", C.c_int64), ("heads", C.c_int64), ("c_pad", C.c_int64),
-                ("concat", C.c_int32), ("negative_slope", C.c_float)]
+                ("concat", C.c_int32), ("negative_slope", C.c_float), ("logit_activation", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class ProjFwdArgs(C.Structure):
@@ -93,6 +94,7 @@ class ProjBwdArgs(C.Structure):
 
 
 ACT_NONE, ACT_ELU = 0, 1
+LOGIT_LEAKY_RELU, LOGIT_LOGSIGMOID, LOGIT_TANH = 0, 1, 2
 
 _SIGNATURES = {
     "b200gat_abi_version": (C.c_int, []),

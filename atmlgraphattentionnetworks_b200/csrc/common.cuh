@@ -33,6 +33,8 @@ inline int validate_layer(const b200gat_layer& L) {
                   "layer: c_pad must be round_up(out_channels, 4)");
   B200GAT_REQUIRE(L.c_pad <= 512, B200GAT_E_UNSUPPORTED, "layer: out_channels > 512 per head is not supported");
   B200GAT_REQUIRE(L.heads <= 1024, B200GAT_E_UNSUPPORTED, "layer: more than 1024 heads is not supported");
+  B200GAT_REQUIRE(L.logit_activation >= B200GAT_LOGIT_LEAKY_RELU && L.logit_activation <= B200GAT_LOGIT_TANH,
+                  B200GAT_E_UNSUPPORTED, "layer: unknown logit_activation %d", L.logit_activation);
   return 0;
 }
 
@@ -49,6 +51,23 @@ inline int validate_graph(const b200gat_graph& g) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
+
+// logit activation e = f(z) and f'(z) (include/b200gat.h B200GAT_LOGIT_*).  GENERIC = false is the LeakyReLU of GAT.py:30
+// with no trace of the other variants in the generated code (the CSC pass's code generation is fragile).
+template <bool GENERIC>
+__device__ __forceinline__ float logit_act(float z, float slope, int act) {
+  if (!GENERIC) return leaky(z, slope);
+  if (act == B200GAT_LOGIT_TANH) return tanhf(z);
+  if (act == B200GAT_LOGIT_LOGSIGMOID) return fminf(z, 0.f) - log1pf(expf(-fabsf(z)));   // -softplus(-z), stable
+  return leaky(z, slope);
+}
+template <bool GENERIC>
+__device__ __forceinline__ float logit_act_grad(float z, float slope, int act) {
+  if (!GENERIC) return z > 0.f ? 1.f : slope;
+  if (act == B200GAT_LOGIT_TANH) { const float t = tanhf(z); return 1.f - t * t; }
+  if (act == B200GAT_LOGIT_LOGSIGMOID) return 1.f / (1.f + expf(z));                     // sigmoid(-z)
+  return z > 0.f ? 1.f : slope;
+}
 
 template <int G>
 __device__ __forceinline__ float group_max(float v) {

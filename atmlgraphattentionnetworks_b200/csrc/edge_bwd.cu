@@ -292,7 +292,7 @@ colsum_kernel(const float* __restrict__ in, int64_t ld, int64_t N, int ncols, in
 struct EdgeBwdParams {
   int64_t N, items;
   int H, Cp, Dp;
-  float slope;
+  float slope; int act;
   const int32_t* colptr; const int32_t* crow; const int32_t* ceid;
   const float* wh; const float* s_src; const float4* rowrec; const float* mask;
   const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
@@ -359,8 +359,8 @@ __device__ __forceinline__ float reduce_deliver(float (&d)[U], int lane, int rel
   return got;
 }
 
-template <int G, int NV, bool HAS_MASK>
-__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
+template <int G, int NV, bool HAS_MASK, bool GENERIC>
+__device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
   // edges gathered per step: bytes in flight decide the streaming-regime throughput (measured: 4 -> 8 gathers in
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp, ldg = p.ldg;
   const float slope = p.slope;
+  const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored; their Wh slice is zero
   int off[NV];
   bool live[NV];
@@ -412,9 +413,9 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
         i = __ldg(p.crow + k);
         const float4 rr = __ldg(p.rowrec + int64_t(i) * H + h);   // {s_dst, rowmax, 1/(rowsum+eps), Drow}
         const float z = rr.x + ss;
-        dslope = z > 0.f ? 1.f : slope;
-        alpha = expf(leaky(z, slope) - rr.y) * rr.z;
-        if (HAS_MASK) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
+        dslope = logit_act_grad<GENERIC>(z, slope, act);
+        alpha = expf(logit_act<GENERIC>(z, slope, act) - rr.y) * rr.z;
+        if (HAS_MASK && (!GENERIC || p.mask)) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
         at = alpha * mk;
         dr = rr.w;
       }
@@ -475,6 +476,12 @@ __global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) {
       if (live[v]) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off[v]) = acc[v];
   }
 }
+
+template <int G, int NV, bool HAS_MASK>
+__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, HAS_MASK, false>(p); }
+// other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
+template <int G, int NV>
+__global__ void __launch_bounds__(256) edge_bwd_act_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, true, true>(p); }
 
 // ---- gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2, plus every column sum the parameters need.  gT is written in
 // place as fp32, or — when the projection backward runs on the tensor cores — directly as that GEMM's operand split
@@ -597,7 +604,8 @@ static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t 
   // measured on the power-law graph: the batched builds (launch_bounds (256, 2) and (256, 3)) are SLOWER here (48.2 /
   // 48.3 vs 42.6 ms): the per-batch dot-product reduce chain wants warps, not loads in flight
   (void)streaming;
-  if (p.mask) edge_bwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_bwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
+  else if (p.mask) edge_bwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
   else edge_bwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_kernel");
 }
@@ -697,7 +705,7 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
                    int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, cudaStream_t stream) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
-  p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope;
+  p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
   p.colptr = colptr; p.crow = crow; p.ceid = ceid;
   p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.mask = mask;
   p.g = gsrc_rows; p.ldg = ldg; p.hs = hs;

@@ -21,7 +21,7 @@ namespace b200gat {
 struct EdgeFwdParams {
   int64_t N, items;
   int H, C, Cp, Dp;
-  float slope;
+  float slope; int act;
   const int32_t* rowptr; const int32_t* col; const int32_t* eid;
   const float* wh; const float* s_src; const float* s_dst; const float* bias; const float* mask;
   float* out; int64_t ldo;
@@ -35,7 +35,7 @@ struct EdgeFwdParams {
 // makes ptxas issue ALL U*NV gathers of a batch back to back (76 registers) — 3x the bytes in flight per warp at 3/4
 // of the occupancy.  Measured (tools/microbench/gather_bench.cu, power-law graph): 5.3 vs 3.7 TB/s gathered.  On the
 // L2-resident PPI-shaped batch the same build is 13 % SLOWER than the occupancy-first one, hence two instantiations.
-template <int G, int NV, bool HAS_MASK, bool STREAM>
+template <int G, int NV, bool HAS_MASK, bool STREAM, bool GENERIC = false>
 __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -45,6 +45,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
   const float slope = p.slope;
+  const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored
   int off[NV];
 #pragma unroll
@@ -97,7 +98,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         };
         load_batch(0);
         float e = -INFINITY;
-        if (ok) e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
+        if (ok) e = logit_act<GENERIC>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
         const float m_new = fmaxf(m, group_max<G>(e));
         if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
           const float scale = expf(m - m_new);
@@ -138,7 +139,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         float e = -INFINITY;
         if (ok) {
           j = __ldg(p.col + k);
-          e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
+          e = logit_act<GENERIC>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
         }
         const float m_new = fmaxf(m, group_max<G>(e));
         if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
@@ -154,7 +155,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         if (ok) {
           pp = expf(e - m);
           pm = pp;
-          if (HAS_MASK) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
+          if (HAS_MASK && (!GENERIC || p.mask)) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
         }
         l += pp;
         const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
@@ -242,6 +243,9 @@ template <int G, int NV, bool HAS_MASK>
 __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, HAS_MASK, false>(p); }
 template <int G, int NV>
 __global__ void __launch_bounds__(256, 3) edge_fwd_stream_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, false, true>(p); }
+// other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
+template <int G, int NV>
+__global__ void __launch_bounds__(256) edge_fwd_act_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, true, false, true>(p); }
 
 // concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c]
 __global__ void __launch_bounds__(256)
@@ -269,7 +273,8 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
   const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  if (p.mask) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_fwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
+  else if (p.mask) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
   else if (streaming && G >= 16) edge_fwd_stream_kernel<(G >= 16 ? G : 32), (G >= 16 ? NV : 1)><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_kernel");
@@ -303,7 +308,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   EdgeFwdParams p;
   p.N = N; p.items = N * H;
   p.H = H; p.C = C; p.Cp = Cp; p.Dp = H * Cp;
-  p.slope = L.negative_slope;
+  p.slope = L.negative_slope; p.act = L.logit_activation;
   p.rowptr = a->graph.rowptr; p.col = a->graph.col; p.eid = a->graph.eid;
   p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.bias = a->bias; p.mask = a->mask;
   p.out = a->out; p.ldo = a->ldo; p.rowmax = a->rowmax; p.rowsum = a->rowsum; p.o_heads = a->o_heads;

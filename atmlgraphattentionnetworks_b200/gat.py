@@ -20,8 +20,9 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _layer_struct(f_in, c, h, concat):
-    return _abi.Layer(int(f_in), int(c), int(h), (int(c) + 3) // 4 * 4, 1 if concat else 0, NEGATIVE_SLOPE)
+def _layer_struct(f_in, c, h, concat, logit_activation=0, negative_slope=NEGATIVE_SLOPE):
+    return _abi.Layer(int(f_in), int(c), int(h), (int(c) + 3) // 4 * 4, 1 if concat else 0, float(negative_slope),
+                      int(logit_activation), 0)
 
 
 def _call(name, fn, args, stream, tag):
@@ -58,11 +59,11 @@ class GATLayerFunction(torch.autograd.Function):
     def forward(ctx, x, bias, graph, geom, mask, fuse, packed, *params):
         w, bw, a1, a2, b1, b2 = packed
         f_in, c, h, concat = geom
-        act_in, act_out, x_amax = fuse
+        act_in, act_out, x_amax, logit = fuse
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
-        layer = _layer_struct(f_in, c, h, concat)
+        layer = _layer_struct(f_in, c, h, concat, *logit)
         cp = layer.c_pad
         dp = h * cp
         d_out = h * c if concat else c
@@ -95,7 +96,7 @@ class GATLayerFunction(torch.autograd.Function):
                                   rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr())
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
-        ctx.graph, ctx.geom, ctx.mask, ctx.act = graph, geom, mask, (bool(act_in), bool(act_out))
+        ctx.graph, ctx.geom, ctx.mask, ctx.act, ctx.logit = graph, geom, mask, (bool(act_in), bool(act_out)), logit
         ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads,
                               x_split)
         ctx.mark_non_differentiable(out_amax)
@@ -109,7 +110,7 @@ class GATLayerFunction(torch.autograd.Function):
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
-        layer = _layer_struct(f_in, c, h, concat)
+        layer = _layer_struct(f_in, c, h, concat, *ctx.logit)
         cp = layer.c_pad
         dp = h * cp
         d_out = h * c if concat else c
@@ -189,6 +190,8 @@ class GraphAttentionLayer(torch.nn.Module):
         self.graph_cache = GLOBAL_CACHE
         self.mask_hook = None   # parity tests: callable (E', H) -> keep-multiplier [E', H] in ORIGINAL edge order
         self._store = None      # persistent packed parameter storage (see _packed_storage)
+        # the function applied to the edge logits before the softmax: (B200GAT_LOGIT_* code, negative slope); GAT.py:30
+        self.logit_activation = (_abi.LOGIT_LEAKY_RELU, NEGATIVE_SLOPE)
 
     # ---- persistent packed storage: the kernels read ONE [Dp, F] / [Dp] / [H] set of arrays per layer (head-major, rows
     # padded to c_pad with zeros).  The per-head Linear parameters of GAT.py:19-25 (and the state_dict keys that come with
@@ -299,5 +302,33 @@ class GraphAttentionLayer(torch.nn.Module):
             raise TypeError("GraphAttentionLayer parameters must be float32 CUDA tensors (move the module with .to(device))")
         packed = self._packed_storage()
         geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
-        return GATLayerFunction.apply(x, self.bias, graph, geom, mask, (bool(act_in), bool(act_out), x_amax), packed,
+        return GATLayerFunction.apply(x, self.bias, graph, geom, mask,
+                                      (bool(act_in), bool(act_out), x_amax, tuple(self.logit_activation)), packed,
                                       *self._head_parameters())
+
+
+def _logit_code(fn):
+    """torch activation module -> (B200GAT_LOGIT_* code, negative slope) — run_act_func_experiment.py:111."""
+    if isinstance(fn, torch.nn.LeakyReLU):
+        return _abi.LOGIT_LEAKY_RELU, float(fn.negative_slope)
+    if isinstance(fn, torch.nn.LogSigmoid):
+        return _abi.LOGIT_LOGSIGMOID, NEGATIVE_SLOPE
+    if isinstance(fn, torch.nn.Tanh):
+        return _abi.LOGIT_TANH, NEGATIVE_SLOPE
+    if isinstance(fn, torch.nn.Softmax):
+        raise NotImplementedError(
+            "nn.Softmax() on the [E', H] logits normalises ACROSS THE HEADS of one edge (implicit dim=1; with one head "
+            "it degenerates to uniform attention): it couples the heads and is not offered by the fused kernels")
+    raise NotImplementedError(f"logit activation {type(fn).__name__} is not offered by the fused kernels "
+                              "(LeakyReLU, LogSigmoid, Tanh are)")
+
+
+class GraphAttentionLayerActivationTest(GraphAttentionLayer):
+    """run_act_func_experiment.py:13-74 — the same layer with a configurable logit activation
+    (`activation_function`, default LeakyReLU(0.2)): same parameters, init order and state_dict keys."""
+
+    def __init__(self, input_channels, output_channels, num_heads=1, concat=False, dropout=0.6,
+                 activation_function=None):
+        super().__init__(input_channels, output_channels, num_heads=num_heads, concat=concat, dropout=dropout)
+        self.attention_relu = activation_function if activation_function is not None else torch.nn.LeakyReLU(negative_slope=0.2)
+        self.logit_activation = _logit_code(self.attention_relu)

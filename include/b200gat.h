@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 7
+#define B200GAT_ABI_VERSION 8
 
 enum {
   B200GAT_OK = 0,
@@ -73,7 +73,14 @@ typedef struct {
   int64_t c_pad;           /* round_up(C, 4) */
   int32_t concat;          /* GAT.py:63-66 */
   float negative_slope;    /* GAT.py:30 (0.2) */
+  int32_t logit_activation;   /* B200GAT_LOGIT_*: the function applied to a_i + a_j before the softmax (GAT.py:58) */
+  int32_t reserved;
 } b200gat_layer;
+
+/* Logit activations.  GAT.py:30 fixes LeakyReLU(0.2); run_act_func_experiment.py:15,111 runs the same layer with
+ * LogSigmoid and Tanh (its third variant, nn.Softmax() over the head axis, couples the heads of an edge and is not
+ * offered by the fused kernels). */
+enum { B200GAT_LOGIT_LEAKY_RELU = 0, B200GAT_LOGIT_LOGSIGMOID = 1, B200GAT_LOGIT_TANH = 2 };
 
 int b200gat_abi_version(void);
 /* number of kernels this library has launched in the process so far (its own kernels; CUB sort passes excluded) */

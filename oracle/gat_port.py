@@ -33,8 +33,10 @@ def segment_softmax(val, index, num_nodes):
 class PortGraphAttentionLayer(torch.nn.Module):
     """Same constructor, parameter registration order and state_dict keys as GAT.py:8-35."""
 
-    def __init__(self, input_channels, output_channels, num_heads=1, concat=False, dropout=0.6):
+    def __init__(self, input_channels, output_channels, num_heads=1, concat=False, dropout=0.6, activation_function=None):
         super().__init__()
+        # run_act_func_experiment.py:15,37: the same layer with another logit activation (default GAT.py:30)
+        self.attention_relu = activation_function if activation_function is not None else torch.nn.LeakyReLU(negative_slope=0.2)
         self.input_channels, self.output_channels = input_channels, output_channels
         self.num_heads, self.dropout_val, self.concat = num_heads, dropout, concat
         self.ws = torch.nn.ModuleList()
@@ -68,7 +70,7 @@ class PortGraphAttentionLayer(torch.nn.Module):
         s_dst = torch.stack(s_dst).squeeze(-1).T                            # [N,H]     GAT.py:52
         x_j = wh.index_select(0, src)                                       # [E',H,C]  propagate/_collect
         z = s_dst.index_select(0, dst) + s_src.index_select(0, src)         # GAT.py:57
-        e = F.leaky_relu(z, 0.2)                                            # GAT.py:58,30
+        e = self.attention_relu(z)                                          # GAT.py:58,30 / run_act_func_experiment.py:62
         alpha = segment_softmax(e, dst, n)                                  # GAT.py:60
         if self.mask_hook is not None:
             alpha = alpha * self.mask_hook(alpha.shape).to(alpha.dtype)

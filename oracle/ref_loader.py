@@ -48,3 +48,21 @@ def load():
             sys.modules.pop("GAT", None)
     _cache["mods"] = (ref_gat, ref_net)
     return _cache["mods"]
+
+
+def load_act_experiment():
+    """The reference's run_act_func_experiment.py module, UNMODIFIED (its experiment lives in main(), which is not
+    run): gives GraphAttentionLayerActivationTest (run_act_func_experiment.py:13-74)."""
+    if "act" in _cache:
+        return _cache["act"]
+    if not os.path.isfile(os.path.join(REFERENCE_DIR, "run_act_func_experiment.py")):
+        raise FileNotFoundError(f"reference not found under {REFERENCE_DIR}")
+    sys.path.insert(0, _STANDIN)
+    try:
+        for k in [m for m in sys.modules if m == "torch_geometric" or m.startswith("torch_geometric.")
+                  or m == "torch_scatter"]:
+            del sys.modules[k]
+        _cache["act"] = _load("run_act_func_experiment", "_reference_run_act_func_experiment")
+    finally:
+        sys.path.remove(_STANDIN)
+    return _cache["act"]

@@ -42,6 +42,17 @@ LAYER_CASES = [
 ]
 
 
+# run_act_func_experiment.py:13-74,111: the same layer with another logit activation.  name, N, E, F, C, H, concat, p, act
+ACT_CASES = [
+    ("logsigmoid_h8c8_cat_drop", 120, 700, 33, 8, 8, True, 0.6, "log_sigmoid"),
+    ("tanh_h8c8_cat_drop", 120, 700, 33, 8, 8, True, 0.6, "tanh"),
+    ("logsigmoid_h1c7_mean", 80, 400, 64, 7, 1, False, 0.0, "log_sigmoid"),
+    ("tanh_h4c16_mean", 90, 600, 20, 16, 4, False, 0.0, "tanh"),
+    ("tanh_h2c64_cat", 100, 900, 40, 64, 2, True, 0.0, "tanh"),
+]
+ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh}
+
+
 def make_graph(name, n, e, special, gen):
     if e == 0:
         return torch.zeros(2, 0, dtype=torch.int64)
@@ -91,11 +102,15 @@ class patched_dropout:
         torch.nn.functional.dropout = self.orig
 
 
-def run_layer(ref_gat, case):
+def run_layer(ref_gat, case, act=None):
     name, n, e, f, c, h, concat, p, special = case
     gen = torch.Generator().manual_seed(sum(map(ord, name)))
     torch.manual_seed(sum(map(ord, name)) + 1)
-    layer = ref_gat.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p)
+    if act is None:
+        layer = ref_gat.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p)
+    else:      # ref_gat is the reference's run_act_func_experiment module here
+        layer = ref_gat.GraphAttentionLayerActivationTest(f, c, num_heads=h, concat=concat, dropout=p,
+                                                         activation_function=ACTIVATIONS[act]())
     with torch.no_grad():
         layer.bias.uniform_(-0.5, 0.5)                   # zero at init (GAT.py:32-35); made non-trivial here
         if special == "big":
@@ -164,6 +179,12 @@ def main():
         rec = run_layer(ref_gat, case)
         np.savez_compressed(os.path.join(HERE, f"layer_{case[0]}.npz"), **rec)
         print("layer", case[0], {k: v.shape for k, v in rec.items() if k in ("x", "edge_index", "out_f32")})
+    ref_act = ref_loader.load_act_experiment()
+    for (name, n, e, f, c, h, concat, p, act) in ACT_CASES:
+        rec = run_layer(ref_act, (name, n, e, f, c, h, concat, p, ""), act=act)
+        rec["activation"] = np.array(act)
+        np.savez_compressed(os.path.join(HERE, f"actlayer_{name}.npz"), **rec)
+        print("actlayer", name, act)
     np.savez_compressed(os.path.join(HERE, "net_cora.npz"), **run_net(ref_net, "Cora", 37, 150, 700, 0, 11))
     np.savez_compressed(os.path.join(HERE, "net_cifar_f3.npz"), **run_net(ref_net, "CIFAR10", 3, 160, 1280, 8, 12))
     np.savez_compressed(os.path.join(HERE, "net_pubmed.npz"), **run_net(ref_net, "Pubmed", 21, 130, 600, 0, 13, classes=3))

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from util import (FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, load_packed, nerr, packed_grads)
+from util import (ACT_FILES, ACTIVATIONS, FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, load_packed, nerr,
+                  packed_grads)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -19,7 +20,12 @@ DEV = "cuda:0"
 def _product_layer(g):
     import GAT
     H, C, F = g["W"].shape
-    layer = GAT.GraphAttentionLayer(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]))
+    if "activation" in g:       # fixtures of the reference's run_act_func_experiment.py layer
+        from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest
+        layer = GraphAttentionLayerActivationTest(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]),
+                                                  activation_function=ACTIVATIONS[str(g["activation"])]())
+    else:
+        layer = GAT.GraphAttentionLayer(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]))
     load_packed(layer, g)
     return layer.to(DEV)
 
@@ -61,7 +67,7 @@ def test_csr_build_rejects_out_of_range_indices():
 
 
 # ------------------------------------------------------------------------- layer fwd + bwd vs the reference fixtures
-@pytest.mark.parametrize("path", LAYER_FILES, ids=case_id)
+@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES, ids=case_id)
 def test_layer_matches_reference_fixture(path):
     g = load(path)
     layer = _product_layer(g)
@@ -328,3 +334,55 @@ def test_stack_with_fused_activation_matches_cpu_oracle(case):
             assert np.abs(got[k] - want[k]).max() <= 2e-5 * scale, (k, floor)
         else:
             assert nerr(got[k], want[k]) <= tol, (k, nerr(got[k], want[k]), floor)
+
+
+# ------------------------------------------ logit-activation variants (run_act_func_experiment.py:13-74,111) vs the oracle
+@pytest.mark.parametrize("act_name", ["log_sigmoid", "tanh", "leaky_0.05"])
+@pytest.mark.parametrize("geom", [(1500, 20000, 40, 8, 8, True, 0.6), (2000, 30000, 50, 256, 2, True, 0.0),
+                                  (1200, 9000, 64, 7, 1, False, 0.0)], ids=["8x8_drop", "2x256", "1x7_mean"])
+def test_activation_experiment_layer_matches_cpu_oracle(act_name, geom):
+    from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest
+    from oracle.gat_port import PortGraphAttentionLayer
+    make = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh, "leaky_0.05": lambda: torch.nn.LeakyReLU(0.05)}[act_name]
+    n, e, f, c, h, concat, p = geom
+    gen = torch.Generator().manual_seed(n + e)
+    torch.manual_seed(2)
+    ref = PortGraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=p, activation_function=make()).double()
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    x = torch.randn(n, f, generator=gen)
+    gout = torch.randn(n, h * c if concat else c, generator=gen)
+    mask = None
+    if p > 0:
+        mask = (torch.rand(e + n, h, generator=gen) >= p).float() / (1 - p)
+        ref.mask_hook = lambda shape: mask
+    ref.train()
+
+    def run_port(dt):
+        m = ref.to(dt)
+        m.zero_grad()
+        xr = x.detach().clone().to(dt).requires_grad_(True)
+        o = m(xr, ei)
+        o.backward(gout.to(dt))
+        res = packed_grads(m, xr.grad)
+        res["out"] = o.detach().numpy()
+        return res
+    want32, want = run_port(torch.float32), run_port(torch.float64)
+    layer = GraphAttentionLayerActivationTest(f, c, num_heads=h, concat=concat, dropout=p, activation_function=make())
+    layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    layer = layer.to(DEV).train()
+    if mask is not None:
+        layer.mask_hook = lambda shape: mask
+    xg = x.detach().clone().to(DEV).requires_grad_(True)
+    out = layer(xg, ei.to(DEV))
+    out.backward(gout.to(DEV))
+    got = packed_grads(layer, xg.grad)
+    got["out"] = out.detach().cpu().numpy()
+    for k in ("out",) + GRAD_KEYS:
+        floor = nerr(want32[k], want[k])
+        assert nerr(got[k], want[k]) <= max(FP32_TOL, 4.0 * floor), (k, nerr(got[k], want[k]), floor)
+
+
+def test_activation_experiment_rejects_head_softmax():
+    from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest
+    with pytest.raises(NotImplementedError):
+        GraphAttentionLayerActivationTest(8, 8, num_heads=2, activation_function=torch.nn.Softmax())

@@ -6,15 +6,15 @@ import torch
 
 from oracle import closed_form, csr_oracle, ref_loader
 from oracle.gat_port import PortGATNet
-from util import (FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, nerr, packed_grads,
+from util import (ACT_FILES, FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, nerr, packed_grads,
                   port_layer_from_golden)
 
 
 def test_fixture_inventory():
-    assert len(LAYER_FILES) >= 18 and len(NET_FILES) >= 3
+    assert len(LAYER_FILES) >= 18 and len(NET_FILES) >= 3 and len(ACT_FILES) >= 5
 
 
-@pytest.mark.parametrize("path", LAYER_FILES, ids=case_id)
+@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES, ids=case_id)
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_port_matches_reference_fixture(path, prec):
     g = load(path)

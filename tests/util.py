@@ -8,6 +8,8 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LAYER_FILES = sorted(glob.glob(os.path.join(GOLDEN, "layer_*.npz")))
 NET_FILES = sorted(glob.glob(os.path.join(GOLDEN, "net_*.npz")))
+ACT_FILES = sorted(glob.glob(os.path.join(GOLDEN, "actlayer_*.npz")))   # run_act_func_experiment.py layer, other logit activations
+ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh}
 GRAD_KEYS = ("g_x", "g_W", "g_bw", "g_a1", "g_b1", "g_a2", "g_b2", "g_bias")
 FP32_TOL = 1e-5   # north-star: fp32 outputs within 1e-5 relative (max|a-b| <= tol * max|b|)
 
@@ -40,7 +42,9 @@ def port_layer_from_golden(g, dtype=torch.float32):
     """Build oracle.gat_port.PortGraphAttentionLayer holding the fixture's parameters."""
     from oracle.gat_port import PortGraphAttentionLayer
     H, C, F = g["W"].shape
-    layer = PortGraphAttentionLayer(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]))
+    act = ACTIVATIONS[str(g["activation"])]() if "activation" in g else None
+    layer = PortGraphAttentionLayer(F, C, num_heads=H, concat=bool(g["concat"]), dropout=float(g["p"]),
+                                    activation_function=act)
     load_packed(layer, g)
     return layer.to(dtype)
 
