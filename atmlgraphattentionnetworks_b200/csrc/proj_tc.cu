@@ -222,6 +222,28 @@ __device__ __forceinline__ void load_plane(uint32_t dst, const CUtensorMap* map,
   }
 }
 
+// s_src / s_dst of the 128 / CP heads inside one epilogue thread's 128 columns (acc already holds Wh + bw)
+template <int CP>
+__device__ __forceinline__ void logits_heads(const float (&acc)[128], const float* __restrict__ va1,
+                                             const float* __restrict__ va2, const TcGemmParams& p, int64_t row, bool row_ok,
+                                             int64_t col0) {
+#pragma unroll
+  for (int hh = 0; hh < 128 / CP; ++hh) {
+    float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      d1 = fmaf(acc[hh * CP + c], va1[hh * CP + c], d1);
+      d2 = fmaf(acc[hh * CP + c], va2[hh * CP + c], d2);
+    }
+    const int64_t col = col0 + hh * CP;
+    if (row_ok && col < p.N) {
+      const int h = static_cast<int>(col / CP);
+      p.s_src[row * p.H + h] = d1 + __ldg(p.b1 + h);
+      p.s_dst[row * p.H + h] = d2 + __ldg(p.b2 + h);
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(TcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -423,22 +445,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         if (EPI == EPI_LOGITS) {
           float d1 = 0.f, d2 = 0.f;
           if (p.Cp <= 128) {
-            // heads tile this thread's 128 columns: Cp divides 128 (checked on the host), hence is a power of two
-            const int cmask = p.Cp - 1, cshift = 31 - __clz(p.Cp);
-#pragma unroll
-            for (int j = 0; j < 128; ++j) {
-              d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
-              d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
-              if (((j + 1) & cmask) == 0) {
-                const int64_t col = col0 + j;
-                if (row_ok && col < p.N) {
-                  const int h = static_cast<int>(col >> cshift);
-                  p.s_src[row * p.H + h] = d1 + __ldg(p.b1 + h);
-                  p.s_dst[row * p.H + h] = d2 + __ldg(p.b2 + h);
-                }
-                d1 = 0.f;
-                d2 = 0.f;
-              }
+            // heads tile this thread's 128 columns: Cp divides 128 (checked on the host), hence is a power of two.  The head
+            // width is a compile-time constant of each case (one store sequence per head instead of one per column: the
+            // fully unrolled run-time version was 11k SASS instructions and stalled on instruction fetch)
+            const float* va1 = vec + BN + cbase;
+            const float* va2 = vec + 2 * BN + cbase;
+            switch (p.Cp) {
+              case 128: logits_heads<128>(acc, va1, va2, p, row, row_ok, col0); break;
+              case 64: logits_heads<64>(acc, va1, va2, p, row, row_ok, col0); break;
+              case 32: logits_heads<32>(acc, va1, va2, p, row, row_ok, col0); break;
+              case 16: logits_heads<16>(acc, va1, va2, p, row, row_ok, col0); break;
+              case 8: logits_heads<8>(acc, va1, va2, p, row, row_ok, col0); break;
+              default: logits_heads<4>(acc, va1, va2, p, row, row_ok, col0); break;
             }
           } else {
             // Cp == 256 == BN: one head per tile, its two halves live in two warps -> combine through shared memory
@@ -462,19 +480,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         if (row_ok) {
           const bool al_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 128; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-          } else if (al_ok) {      // N tail inside this thread's columns: whole float4 groups, then the ragged rest
+          if (al_ok) {             // 128-bit stores for whole groups of four columns; the (rare) ragged group is scalar
 #pragma unroll
             for (int j = 0; j < 128; j += 4) {
               if (col0 + j + 4 <= p.N) {
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (col0 + j + u < p.N) dst[j + u] = acc[j + u];
+              } else if (col0 + j < p.N) {
+                dst[j] = acc[j];
+                if (col0 + j + 1 < p.N) dst[j + 1] = acc[j + 1];
+                if (col0 + j + 2 < p.N) dst[j + 2] = acc[j + 2];
               }
             }
           } else {

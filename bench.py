@@ -488,7 +488,7 @@ def main():
         return 0
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         val, dt, desc = cpu_reference_leg(args.workload, 3, 1, args.cpu_sample_graphs if args.workload != "large" else 1)
         cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc,
                "s_per_step": dt}
