@@ -554,32 +554,48 @@ __global__ void __launch_bounds__(256) bwd_finish_kernel(const FinishParams p) {
   const int64_t rows_per = ceil_div(p.N, gridDim.y);
   const int64_t r0 = int64_t(blockIdx.y) * rows_per;
   const int64_t r1 = r0 + rows_per < p.N ? r0 + rows_per : p.N;
-#pragma unroll 4
-  for (int64_t r = r0; r < r1; ++r) {
-    const float gs = __ldg(p.g_s_src + r * p.H + h), gd = __ldg(p.g_s_dst + r * p.H + h);
-    const float4 w = ldg4(p.wh + r * p.Dp + c);
-    float4 t = *reinterpret_cast<const float4*>(p.g_t + r * p.Dp + c);
-    t.x += gs * a1c.x + gd * a2c.x;
-    t.y += gs * a1c.y + gd * a2c.y;
-    t.z += gs * a1c.z + gd * a2c.z;
-    t.w += gs * a1c.w + gd * a2c.w;
-    if (PLANES) {
-      __align__(8) __half hv[4];
-      __align__(8) __half lv[4];
-      split_half(t.x * scale, hv[0], lv[0]);
-      split_half(t.y * scale, hv[1], lv[1]);
-      split_half(t.z * scale, hv[2], lv[2]);
-      split_half(t.w * scale, hv[3], lv[3]);
-      *reinterpret_cast<uint2*>(p.hi + r * p.ldp + c) = *reinterpret_cast<const uint2*>(hv);
-      *reinterpret_cast<uint2*>(p.lo + r * p.ldp + c) = *reinterpret_cast<const uint2*>(lv);
-    } else {
-      *reinterpret_cast<float4*>(p.g_t + r * p.Dp + c) = t;
+  // rows in batches of RB: ALL loads of a batch are issued before its first store — the stores (g_t / planes) may alias
+  // the loads as far as the compiler can tell, so a plain unrolled loop kept one row in flight per thread (3.9 TB/s)
+  constexpr int RB = 4;
+  for (int64_t rb = r0; rb < r1; rb += RB) {
+    float gs[RB], gd[RB];
+    float4 w[RB], t[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int64_t r = rb + u < r1 ? rb + u : r1 - 1;      // tail rows re-read the last row and are not stored
+      gs[u] = __ldg(p.g_s_src + r * p.H + h);
+      gd[u] = __ldg(p.g_s_dst + r * p.H + h);
+      w[u] = ldg4(p.wh + r * p.Dp + c);
+      t[u] = *reinterpret_cast<const float4*>(p.g_t + r * p.Dp + c);
     }
-    sbw.x += t.x; sbw.y += t.y; sbw.z += t.z; sbw.w += t.w;
-    sa1.x = fmaf(gs, w.x, sa1.x); sa1.y = fmaf(gs, w.y, sa1.y); sa1.z = fmaf(gs, w.z, sa1.z); sa1.w = fmaf(gs, w.w, sa1.w);
-    sa2.x = fmaf(gd, w.x, sa2.x); sa2.y = fmaf(gd, w.y, sa2.y); sa2.z = fmaf(gd, w.z, sa2.z); sa2.w = fmaf(gd, w.w, sa2.w);
-    sb1 += gs;
-    sb2 += gd;
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int64_t r = rb + u;
+      if (r >= r1) break;
+      t[u].x += gs[u] * a1c.x + gd[u] * a2c.x;
+      t[u].y += gs[u] * a1c.y + gd[u] * a2c.y;
+      t[u].z += gs[u] * a1c.z + gd[u] * a2c.z;
+      t[u].w += gs[u] * a1c.w + gd[u] * a2c.w;
+      if (PLANES) {
+        __align__(8) __half hv[4];
+        __align__(8) __half lv[4];
+        split_half(t[u].x * scale, hv[0], lv[0]);
+        split_half(t[u].y * scale, hv[1], lv[1]);
+        split_half(t[u].z * scale, hv[2], lv[2]);
+        split_half(t[u].w * scale, hv[3], lv[3]);
+        *reinterpret_cast<uint2*>(p.hi + r * p.ldp + c) = *reinterpret_cast<const uint2*>(hv);
+        *reinterpret_cast<uint2*>(p.lo + r * p.ldp + c) = *reinterpret_cast<const uint2*>(lv);
+      } else {
+        *reinterpret_cast<float4*>(p.g_t + r * p.Dp + c) = t[u];
+      }
+      sbw.x += t[u].x; sbw.y += t[u].y; sbw.z += t[u].z; sbw.w += t[u].w;
+      sa1.x = fmaf(gs[u], w[u].x, sa1.x); sa1.y = fmaf(gs[u], w[u].y, sa1.y);
+      sa1.z = fmaf(gs[u], w[u].z, sa1.z); sa1.w = fmaf(gs[u], w[u].w, sa1.w);
+      sa2.x = fmaf(gd[u], w[u].x, sa2.x); sa2.y = fmaf(gd[u], w[u].y, sa2.y);
+      sa2.z = fmaf(gd[u], w[u].z, sa2.z); sa2.w = fmaf(gd[u], w[u].w, sa2.w);
+      sb1 += gs[u];
+      sb2 += gd[u];
+    }
   }
   const float bw4[4] = {sbw.x, sbw.y, sbw.z, sbw.w}, a14[4] = {sa1.x, sa1.y, sa1.z, sa1.w}, a24[4] = {sa2.x, sa2.y, sa2.z, sa2.w};
 #pragma unroll
