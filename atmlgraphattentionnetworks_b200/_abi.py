@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -18,7 +18,12 @@ _i64p = C.POINTER(C.c_int64)
 class Graph(C.Structure):
     _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("eid", C.c_void_p),
-                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p), ("span", C.c_int64)]
+                ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p), ("span", C.c_int64),
+                ("hub_rows", C.c_void_p), ("num_hub_rows", C.c_int64), ("rowend", C.c_void_p),
+                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p)]
+
+
+HUB_DEGREE = 512   # B200GAT_HUB_DEGREE
 
 
 class Layer(C.Structure):
@@ -73,7 +78,8 @@ class EdgeBwdCscArgs(C.Structure):
                 ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p),
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("rowrec", C.c_void_p), ("mask", C.c_void_p),
                 ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
-                ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64)]
+                ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64),
+                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p)]
 
 
 class EdgeBwdFinishArgs(C.Structure):
@@ -103,6 +109,7 @@ _SIGNATURES = {
     "b200gat_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b200gat_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 +
                           [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200gat_hub_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200gat_proj_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_split_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_fwd": (C.c_int, [C.POINTER(ProjFwdArgs), C.c_void_p]),

@@ -70,6 +70,20 @@ __global__ void csr_finish_cols(int64_t EP, int64_t N, const int32_t* __restrict
   }
 }
 
+// rows whose degree exceeds B200GAT_HUB_DEGREE (b200gat_graph.hub_rows / hub_cols)
+__global__ void hub_list_kernel(const int32_t* __restrict__ ptr, int64_t n, int32_t* __restrict__ list, int64_t cap,
+                                int32_t* __restrict__ count, int32_t* __restrict__ ends) {
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t b = ptr[r], e = ptr[r + 1];
+    const bool hub = e - b > B200GAT_HUB_DEGREE;
+    ends[r] = hub ? b : e;
+    if (hub) {
+      const int pos = atomicAdd(count, 1);
+      if (pos < cap) list[pos] = static_cast<int32_t>(r);
+    }
+  }
+}
+
 struct CsrWorkspace {
   size_t off_a, off_iota, off_row, off_pos, off_cub, cub_bytes, total;
 };
@@ -156,4 +170,17 @@ extern "C" int b200gat_csr_build(const int64_t* edge_index, int64_t E, int64_t N
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "csr_build: sort by source: %s", cudaGetErrorString(ce));
   csr_finish_cols<<<blocks, threads, 0, stream>>>(EP, N, buf_a, cpos, row_of, eid, crow, ceid, colptr);
   return check_launch("csr_finish_cols");
+}
+
+extern "C" int b200gat_hub_rows(const int32_t* ptr, int64_t num_rows, int32_t* list, int64_t cap, int32_t* count,
+                                int32_t* ends, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(num_rows >= 0 && cap >= 0, B200GAT_E_SHAPE, "hub_rows: negative size");
+  B200GAT_REQUIRE(count && (num_rows == 0 || (ptr && ends)) && (cap == 0 || list), B200GAT_E_NULL, "hub_rows: NULL pointer");
+  cudaError_t ce = cudaMemsetAsync(count, 0, sizeof(int32_t), stream);
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "hub_rows: memset: %s", cudaGetErrorString(ce));
+  if (num_rows == 0) return 0;
+  const int64_t want = ceil_div(num_rows, 256);
+  hub_list_kernel<<<static_cast<int>(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(ptr, num_rows, list, cap, count, ends);
+  return check_launch("hub_list_kernel");
 }

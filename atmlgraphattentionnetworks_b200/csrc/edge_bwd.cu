@@ -298,6 +298,10 @@ struct EdgeBwdParams {
   const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
   float* gwh;                              // [N, Dp]
   float* g_s_src; float* g_s_dst;          // [N, H]; g_s_dst is zero-initialised and accumulated atomically
+  // scheduling by degree (b200gat_graph.hub_cols): colend[j] = colptr[j + 1] except for hub source rows, which look
+  // EMPTY to the row-per-group kernels (they write zeros) and are then walked — and their outputs overwritten — by
+  // edge_bwd_hub_kernel, one CTA per (source row, head).  No compare, no extra register in the hot kernels.
+  const int32_t* colend; const int32_t* hub; int64_t nhub;
 };
 
 // Sum U per-lane partials over the G lanes of a group and hand the total of edge u to the lane with rel == u.
@@ -359,7 +363,7 @@ __device__ __forceinline__ float reduce_deliver(float (&d)[U], int lane, int rel
   return got;
 }
 
-template <int G, int NV, bool HAS_MASK, bool GENERIC>
+template <int G, int NV, bool HAS_MASK, bool GENERIC, bool HUB>
 __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -372,7 +376,8 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
-  const int64_t Dp = p.Dp, ldg = p.ldg;
+  const int64_t Dp = p.Dp;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
   const float slope = p.slope;
   const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored; their Wh slice is zero
@@ -390,7 +395,9 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
     const int64_t j = valid ? item / H : 0;
     const int h = valid ? static_cast<int>(item - j * H) : 0;
     const int beg = valid ? __ldg(p.colptr + j) : 0;
-    const int end = valid ? __ldg(p.colptr + j + 1) : 0;
+    // HUB: hub rows are empty here (edge_bwd_hub_kernel).  A separate instantiation because even the extra pointer of
+    // the colend read perturbs this kernel's code generation (measured +4 % on the PPI-shaped batch, which has no hubs)
+    const int end = valid ? (HUB ? __ldg(p.colend + j) : __ldg(p.colptr + j + 1)) : 0;
     const int deg = end - beg;
     const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
     const float ss = valid ? __ldg(p.s_src + j * H + h) : 0.f;
@@ -402,7 +409,9 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
       whv[v] = (valid && live[v]) ? ldg4(p.wh + j * Dp + h * Cp + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float gsrc = 0.f;
-    const float* gh = p.g + h * p.hs;
+    const char* gb[NV];                                   // this lane's column slices of row 0 of G[:, h, :]
+#pragma unroll
+    for (int v = 0; v < NV; ++v) gb[v] = reinterpret_cast<const char*>(p.g + h * p.hs + off[v]);
 
     for (int k0 = 0; k0 < maxdeg; k0 += G) {
       const int k = beg + k0 + gl;
@@ -427,19 +436,18 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           it[u] = __shfl_sync(FULL, i, t + u, G);
-          a_t[u] = __shfl_sync(FULL, at, t + u, G);
-          if (t + u >= cnt) a_t[u] = 0.f;
+          a_t[u] = __shfl_sync(FULL, at, t + u, G);       // slots past the chunk's edges carry at = 0 ...
+          if (U > G && t + u >= cnt) a_t[u] = 0.f;        // ... unless the batch is wider than the group (shuffle wraps)
         }
         float4 g4[U][NV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float* src = gh + int64_t(it[u]) * ldg;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6): dz needs no dot product, skip the gather
-              g4[u][v] = a_t[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              g4[u][v] = a_t[u] != 0.f ? ldg4_row(gb[v], it[u], g_row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-              g4[u][v] = ldg4(src + off[v]);
+              g4[u][v] = ldg4_row(gb[v], it[u], g_row_bytes);
             }
           }
         }
@@ -477,11 +485,320 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   }
 }
 
-template <int G, int NV, bool HAS_MASK>
-__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, HAS_MASK, false>(p); }
+template <int G, int NV, bool HAS_MASK, bool HUB>
+__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, HAS_MASK, false, HUB>(p); }
 // other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
 template <int G, int NV>
-__global__ void __launch_bounds__(256) edge_bwd_act_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, true, true>(p); }
+__global__ void __launch_bounds__(256) edge_bwd_act_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, true, true, true>(p); }
+
+// ---- the CSC pass of mean-over-heads layers (GAT.py:65-66; hs == 0): G[i,:] = gout[i,:] / H is the SAME row for every
+// head, so one lane group per SOURCE ROW j walks the column once for all HH heads — G[i] is gathered once per edge
+// instead of once per (edge, head), the col[] -> rowrec -> G dependent chain is paid once per chunk instead of HH
+// times, and the HH row records of a destination are one contiguous 16*HH-byte read.  Each lane keeps its 4-channel
+// slice of Wh[j,h,:] and of the gWh accumulator for every head in registers (Cp <= 128).
+// Transposing reduce: V values per lane summed over the G lanes of the group in V - 1 + log2(G / V) shuffles; afterwards
+// lane gl holds the total of value index gl / (G / V).
+template <int G, int V>
+__device__ __forceinline__ float transpose_reduce(float (&d)[V], int gl) {
+  constexpr unsigned FULL = 0xffffffffu;
+  static_assert(V <= G && (V & (V - 1)) == 0, "V must be a power of two <= G");
+#pragma unroll
+  for (int s = 1; (V >> s) >= 1; ++s) {
+    const int half = V >> s, o = G >> s;
+    const bool up = gl & o;
+#pragma unroll
+    for (int v = 0; v < half; ++v) {
+      const float r = __shfl_xor_sync(FULL, up ? d[v] : d[v + half], o, G);
+      d[v] = (up ? d[v + half] : d[v]) + r;
+    }
+  }
+  float k = d[0];
+#pragma unroll
+  for (int o = G / (2 * V); o > 0; o >>= 1) k += __shfl_xor_sync(FULL, k, o, G);
+  return k;
+}
+
+__host__ __device__ constexpr int pow2ceil_c(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+template <int G, int HH, bool HAS_MASK>
+__global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GPW = 32 / G;
+  constexpr int HP = pow2ceil_c(HH);
+  static_assert(HP <= G, "heads (padded to a power of two) must fit the lane group");
+  constexpr int UMAX = HH > 6 ? 1 : (HH > 4 ? 2 : 4);
+  constexpr int U = (G / HP) < UMAX ? (G / HP) : UMAX;    // edges per gather batch; V = U * HP values per reduce
+  constexpr int V = U * HP;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Cp = p.Cp, Q = p.Cp >> 2;
+  const int64_t Dp = p.Dp;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
+  const float slope = p.slope;
+  const bool live = gl < Q;                               // dead lanes gather a clamped (valid) column; their Wh slice is zero
+  const int off = 4 * (live ? gl : Q - 1);
+  const char* gb = reinterpret_cast<const char*>(p.g + off);
+
+  for (int64_t base = warp * GPW; base < p.N; base += nwarps * GPW) {
+    const int64_t j = base + gi < p.N ? base + gi : p.N - 1;
+    const bool valid = base + gi < p.N;
+    const int beg = valid ? __ldg(p.colptr + j) : 0;
+    const int end = valid ? __ldg(p.colend + j) : 0;            // hub rows are empty here (edge_bwd_hub_kernel)
+    const int deg = end - beg;
+    const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
+    float ss[HH], gsrc[HH];
+    float4 whv[HH], acc[HH];
+#pragma unroll
+    for (int h = 0; h < HH; ++h) {
+      ss[h] = __ldg(p.s_src + j * HH + h);
+      gsrc[h] = 0.f;
+      acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      whv[h] = live ? ldg4(p.wh + j * Dp + h * Cp + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    for (int k0 = 0; k0 < maxdeg; k0 += G) {
+      const int k = beg + k0 + gl;
+      const bool ok = k < end;
+      int i = static_cast<int>(j);
+      float at[HH], ca[HH], cb[HH];                       // alpha * mask;  dz = ca * <G[i], Wh[j,h]> - cb
+#pragma unroll
+      for (int h = 0; h < HH; ++h) at[h] = ca[h] = cb[h] = 0.f;
+      if (ok) {
+        i = __ldg(p.crow + k);
+        const float4* rec = p.rowrec + int64_t(i) * HH;
+        const float* mrow = HAS_MASK ? p.mask + int64_t(__ldg(p.ceid + k)) * HH : nullptr;
+#pragma unroll
+        for (int h = 0; h < HH; ++h) {
+          const float4 rr = __ldg(rec + h);               // {s_dst, rowmax, 1/(rowsum+eps), Drow}
+          const float z = rr.x + ss[h];
+          const float alpha = expf(leaky(z, slope) - rr.y) * rr.z;
+          const float ad = alpha * (z > 0.f ? 1.f : slope);
+          const float mk = HAS_MASK ? __ldg(mrow + h) : 1.f;
+          at[h] = alpha * mk;
+          ca[h] = ad * mk;
+          cb[h] = ad * rr.w;
+        }
+      }
+      float dot[HH];
+#pragma unroll
+      for (int h = 0; h < HH; ++h) dot[h] = 0.f;
+      const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
+      for (int t = 0; t < cnt; t += U) {                  // t + u < G always; lanes past the chunk's edges carry at = 0
+        float4 g4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int it = __shfl_sync(FULL, i, t + u, G);
+          g4[u] = ldg4_row(gb, it, g_row_bytes);
+        }
+        float d[V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int h = 0; h < HP; ++h) {
+            if (h < HH) {
+              const float a = __shfl_sync(FULL, at[h < HH ? h : 0], t + u, G);
+              acc[h < HH ? h : 0].x = fmaf(a, g4[u].x, acc[h < HH ? h : 0].x);
+              acc[h < HH ? h : 0].y = fmaf(a, g4[u].y, acc[h < HH ? h : 0].y);
+              acc[h < HH ? h : 0].z = fmaf(a, g4[u].z, acc[h < HH ? h : 0].z);
+              acc[h < HH ? h : 0].w = fmaf(a, g4[u].w, acc[h < HH ? h : 0].w);
+              const float4 w = whv[h < HH ? h : 0];
+              d[u * HP + h] = fmaf(g4[u].x, w.x, fmaf(g4[u].y, w.y, fmaf(g4[u].z, w.z, g4[u].w * w.w)));
+            } else {
+              d[u * HP + h] = 0.f;
+            }
+          }
+        }
+        const float tot = transpose_reduce<G, V>(d, gl);  // lane gl: total of value (gl / (G / V)) = edge u * HP + head h
+        const int rel = gl - t;
+        const bool mine = rel >= 0 && rel < U;
+        const int src0 = (mine ? rel : 0) * HP * (G / V);
+#pragma unroll
+        for (int h = 0; h < HH; ++h) {
+          const float got = __shfl_sync(FULL, tot, src0 + h * (G / V), G);
+          if (mine) dot[h] = got;
+        }
+      }
+      if (ok) {
+#pragma unroll
+        for (int h = 0; h < HH; ++h) {
+          const float dz = ca[h] * dot[h] - cb[h];
+          gsrc[h] += dz;
+          atomicAdd(p.g_s_dst + int64_t(i) * HH + h, dz);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HH; ++h) gsrc[h] = group_sum<G>(gsrc[h]);
+    if (!valid) continue;
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < HH; ++h) p.g_s_src[j * HH + h] = gsrc[h];
+    }
+    if (live) {
+#pragma unroll
+      for (int h = 0; h < HH; ++h) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off) = acc[h];
+    }
+  }
+}
+
+template <int G, int HH>
+static int launch_edge_bwd_mean(const EdgeBwdParams& p, cudaStream_t stream) {
+  constexpr int GPW = 32 / G;
+  const int threads = 256;
+  const int64_t want = ceil_div(ceil_div(p.N, GPW), threads / 32);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (p.mask) edge_bwd_mean_kernel<G, HH, true><<<blocks, threads, 0, stream>>>(p);
+  else edge_bwd_mean_kernel<G, HH, false><<<blocks, threads, 0, stream>>>(p);
+  return check_launch("edge_bwd_mean_kernel");
+}
+
+template <int HH>
+static int dispatch_edge_bwd_mean(const EdgeBwdParams& p, int Q, cudaStream_t stream) {
+  constexpr int HP = pow2ceil_c(HH);
+  if constexpr (HP <= 4) {
+    if (Q <= 4) return launch_edge_bwd_mean<4, HH>(p, stream);
+  }
+  if (Q <= 8) return launch_edge_bwd_mean<8, HH>(p, stream);
+  if (Q <= 16) return launch_edge_bwd_mean<16, HH>(p, stream);
+  return launch_edge_bwd_mean<32, HH>(p, stream);
+}
+
+// the heads-shared CSC pass covers H in {2, 3, 4, 6, 8}, head width <= 128 channels, LeakyReLU logits
+static bool edge_bwd_mean_supported(int H, int Q, int hs, int act) {
+  return hs == 0 && act == B200GAT_LOGIT_LEAKY_RELU && Q <= 32 && (H == 2 || H == 3 || H == 4 || H == 6 || H == 8);
+}
+
+// ---- hub source rows (out-degree > B200GAT_HUB_DEGREE): one CTA per (source row, head); the 8 warps walk interleaved
+// 32-edge chunks of the column (same arithmetic as edge_bwd_body with a full-warp group) and merge their gWh / g_s_src
+// partial sums through shared memory.  Handles every logit activation and the optional mask at run time.
+template <int NV>
+__global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int U = NV <= 2 ? 4 : 2;
+  __shared__ float sm_g[8];
+  __shared__ float4 sm_acc[8][32 * NV];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
+  const int64_t Dp = p.Dp;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
+  const float slope = p.slope;
+  const int act = p.act;
+  int off[NV];
+  bool live[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    live[v] = lane + v * 32 < Q;
+    off[v] = 4 * (live[v] ? lane + v * 32 : Q - 1);
+  }
+  for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
+    const int64_t j = __ldg(p.hub + item / H);
+    const int h = static_cast<int>(item % H);
+    const int beg = __ldg(p.colptr + j), end = __ldg(p.colptr + j + 1);
+    const float ss = __ldg(p.s_src + j * H + h);
+    float4 whv[NV], acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      whv[v] = live[v] ? ldg4(p.wh + j * Dp + h * Cp + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float gsrc = 0.f;
+    const char* gb[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) gb[v] = reinterpret_cast<const char*>(p.g + h * p.hs + off[v]);
+    for (int k0 = beg + w * 32; k0 < end; k0 += 256) {
+      const int k = k0 + lane;
+      const bool ok = k < end;
+      int i = static_cast<int>(j);
+      float alpha = 0.f, at = 0.f, mk = 1.f, dr = 0.f, dslope = 0.f;
+      if (ok) {
+        i = __ldg(p.crow + k);
+        const float4 rr = __ldg(p.rowrec + int64_t(i) * H + h);   // {s_dst, rowmax, 1/(rowsum+eps), Drow}
+        const float z = rr.x + ss;
+        dslope = logit_act_grad<true>(z, slope, act);
+        alpha = expf(logit_act<true>(z, slope, act) - rr.y) * rr.z;
+        if (p.mask) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
+        at = alpha * mk;
+        dr = rr.w;
+      }
+      float dot_mine = 0.f;
+      const int cnt = (end - k0) < 32 ? (end - k0) : 32;
+      for (int t = 0; t < cnt; t += U) {
+        int it[U];
+        float a_t[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          it[u] = __shfl_sync(FULL, i, t + u);
+          a_t[u] = __shfl_sync(FULL, at, t + u);
+        }
+        float4 g4[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) g4[u][v] = ldg4_row(gb[v], it[u], g_row_bytes);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          d[u] = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(a_t[u], g4[u][v].x, acc[v].x);
+            acc[v].y = fmaf(a_t[u], g4[u][v].y, acc[v].y);
+            acc[v].z = fmaf(a_t[u], g4[u][v].z, acc[v].z);
+            acc[v].w = fmaf(a_t[u], g4[u][v].w, acc[v].w);
+            d[u] = fmaf(g4[u][v].x, whv[v].x, d[u]);
+            d[u] = fmaf(g4[u][v].y, whv[v].y, d[u]);
+            d[u] = fmaf(g4[u][v].z, whv[v].z, d[u]);
+            d[u] = fmaf(g4[u][v].w, whv[v].w, d[u]);
+          }
+        }
+        const int rel = lane - t;
+        const float got = reduce_deliver<32, U>(d, lane, rel);
+        if (rel >= 0 && rel < U) dot_mine = got;
+      }
+      if (ok) {
+        const float dz = alpha * (mk * dot_mine - dr) * dslope;
+        gsrc += dz;
+        atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+      }
+    }
+    gsrc = group_sum<32>(gsrc);
+    if (lane == 0) sm_g[w] = gsrc;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sm_acc[w][lane + 32 * v] = acc[v];
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q < Q) {
+      float4 o = sm_acc[0][q];
+#pragma unroll
+      for (int w2 = 1; w2 < 8; ++w2) {
+        const float4 a = sm_acc[w2][q];
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + 4 * q) = o;
+    }
+    if (threadIdx.x == 0) {
+      float g = sm_g[0];
+#pragma unroll
+      for (int w2 = 1; w2 < 8; ++w2) g += sm_g[w2];
+      p.g_s_src[j * H + h] = g;
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_edge_bwd_hub(const EdgeBwdParams& p, cudaStream_t stream) {
+  if (!p.hub || p.nhub <= 0) return 0;
+  const int64_t want = p.nhub * p.H;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? want : cap);
+  const int Q = p.Cp / 4;
+  if (Q <= 32) edge_bwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
+  else if (Q <= 64) edge_bwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
+  else edge_bwd_hub_kernel<4><<<blocks, 256, 0, stream>>>(p);
+  return check_launch("edge_bwd_hub_kernel");
+}
 
 // ---- gT = gWh + g_s_src (x) a1 + g_s_dst (x) a2, plus every column sum the parameters need.  gT is written in
 // place as fp32, or — when the projection backward runs on the tensor cores — directly as that GEMM's operand split
@@ -620,9 +937,12 @@ static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t 
   // measured on the power-law graph: the batched builds (launch_bounds (256, 2) and (256, 3)) are SLOWER here (48.2 /
   // 48.3 vs 42.6 ms): the per-batch dot-product reduce chain wants warps, not loads in flight
   (void)streaming;
+  const bool hub = p.nhub > 0;
   if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_bwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
-  else if (p.mask) edge_bwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
-  else edge_bwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
+  else if (p.mask && hub) edge_bwd_kernel<G, NV, true, true><<<blocks, threads, 0, stream>>>(p);
+  else if (p.mask) edge_bwd_kernel<G, NV, true, false><<<blocks, threads, 0, stream>>>(p);
+  else if (hub) edge_bwd_kernel<G, NV, false, true><<<blocks, threads, 0, stream>>>(p);
+  else edge_bwd_kernel<G, NV, false, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_kernel");
 }
 
@@ -718,7 +1038,8 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
 // crow holds GLOBAL destination ids indexing rowrec / g / g_s_dst (identical spaces on a single GPU).
 static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, const int32_t* crow, const int32_t* ceid,
                    const float* wh, const float* s_src, const float4* rowrec, const float* mask, const float* gsrc_rows,
-                   int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, cudaStream_t stream) {
+                   int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, const int32_t* colend,
+                   const int32_t* hub, int64_t nhub, cudaStream_t stream) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
   p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
@@ -726,16 +1047,30 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
   p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.mask = mask;
   p.g = gsrc_rows; p.ldg = ldg; p.hs = hs;
   p.gwh = gwh; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
+  B200GAT_REQUIRE(nhub >= 0 && (nhub == 0 || (hub && colend)), B200GAT_E_NULL, "edge_bwd: hub_cols / colend missing");
+  p.hub = hub; p.nhub = nhub; p.colend = nhub > 0 ? colend : colptr + 1;
   const int Q = g.Cp / 4;
   const bool streaming = edge_schedule_streaming(span, ldg * 4);
-  if (Q <= 1) return launch_edge_bwd<1, 1>(p, streaming, stream);
-  if (Q <= 2) return launch_edge_bwd<2, 1>(p, streaming, stream);
-  if (Q <= 4) return launch_edge_bwd<4, 1>(p, streaming, stream);
-  if (Q <= 8) return launch_edge_bwd<8, 1>(p, streaming, stream);
-  if (Q <= 16) return launch_edge_bwd<16, 1>(p, streaming, stream);
-  if (Q <= 32) return launch_edge_bwd<32, 1>(p, streaming, stream);
-  if (Q <= 64) return launch_edge_bwd<32, 2>(p, streaming, stream);
-  return launch_edge_bwd<32, 4>(p, streaming, stream);
+  int rc;
+  if (edge_bwd_mean_supported(g.H, Q, hs, p.act)) {
+    switch (g.H) {
+      case 2: rc = dispatch_edge_bwd_mean<2>(p, Q, stream); break;
+      case 3: rc = dispatch_edge_bwd_mean<3>(p, Q, stream); break;
+      case 4: rc = dispatch_edge_bwd_mean<4>(p, Q, stream); break;
+      case 6: rc = dispatch_edge_bwd_mean<6>(p, Q, stream); break;
+      default: rc = dispatch_edge_bwd_mean<8>(p, Q, stream); break;
+    }
+  }
+  else if (Q <= 1) rc = launch_edge_bwd<1, 1>(p, streaming, stream);
+  else if (Q <= 2) rc = launch_edge_bwd<2, 1>(p, streaming, stream);
+  else if (Q <= 4) rc = launch_edge_bwd<4, 1>(p, streaming, stream);
+  else if (Q <= 8) rc = launch_edge_bwd<8, 1>(p, streaming, stream);
+  else if (Q <= 16) rc = launch_edge_bwd<16, 1>(p, streaming, stream);
+  else if (Q <= 32) rc = launch_edge_bwd<32, 1>(p, streaming, stream);
+  else if (Q <= 64) rc = launch_edge_bwd<32, 2>(p, streaming, stream);
+  else rc = launch_edge_bwd<32, 4>(p, streaming, stream);
+  if (rc) return rc;
+  return launch_edge_bwd_hub(p, stream);
 }
 
 // stage 3: gT (fp32 in place, or as the operand split `gsplit` when given) + parameter column sums over `rows` rows
@@ -852,7 +1187,7 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
   const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
   if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
-                    a->g_t, g_s_src, g_s_dst, a->graph.span, stream)))
+                    a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols, stream)))
     return rc;
   return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
                     gsplit, amax, stream);
@@ -895,7 +1230,7 @@ extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* st
                   a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
   return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
                  reinterpret_cast<const float4*>(a->rowrec), a->mask, a->g, a->ldg, static_cast<int>(a->g_head_stride),
-                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, stream);
+                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, stream);
 }
 
 extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream_) {

@@ -29,6 +29,10 @@ struct EdgeFwdParams {
   int heads_mode;   // 1: write per-head aggregate to o_heads (mean over heads done by head_mean_kernel)
   int vec_out;      // 1: out rows / head offsets are 16-byte aligned -> float4 stores
   uint32_t* out_amax;   // optional: bit pattern of max|out| (atomicMax; zeroed by the host)
+  // scheduling by degree (b200gat_graph.hub_rows): rowend[i] = rowptr[i + 1] except for hub rows, which look EMPTY to
+  // the row-per-group kernels (rowend[i] = rowptr[i]; they write a placeholder) and are then walked — and their outputs
+  // overwritten — by edge_fwd_hub_kernel, one CTA per (row, head).  No compare, no extra register in the hot kernels.
+  const int32_t* rowend; const int32_t* hub; int64_t nhub;
 };
 
 // STREAM: the schedule for graphs whose gathered rows come from HBM (b200gat_graph.span): __launch_bounds__(256, 3)
@@ -44,6 +48,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
   const float slope = p.slope;
   const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored
@@ -58,7 +63,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
     const int64_t i = valid ? item / H : 0;
     const int h = valid ? static_cast<int>(item - i * H) : 0;
     const int beg = valid ? __ldg(p.rowptr + i) : 0;
-    const int end = valid ? __ldg(p.rowptr + i + 1) : 0;
+    const int end = valid ? __ldg(p.rowend + i) : 0;            // hub rows are empty here (edge_fwd_hub_kernel)
     const int deg = end - beg;
     const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
     const float sd = valid ? __ldg(p.s_dst + i * H + h) : 0.f;
@@ -71,7 +76,9 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     float m = -INFINITY, l = 0.f;
-    const float* whh = p.wh + h * Cp;
+    const char* wb[NV];                                   // this lane's column slices of row 0 of head h
+#pragma unroll
+    for (int v = 0; v < NV; ++v) wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + off[v]);
     // For 256-wide heads (NV = 2) the FIRST gather batch of a chunk is issued as soon as col[] is known — before the
     // dependent s_src gather, the exp and the softmax bookkeeping, none of which the Wh gathers need.  Tuned with
     // tools/microbench/gather_bench.cu (PPI-shaped batch, same loop): NV=2: weights-first U=4 0.279 ms, early U=4 0.317,
@@ -91,9 +98,8 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
           for (int u = 0; u < U; ++u) {
             // slots past the chunk's edge count read a valid row (lane t+u's own j, or the destination itself), weight 0
             const int jt = __shfl_sync(FULL, j, t + u, G);
-            const float* src = whh + int64_t(jt) * Dp;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) w[u][v] = ldg4(src + off[v]);
+            for (int v = 0; v < NV; ++v) w[u][v] = ldg4_row(wb[v], jt, row_bytes);
           }
         };
         load_batch(0);
@@ -114,10 +120,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         for (int t = 0; t < cnt; t += U) {
           float pt[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            pt[u] = __shfl_sync(FULL, pp, t + u, G);
-            if (t + u >= cnt) pt[u] = 0.f;
-          }
+          for (int u = 0; u < U; ++u) pt[u] = __shfl_sync(FULL, pp, t + u, G);   // slots past the edges carry pp = 0
           if (t > 0) load_batch(t);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -168,19 +171,18 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   #pragma unroll
           for (int u = 0; u < U; ++u) {
             jt[u] = __shfl_sync(FULL, j, t + u, G);
-            pt[u] = __shfl_sync(FULL, pm, t + u, G);
-            if (t + u >= cnt) pt[u] = 0.f;
+            pt[u] = __shfl_sync(FULL, pm, t + u, G);       // slots past the chunk's edges carry pm = 0 ...
+            if (U > G && t + u >= cnt) pt[u] = 0.f;        // ... unless the batch is wider than the group (shuffle wraps)
           }
           float4 w[U][NV];
   #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const float* src = whh + int64_t(jt[u]) * Dp;
   #pragma unroll
             for (int v = 0; v < NV; ++v) {
               if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6) contribute nothing: skip the gather
-                w[u][v] = pt[u] != 0.f ? ldg4(src + off[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u][v] = pt[u] != 0.f ? ldg4_row(wb[v], jt[u], row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
               } else {          // no predicate, no branch: padded slots gather the row's own (valid) Wh and weigh it by 0
-                w[u][v] = ldg4(src + off[v]);
+                w[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
               }
             }
           }
@@ -280,6 +282,363 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
   return check_launch("edge_fwd_kernel");
 }
 
+// ---- hub rows (in-degree > B200GAT_HUB_DEGREE): one CTA per (row, head).  Its 8 warps walk interleaved 32-edge
+// chunks of the row with the same online softmax as above and merge their (max, sum, aggregate) partials through
+// shared memory.  A 40 k-edge row of the power-law graph costs 1257 dependent chunk walks in the row-per-group
+// kernels (~20 ms on one warp, longer than the rest of the grid needs for the other 2.4 M rows); here it is 157 per warp.
+template <int NV>
+__global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int U = NV >= 4 ? 2 : 4;
+  __shared__ float sm_m[8], sm_l[8];
+  __shared__ float4 sm_acc[8][32 * NV];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
+  const int64_t Dp = p.Dp;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const float slope = p.slope;
+  const int act = p.act;
+  int off[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) off[v] = 4 * ((lane + v * 32 < Q) ? lane + v * 32 : Q - 1);
+  float amax = 0.f;
+  for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
+    const int64_t i = __ldg(p.hub + item / H);
+    const int h = static_cast<int>(item % H);
+    const int beg = __ldg(p.rowptr + i), end = __ldg(p.rowptr + i + 1);
+    const float sd = __ldg(p.s_dst + i * H + h);
+    const float* ssrc_h = p.s_src + h;
+    const char* wb[NV];
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + off[v]);
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = beg + w * 32; k0 < end; k0 += 256) {
+      const int k = k0 + lane;
+      const bool ok = k < end;
+      int j = static_cast<int>(i);
+      float e = -INFINITY;
+      if (ok) {
+        j = __ldg(p.col + k);
+        e = logit_act<true>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
+      }
+      const float m_new = fmaxf(m, group_max<32>(e));
+      if (m_new != m) {                                   // exp(-inf) = 0 covers the first chunk
+        const float scale = expf(m - m_new);
+        l *= scale;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale; }
+      }
+      m = m_new;
+      float pp = 0.f, pm = 0.f;
+      if (ok) {
+        pp = expf(e - m);
+        pm = p.mask ? pp * __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h) : pp;
+      }
+      l += pp;
+      const int cnt = (end - k0) < 32 ? (end - k0) : 32;
+      for (int t = 0; t < cnt; t += U) {                  // lanes past the chunk's edges carry weight 0 and a valid row id
+        int jt[U];
+        float pt[U];
+        float4 wv[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          jt[u] = __shfl_sync(FULL, j, t + u);
+          pt[u] = __shfl_sync(FULL, pm, t + u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) wv[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(pt[u], wv[u][v].x, acc[v].x);
+            acc[v].y = fmaf(pt[u], wv[u][v].y, acc[v].y);
+            acc[v].z = fmaf(pt[u], wv[u][v].z, acc[v].z);
+            acc[v].w = fmaf(pt[u], wv[u][v].w, acc[v].w);
+          }
+        }
+      }
+    }
+    l = group_sum<32>(l);
+    if (lane == 0) { sm_m[w] = m; sm_l[w] = l; }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sm_acc[w][lane + 32 * v] = acc[v];
+    __syncthreads();
+    float M = sm_m[0];
+#pragma unroll
+    for (int w2 = 1; w2 < 8; ++w2) M = fmaxf(M, sm_m[w2]);
+    float L = 0.f, sc[8];
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) {
+      sc[w2] = expf(sm_m[w2] - M);                        // warps that saw no chunk: exp(-inf) = 0
+      L = fmaf(sm_l[w2], sc[w2], L);
+    }
+    const float inv = 1.f / (L + 1e-16f);
+    const int q = threadIdx.x;
+    if (q < Q) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) {
+        const float4 a = sm_acc[w2][q];
+        o.x = fmaf(a.x, sc[w2], o.x); o.y = fmaf(a.y, sc[w2], o.y); o.z = fmaf(a.z, sc[w2], o.z); o.w = fmaf(a.w, sc[w2], o.w);
+      }
+      o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+      if (p.heads_mode) {
+        *reinterpret_cast<float4*>(p.o_heads + i * Dp + h * Cp + 4 * q) = o;
+      } else {
+        const int c = 4 * q;
+        const float* b = p.bias + h * p.C + c;
+        float* dst = p.out + i * p.ldo + h * p.C + c;
+        if (p.vec_out) {
+          const float4 bb = ldg4(b);
+          const float4 r = make_float4(o.x + bb.x, o.y + bb.y, o.z + bb.z, o.w + bb.w);
+          *reinterpret_cast<float4*>(dst) = r;
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
+        } else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c + u < p.C) {
+              const float r = ov[u] + __ldg(b + u);
+              dst[u] = r;
+              amax = fmaxf(amax, fabsf(r));
+            }
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      p.rowmax[i * H + h] = M;
+      p.rowsum[i * H + h] = L;
+    }
+    __syncthreads();
+  }
+  if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
+}
+
+static int launch_edge_fwd_hub(const EdgeFwdParams& p, cudaStream_t stream) {
+  if (!p.hub || p.nhub <= 0) return 0;
+  const int64_t want = p.nhub * p.H;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? want : cap);
+  const int Q = p.Cp / 4;
+  if (Q <= 32) edge_fwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
+  else if (Q <= 64) edge_fwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
+  else edge_fwd_hub_kernel<4><<<blocks, 256, 0, stream>>>(p);
+  return check_launch("edge_fwd_hub_kernel");
+}
+
+// ---- row-wide schedule for NARROW heads (head width < 128 channels, 2..8 heads, at most 512 padded channels per row):
+// one lane group per destination ROW covers all heads — lane slots run over the whole padded Wh row [H, Cp], so a
+// gathered row is one contiguous H*Cp*4-byte read and the col[] -> s_src -> exp -> gather dependent chain is paid once
+// per chunk of G edges instead of once per (chunk, head) with chunks of only Cp/4 edges.  The edge-parallel phase
+// computes the H softmax weights of each edge and parks them (and the edge's source id) in shared memory; in the
+// feature-parallel phase every lane reads the weight of ITS slot's head.  Measured motivation: the per-(row, head)
+// schedule ran the 4 x 47 layer of the 2.4 M-node graph at 2.8 TB/s against 4.8 TB/s for 4 x 128.
+template <int G, int NV, int HH, bool HAS_MASK>
+__device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GPW = 32 / G;
+  constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
+  __shared__ float ps_all[8][32 * HH];
+  __shared__ int js_all[8][32];
+  __shared__ float sc_all[8][GPW * HH];
+  const int wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  float* ps = ps_all[wid] + gi * G * HH;
+  int* js = js_all[wid] + gi * G;
+  float* sc = sc_all[wid] + gi * HH;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = p.Cp >> 2, S = HH * Q;
+  const int64_t Dp = p.Dp;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const float slope = p.slope;
+  int off[NV], hv[NV];
+  bool live[NV];
+  const char* wb[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int s = gl + v * G;
+    live[v] = s < S;
+    const int sl = live[v] ? s : S - 1;                   // dead slots gather a clamped (valid) column and are never stored
+    off[v] = 4 * sl;
+    hv[v] = sl / Q;
+    wb[v] = reinterpret_cast<const char*>(p.wh + off[v]);
+  }
+
+  float amax = 0.f;
+  for (int64_t base = warp * GPW; base < p.N; base += nwarps * GPW) {
+    const bool valid = base + gi < p.N;
+    const int64_t i = valid ? base + gi : p.N - 1;
+    const int beg = valid ? __ldg(p.rowptr + i) : 0;
+    const int end = valid ? __ldg(p.rowend + i) : 0;            // hub rows are empty here (edge_fwd_hub_kernel)
+    const int deg = end - beg;
+    const int maxdeg = GPW == 1 ? deg : __reduce_max_sync(FULL, deg);
+    float sd[HH], m[HH], l[HH];
+#pragma unroll
+    for (int h = 0; h < HH; ++h) {
+      sd[h] = __ldg(p.s_dst + i * HH + h);
+      m[h] = -INFINITY;
+      l[h] = 0.f;
+    }
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int k0 = 0; k0 < maxdeg; k0 += G) {
+      const int k = beg + k0 + gl;
+      const bool ok = k < end;
+      int j = static_cast<int>(i);
+      float e[HH];
+#pragma unroll
+      for (int h = 0; h < HH; ++h) e[h] = -INFINITY;
+      const float* mrow = nullptr;
+      if (ok) {
+        j = __ldg(p.col + k);
+        const float* sj = p.s_src + int64_t(j) * HH;
+#pragma unroll
+        for (int h = 0; h < HH; ++h) e[h] = leaky(sd[h] + __ldg(sj + h), slope);
+        if (HAS_MASK) mrow = p.mask + int64_t(__ldg(p.eid + k)) * HH;
+      }
+      js[gl] = j;
+#pragma unroll
+      for (int h = 0; h < HH; ++h) {
+        const float m_new = fmaxf(m[h], group_max<G>(e[h]));
+        if (k0 > 0) {                                     // group-uniform; exp(-inf - x) = 0 covers "nothing accumulated yet"
+          const float scale = m_new != m[h] ? expf(m[h] - m_new) : 1.f;
+          l[h] *= scale;
+          if (gl == 0) sc[h] = scale;
+        }
+        m[h] = m_new;
+        float pp = 0.f, pm = 0.f;
+        if (ok) {
+          pp = expf(e[h] - m_new);
+          pm = HAS_MASK ? pp * __ldg(mrow + h) : pp;
+        }
+        l[h] += pp;
+        ps[gl * HH + h] = pm;
+      }
+      __syncwarp();
+      if (k0 > 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float scale = sc[hv[v]];
+          acc[v].x *= scale; acc[v].y *= scale; acc[v].z *= scale; acc[v].w *= scale;
+        }
+      }
+      const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
+      // slots t + u past the chunk's edge count (always < G) hold weight 0 and the row's own (valid) id
+      for (int t = 0; t < cnt; t += U) {
+        float pt[U][NV];
+        float4 w[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jt = js[t + u];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            pt[u][v] = ps[(t + u) * HH + hv[v]];
+            if (HAS_MASK) w[u][v] = pt[u][v] != 0.f ? ldg4_row(wb[v], jt, row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else w[u][v] = ldg4_row(wb[v], jt, row_bytes);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(pt[u][v], w[u][v].x, acc[v].x);
+            acc[v].y = fmaf(pt[u][v], w[u][v].y, acc[v].y);
+            acc[v].z = fmaf(pt[u][v], w[u][v].z, acc[v].z);
+            acc[v].w = fmaf(pt[u][v], w[u][v].w, acc[v].w);
+          }
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < HH; ++h) {
+      l[h] = group_sum<G>(l[h]);
+      if (gl == 0) {
+        sc[h] = 1.f / (l[h] + 1e-16f);
+        if (valid) {
+          p.rowmax[i * HH + h] = m[h];
+          p.rowsum[i * HH + h] = l[h];
+        }
+      }
+    }
+    __syncwarp();
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!live[v]) continue;
+        const float inv = sc[hv[v]];
+        const float4 o = make_float4(acc[v].x * inv, acc[v].y * inv, acc[v].z * inv, acc[v].w * inv);
+        if (p.heads_mode) {
+          *reinterpret_cast<float4*>(p.o_heads + i * Dp + off[v]) = o;
+        } else {
+          const int c = off[v] - hv[v] * p.Cp;
+          const float* b = p.bias + hv[v] * p.C + c;
+          float* dst = p.out + i * p.ldo + hv[v] * p.C + c;
+          if (p.vec_out) {
+            const float4 bb = ldg4(b);
+            const float4 r = make_float4(o.x + bb.x, o.y + bb.y, o.z + bb.z, o.w + bb.w);
+            *reinterpret_cast<float4*>(dst) = r;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c + u < p.C) {
+                const float r = ov[u] + __ldg(b + u);
+                dst[u] = r;
+                amax = fmaxf(amax, fabsf(r));
+              }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
+}
+
+template <int G, int NV, int HH, bool HAS_MASK>
+__global__ void __launch_bounds__(256) edge_fwd_row_kernel(const EdgeFwdParams p) { edge_fwd_row_body<G, NV, HH, HAS_MASK>(p); }
+template <int G, int NV, int HH>
+__global__ void __launch_bounds__(256, 3) edge_fwd_row_stream_kernel(const EdgeFwdParams p) { edge_fwd_row_body<G, NV, HH, false>(p); }
+
+template <int G, int NV, int HH>
+static int launch_edge_fwd_row(const EdgeFwdParams& p, bool streaming, cudaStream_t stream) {
+  constexpr int GPW = 32 / G;
+  const int threads = 256;
+  const int64_t want = ceil_div(ceil_div(p.N, GPW), threads / 32);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (p.mask) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
+  else if (streaming) edge_fwd_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
+  else edge_fwd_row_kernel<G, NV, HH, false><<<blocks, threads, 0, stream>>>(p);
+  return check_launch("edge_fwd_row_kernel");
+}
+
+template <int HH>
+static int dispatch_edge_fwd_row(const EdgeFwdParams& p, int S, bool streaming, cudaStream_t stream) {
+  if (S <= 16) return launch_edge_fwd_row<16, 1, HH>(p, streaming, stream);
+  if (S <= 32) return launch_edge_fwd_row<32, 1, HH>(p, streaming, stream);
+  if (S <= 64) return launch_edge_fwd_row<32, 2, HH>(p, streaming, stream);
+  return launch_edge_fwd_row<32, 4, HH>(p, streaming, stream);
+}
+
+// narrow heads: 2..8 heads (compile-time instantiations), head width < 128 channels, row <= 512 padded channels
+static bool edge_fwd_row_supported(int H, int Q, int act) {
+  return act == B200GAT_LOGIT_LEAKY_RELU && Q < 32 && H * Q <= 128 && (H == 2 || H == 3 || H == 4 || H == 6 || H == 8);
+}
+
 }  // namespace b200gat
 
 using namespace b200gat;
@@ -315,6 +674,11 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   p.heads_mode = heads_mode ? 1 : 0;
   p.vec_out = (!heads_mode && C % 4 == 0 && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
   p.out_amax = a->out_amax;
+  B200GAT_REQUIRE(a->graph.num_hub_rows >= 0 && (a->graph.num_hub_rows == 0 || a->graph.hub_rows), B200GAT_E_NULL,
+                  "edge_fwd: graph.hub_rows missing");
+  B200GAT_REQUIRE(a->graph.num_hub_rows == 0 || a->graph.rowend, B200GAT_E_NULL, "edge_fwd: graph.rowend missing");
+  p.hub = a->graph.hub_rows; p.nhub = a->graph.num_hub_rows;
+  p.rowend = p.nhub > 0 ? a->graph.rowend : a->graph.rowptr + 1;
   if (a->out_amax) {
     cudaError_t ce = cudaMemsetAsync(a->out_amax, 0, sizeof(uint32_t), stream);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_fwd: memset: %s", cudaGetErrorString(ce));
@@ -322,7 +686,15 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
 
   const int Q = Cp / 4;
   const bool streaming = edge_schedule_streaming(a->graph.span, int64_t(H) * Cp * 4);
-  if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, streaming, stream);
+  if (edge_fwd_row_supported(H, Q, p.act)) {
+    switch (H) {
+      case 2: rc = dispatch_edge_fwd_row<2>(p, H * Q, streaming, stream); break;
+      case 3: rc = dispatch_edge_fwd_row<3>(p, H * Q, streaming, stream); break;
+      case 4: rc = dispatch_edge_fwd_row<4>(p, H * Q, streaming, stream); break;
+      case 6: rc = dispatch_edge_fwd_row<6>(p, H * Q, streaming, stream); break;
+      default: rc = dispatch_edge_fwd_row<8>(p, H * Q, streaming, stream); break;
+    }
+  } else if (Q <= 1) rc = launch_edge_fwd<1, 1>(p, streaming, stream);
   else if (Q <= 2) rc = launch_edge_fwd<2, 1>(p, streaming, stream);
   else if (Q <= 4) rc = launch_edge_fwd<4, 1>(p, streaming, stream);
   else if (Q <= 8) rc = launch_edge_fwd<8, 1>(p, streaming, stream);
@@ -331,6 +703,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   else if (Q <= 64) rc = launch_edge_fwd<32, 2>(p, streaming, stream);
   else rc = launch_edge_fwd<32, 4>(p, streaming, stream);
   if (rc) return rc;
+  if ((rc = launch_edge_fwd_hub(p, stream))) return rc;
   if (heads_mode) {
     const int64_t total = N * C;
     const int64_t want = ceil_div(total, 256);

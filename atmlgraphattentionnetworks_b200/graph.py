@@ -15,7 +15,7 @@ class GraphCSR:
     """int32 device arrays of [edge_index ; self loops] (see include/b200gat.h: b200gat_graph)."""
 
     __slots__ = ("num_nodes", "num_input_edges", "num_edges", "rowptr", "col", "eid", "colptr", "crow", "ceid",
-                 "device", "span", "_struct", "__weakref__")
+                 "device", "span", "hub_rows", "hub_cols", "rowend", "colend", "_struct", "__weakref__")
 
     def c_struct(self):
         return self._struct
@@ -48,7 +48,10 @@ def build_csr(edge_index, num_nodes, validate=True):
         g.eid = torch.empty(ep, **i32)
         g.crow = torch.empty(ep, **i32)
         g.ceid = torch.empty(ep, **i32)
-        status = torch.empty(2, **i32)
+        status = torch.zeros(4, **i32)          # {bad indices, span, rows / columns with degree > HUB_DEGREE}
+        hub_cap = ep // _abi.HUB_DEGREE + 1
+        hubs = torch.empty((2, hub_cap), **i32)
+        ends = torch.empty((2, max(n, 1)), **i32)
         ws_bytes = int(lib.b200gat_csr_workspace_bytes(n, e))
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -58,13 +61,27 @@ def build_csr(edge_index, num_nodes, validate=True):
         _abi.check(rc, "b200gat_csr_build")
         _abi.launches += 5 if ep else 0
         g.span = -1
+        g.hub_rows = g.hub_cols = g.rowend = g.colend = None
+        n_hub = [0, 0]
         if validate:
-            bad, span = (int(v) for v in status.tolist())      # one D2H read: index check + the locality statistic
+            # scheduling by degree (b200gat_graph.hub_rows): list the rows / columns longer than HUB_DEGREE
+            for which, ptr in enumerate((g.rowptr, g.colptr)):
+                rc = lib.b200gat_hub_rows(ptr.data_ptr(), n, hubs[which].data_ptr(), hub_cap,
+                                          status[2 + which:].data_ptr(), ends[which].data_ptr(), stream)
+                _abi.check(rc, "b200gat_hub_rows")
+            # one D2H read: index check, the locality statistic, the hub counts
+            bad, span, n_hub[0], n_hub[1] = (int(v) for v in status.tolist())
             if bad:
                 raise IndexError(f"edge_index has {bad} entries outside [0, {n})")
             g.span = span
+            g.hub_rows, g.hub_cols = hubs[0, :n_hub[0]], hubs[1, :n_hub[1]]
+            g.rowend, g.colend = (ends[0] if n_hub[0] else None), (ends[1] if n_hub[1] else None)
     g._struct = _abi.Graph(n, ep, g.rowptr.data_ptr(), g.col.data_ptr(), g.eid.data_ptr(), g.colptr.data_ptr(),
-                           g.crow.data_ptr(), g.ceid.data_ptr(), g.span)
+                           g.crow.data_ptr(), g.ceid.data_ptr(), g.span,
+                           g.hub_rows.data_ptr() if n_hub[0] else None, n_hub[0],
+                           g.rowend.data_ptr() if n_hub[0] else None,
+                           g.hub_cols.data_ptr() if n_hub[1] else None, n_hub[1],
+                           g.colend.data_ptr() if n_hub[1] else None)
     return g
 
 

@@ -26,7 +26,7 @@ from .gat import _call, _layer_struct, _ptr, _workspace
 # ------------------------------------------------------------------------------------------------ graph partition
 class RowPartition:
     __slots__ = ("num_nodes", "world", "rank", "block", "lo", "hi", "rowptr", "col", "eid", "colptr", "crow", "ceid",
-                 "_struct")
+                 "hub_rows", "hub_cols", "rowend", "colend", "_struct")
 
     @property
     def n_own(self):
@@ -77,9 +77,17 @@ def build_row_partition(edge_index, num_nodes, world, rank):
     p.num_nodes, p.world, p.rank, p.block, p.lo, p.hi = n, world, rank, b, lo, hi
     p.rowptr, p.col, p.eid, p.colptr, p.crow, p.ceid = rowptr, col, eid, colptr, crow, ceid
     p._struct = None
+    # scheduling by degree (include/b200gat.h: b200gat_graph.hub_rows): own rows / columns longer than HUB_DEGREE
+    def hubs(ptr):
+        is_hub = (ptr[1:] - ptr[:-1]) > _abi.HUB_DEGREE
+        return torch.nonzero(is_hub).flatten().to(torch.int32), torch.where(is_hub, ptr[:-1], ptr[1:]).contiguous()
+    (p.hub_rows, p.rowend), (p.hub_cols, p.colend) = hubs(rowptr), hubs(colptr)
     if rowptr.is_cuda:
+        nr, nc = int(p.hub_rows.numel()), int(p.hub_cols.numel())
         p._struct = _abi.Graph(hi - lo, int(col.numel()), rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
-                               colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr(), n)   # span: one big graph
+                               colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr(), n,   # span: one big graph
+                               p.hub_rows.data_ptr() if nr else None, nr, p.rowend.data_ptr() if nr else None,
+                               p.hub_cols.data_ptr() if nc else None, nc, p.colend.data_ptr() if nc else None)
     return p
 
 
@@ -183,7 +191,8 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
     ca = _abi.EdgeBwdCscArgs(layer, n, part.colptr.data_ptr(), part.crow.data_ptr(), part.ceid.data_ptr(),
                              wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
                              g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
-                             part.num_nodes)
+                             part.num_nodes, part.hub_cols.data_ptr() if part.hub_cols.numel() else None,
+                             int(part.hub_cols.numel()), part.colend.data_ptr() if part.hub_cols.numel() else None)
     _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
     return g_wh, g_s_src, g_s_dst_full
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 8
+#define B200GAT_ABI_VERSION 9
 
 enum {
   B200GAT_OK = 0,
@@ -63,7 +63,20 @@ typedef struct {
                               unknown.  The edge kernels use it to pick their schedule: a small span (block-diagonal
                               graph batches) keeps the gathered rows L2-resident and favours occupancy; a large one
                               (one big graph) streams them from HBM and favours more gathers in flight per warp */
+  /* Scheduling by degree.  The edge kernels walk a row with ONE lane group; a power-law hub (the 2.4 M-node graph has
+   * rows of 40 k edges) would keep a single warp busy long after the rest of the grid has drained.  Rows whose degree
+   * exceeds B200GAT_HUB_DEGREE are therefore listed here (b200gat_hub_rows) and processed by a second launch with one
+   * whole CTA per (row, head); the row-per-group kernels read a row's end from rowend / colend, where those rows are
+   * empty.  num_hub_* == 0 (then the four pointers may be NULL): no row is treated specially. */
+  const int32_t* hub_rows; /* [num_hub_rows] destination rows with in-degree  > B200GAT_HUB_DEGREE (any order) */
+  int64_t num_hub_rows;
+  const int32_t* rowend;   /* [N] rowptr[i + 1], but rowptr[i] for the rows listed in hub_rows */
+  const int32_t* hub_cols; /* [num_hub_cols] source rows      with out-degree > B200GAT_HUB_DEGREE (any order) */
+  int64_t num_hub_cols;
+  const int32_t* colend;   /* [N] colptr[j + 1], but colptr[j] for the rows listed in hub_cols */
 } b200gat_graph;
+
+#define B200GAT_HUB_DEGREE 512
 
 /* Layer geometry, GAT.py:8 (input_channels, output_channels, num_heads, concat). */
 typedef struct {
@@ -96,6 +109,13 @@ int b200gat_csr_build(const int64_t* edge_index, int64_t num_input_edges, int64_
                       int32_t* rowptr, int32_t* col, int32_t* eid,
                       int32_t* colptr, int32_t* crow, int32_t* ceid,
                       int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Lists the rows of a CSR / CSC pointer array whose degree exceeds B200GAT_HUB_DEGREE: list[0 .. *count) (device, any
+ * order, at most `cap` entries written; cap >= ptr[num_rows] / B200GAT_HUB_DEGREE + 1 always suffices), *count (device
+ * int32) = their number, ends[r] (device [num_rows]) = ptr[r + 1], or ptr[r] for a listed row.  The caller reads
+ * *count back and passes it as num_hub_rows / num_hub_cols. */
+int b200gat_hub_rows(const int32_t* ptr, int64_t num_rows, int32_t* list, int64_t cap, int32_t* count, int32_t* ends,
+                     void* stream);
 
 /* ---- K1: projection + attention logits (GAT.py:42-52) ----------------------------------------------------- */
 typedef struct {
@@ -197,6 +217,8 @@ typedef struct {
   float* g_s_src;                     /* out [rows, H] */
   float* g_s_dst;                     /* in/out ALL nodes [N, H]: zero-initialised by the caller, accumulated atomically */
   int64_t span;                       /* as b200gat_graph.span for the gathered rows `g` (< 0: unknown) */
+  const int32_t* hub_cols; int64_t num_hub_cols;   /* own source rows with out-degree > B200GAT_HUB_DEGREE (or NULL / 0) */
+  const int32_t* colend;              /* [rows] as b200gat_graph.colend (required when num_hub_cols > 0) */
 } b200gat_edge_bwd_csc_args;
 int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
 

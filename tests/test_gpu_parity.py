@@ -55,6 +55,16 @@ def test_csr_build_bit_exact(name, ei, n):
         got = t.cpu().numpy().astype(np.int64)
         assert got.shape == want[k].shape, k
         assert np.array_equal(got, want[k]), k
+    # scheduling by degree: rows / columns longer than HUB_DEGREE are listed, and look empty through rowend / colend
+    from atmlgraphattentionnetworks_b200._abi import HUB_DEGREE
+    for ptr_k, hub, ends in (("rowptr", g.hub_rows, g.rowend), ("colptr", g.hub_cols, g.colend)):
+        ptr = want[ptr_k]
+        is_hub = np.diff(ptr) > HUB_DEGREE
+        assert np.array_equal(np.sort(hub.cpu().numpy()), np.nonzero(is_hub)[0]), ptr_k
+        if is_hub.any():
+            assert np.array_equal(ends.cpu().numpy(), np.where(is_hub, ptr[:-1], ptr[1:])), ptr_k
+        else:
+            assert ends is None
 
 
 def test_csr_build_rejects_out_of_range_indices():
@@ -138,6 +148,13 @@ ORACLE_CASES = [
     ("c128_hub", 4000, 80000, 100, 128, 4, True, 0.0, True),
     ("wide_c512", 500, 6000, 32, 512, 1, True, 0.0, False),
     ("c20_cat_unaligned_out", 900, 9000, 17, 5, 3, True, 0.0, False),
+    # narrow heads: row-wide edge_fwd schedule (all heads per lane group) / heads-shared CSC pass of mean layers
+    ("heads8x64_hub", 2500, 40000, 50, 64, 8, True, 0.0, True),
+    ("heads2x64_drop_hub", 2000, 30000, 50, 64, 2, True, 0.6, True),
+    ("mean_h8c12_drop_hub", 1500, 30000, 20, 12, 8, False, 0.6, True),
+    ("mean_h3c33_hub", 1200, 24000, 16, 33, 3, False, 0.0, True),
+    ("mean_h6c100_hub", 1500, 30000, 40, 100, 6, False, 0.0, True),
+    ("mean_h2c128", 1000, 12000, 32, 128, 2, False, 0.0, False),
 ]
 
 
