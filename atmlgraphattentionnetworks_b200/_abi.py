@@ -20,7 +20,8 @@ class Graph(C.Structure):
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("eid", C.c_void_p),
                 ("colptr", C.c_void_p), ("crow", C.c_void_p), ("ceid", C.c_void_p), ("span", C.c_int64),
                 ("hub_rows", C.c_void_p), ("num_hub_rows", C.c_int64), ("rowend", C.c_void_p),
-                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p)]
+                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p),
+                ("max_in_degree", C.c_int64), ("max_out_degree", C.c_int64)]
 
 
 HUB_DEGREE = 512   # B200GAT_HUB_DEGREE
@@ -79,7 +80,8 @@ class EdgeBwdCscArgs(C.Structure):
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("rowrec", C.c_void_p), ("mask", C.c_void_p),
                 ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
                 ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64),
-                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p)]
+                ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p),
+                ("max_out_degree", C.c_int64)]
 
 
 class EdgeBwdFinishArgs(C.Structure):

@@ -73,15 +73,19 @@ __global__ void csr_finish_cols(int64_t EP, int64_t N, const int32_t* __restrict
 // rows whose degree exceeds B200GAT_HUB_DEGREE (b200gat_graph.hub_rows / hub_cols)
 __global__ void hub_list_kernel(const int32_t* __restrict__ ptr, int64_t n, int32_t* __restrict__ list, int64_t cap,
                                 int32_t* __restrict__ count, int32_t* __restrict__ ends) {
+  int maxdeg = 0;
   for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n; r += int64_t(gridDim.x) * blockDim.x) {
     const int32_t b = ptr[r], e = ptr[r + 1];
     const bool hub = e - b > B200GAT_HUB_DEGREE;
     ends[r] = hub ? b : e;
+    maxdeg = e - b > maxdeg ? e - b : maxdeg;
     if (hub) {
       const int pos = atomicAdd(count, 1);
       if (pos < cap) list[pos] = static_cast<int32_t>(r);
     }
   }
+  maxdeg = __reduce_max_sync(0xffffffffu, maxdeg);
+  if ((threadIdx.x & 31) == 0) atomicMax(count + 1, maxdeg);
 }
 
 struct CsrWorkspace {
@@ -177,7 +181,7 @@ extern "C" int b200gat_hub_rows(const int32_t* ptr, int64_t num_rows, int32_t* l
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200GAT_REQUIRE(num_rows >= 0 && cap >= 0, B200GAT_E_SHAPE, "hub_rows: negative size");
   B200GAT_REQUIRE(count && (num_rows == 0 || (ptr && ends)) && (cap == 0 || list), B200GAT_E_NULL, "hub_rows: NULL pointer");
-  cudaError_t ce = cudaMemsetAsync(count, 0, sizeof(int32_t), stream);
+  cudaError_t ce = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "hub_rows: memset: %s", cudaGetErrorString(ce));
   if (num_rows == 0) return 0;
   const int64_t want = ceil_div(num_rows, 256);

@@ -302,6 +302,7 @@ struct EdgeBwdParams {
   // EMPTY to the row-per-group kernels (they write zeros) and are then walked — and their outputs overwritten — by
   // edge_bwd_hub_kernel, one CTA per (source row, head).  No compare, no extra register in the hot kernels.
   const int32_t* colend; const int32_t* hub; int64_t nhub;
+  int max_deg;          // largest out-degree: source rows above B200GAT_GIANT_DEGREE are split into segments (grid.y)
 };
 
 // Sum U per-lane partials over the G lanes of a group and hand the total of edge u to the lane with rel == u.
@@ -676,7 +677,7 @@ static bool edge_bwd_mean_supported(int H, int Q, int hs, int act) {
 template <int NV>
 __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int U = NV <= 2 ? 4 : 2;
+  constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
   __shared__ float sm_g[8];
   __shared__ float4 sm_acc[8][32 * NV];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -695,7 +696,14 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
   for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
     const int64_t j = __ldg(p.hub + item / H);
     const int h = static_cast<int>(item % H);
-    const int beg = __ldg(p.colptr + j), end = __ldg(p.colptr + j + 1);
+    // giant source rows (out-degree > B200GAT_GIANT_DEGREE) are cut into segments, one CTA each (grid.y = segment); their
+    // partial sums are ADDED to the zeros the row-per-group kernel left in gwh / g_s_src.  CTA-uniform control flow.
+    const int beg0 = __ldg(p.colptr + j), end0 = __ldg(p.colptr + j + 1);
+    const bool giant = end0 - beg0 > B200GAT_GIANT_DEGREE;
+    if (!giant && blockIdx.y > 0) continue;
+    const int beg = giant ? beg0 + static_cast<int>(blockIdx.y) * B200GAT_GIANT_DEGREE : beg0;
+    const int end = giant && beg + B200GAT_GIANT_DEGREE < end0 ? beg + B200GAT_GIANT_DEGREE : end0;
+    if (beg >= end) continue;
     const float ss = __ldg(p.s_src + j * H + h);
     float4 whv[NV], acc[NV];
 #pragma unroll
@@ -776,13 +784,16 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
         const float4 a = sm_acc[w2][q];
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
       }
-      *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + 4 * q) = o;
+      float* dst = p.gwh + j * Dp + h * Cp + 4 * q;
+      if (giant) { atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w); }
+      else *reinterpret_cast<float4*>(dst) = o;
     }
     if (threadIdx.x == 0) {
       float g = sm_g[0];
 #pragma unroll
       for (int w2 = 1; w2 < 8; ++w2) g += sm_g[w2];
-      p.g_s_src[j * H + h] = g;
+      if (giant) atomicAdd(p.g_s_src + j * H + h, g);
+      else p.g_s_src[j * H + h] = g;
     }
     __syncthreads();
   }
@@ -792,7 +803,9 @@ static int launch_edge_bwd_hub(const EdgeBwdParams& p, cudaStream_t stream) {
   if (!p.hub || p.nhub <= 0) return 0;
   const int64_t want = p.nhub * p.H;
   const int64_t cap = int64_t(sm_count()) * 8;
-  const int blocks = static_cast<int>(want < cap ? want : cap);
+  const int64_t nseg = p.max_deg > B200GAT_GIANT_DEGREE ? ceil_div(p.max_deg, B200GAT_GIANT_DEGREE) : 1;
+  B200GAT_REQUIRE(nseg <= 65535, B200GAT_E_UNSUPPORTED, "edge_bwd: a source row of %d edges is not supported", p.max_deg);
+  const dim3 blocks(static_cast<unsigned>(want < cap ? want : cap), static_cast<unsigned>(nseg));
   const int Q = p.Cp / 4;
   if (Q <= 32) edge_bwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
   else if (Q <= 64) edge_bwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
@@ -1039,7 +1052,7 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
 static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, const int32_t* crow, const int32_t* ceid,
                    const float* wh, const float* s_src, const float4* rowrec, const float* mask, const float* gsrc_rows,
                    int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, const int32_t* colend,
-                   const int32_t* hub, int64_t nhub, cudaStream_t stream) {
+                   const int32_t* hub, int64_t nhub, int64_t max_deg, cudaStream_t stream) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
   p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
@@ -1049,6 +1062,7 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
   p.gwh = gwh; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
   B200GAT_REQUIRE(nhub >= 0 && (nhub == 0 || (hub && colend)), B200GAT_E_NULL, "edge_bwd: hub_cols / colend missing");
   p.hub = hub; p.nhub = nhub; p.colend = nhub > 0 ? colend : colptr + 1;
+  p.max_deg = static_cast<int>(max_deg);
   const int Q = g.Cp / 4;
   const bool streaming = edge_schedule_streaming(span, ldg * 4);
   int rc;
@@ -1187,7 +1201,8 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
   const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
   if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
-                    a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols, stream)))
+                    a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols,
+                    a->graph.max_out_degree, stream)))
     return rc;
   return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
                     gsplit, amax, stream);
@@ -1230,7 +1245,7 @@ extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* st
                   a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
   return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
                  reinterpret_cast<const float4*>(a->rowrec), a->mask, a->g, a->ldg, static_cast<int>(a->g_head_stride),
-                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, stream);
+                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, stream);
 }
 
 extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream_) {

@@ -33,6 +33,7 @@ struct EdgeFwdParams {
   // the row-per-group kernels (rowend[i] = rowptr[i]; they write a placeholder) and are then walked — and their outputs
   // overwritten — by edge_fwd_hub_kernel, one CTA per (row, head).  No compare, no extra register in the hot kernels.
   const int32_t* rowend; const int32_t* hub; int64_t nhub;
+  int max_deg;          // largest in-degree (>= any hub row's): rows above B200GAT_GIANT_DEGREE are split into segments
 };
 
 // STREAM: the schedule for graphs whose gathered rows come from HBM (b200gat_graph.span): __launch_bounds__(256, 3)
@@ -289,7 +290,7 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
 template <int NV>
 __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int U = NV >= 4 ? 2 : 4;
+  constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
   __shared__ float sm_m[8], sm_l[8];
   __shared__ float4 sm_acc[8][32 * NV];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
     const int64_t i = __ldg(p.hub + item / H);
     const int h = static_cast<int>(item % H);
     const int beg = __ldg(p.rowptr + i), end = __ldg(p.rowptr + i + 1);
+    if (end - beg > B200GAT_GIANT_DEGREE) continue;       // CTA-uniform: split into segments by the giant kernels below
     const float sd = __ldg(p.s_dst + i * H + h);
     const float* ssrc_h = p.s_src + h;
     const char* wb[NV];
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
   if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
 }
 
+static int launch_edge_fwd_giant(const EdgeFwdParams& p, cudaStream_t stream);
 static int launch_edge_fwd_hub(const EdgeFwdParams& p, cudaStream_t stream) {
   if (!p.hub || p.nhub <= 0) return 0;
   const int64_t want = p.nhub * p.H;
@@ -431,7 +434,180 @@ static int launch_edge_fwd_hub(const EdgeFwdParams& p, cudaStream_t stream) {
   if (Q <= 32) edge_fwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
   else if (Q <= 64) edge_fwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
   else edge_fwd_hub_kernel<4><<<blocks, 256, 0, stream>>>(p);
-  return check_launch("edge_fwd_hub_kernel");
+  const int rc = check_launch("edge_fwd_hub_kernel");
+  return rc ? rc : launch_edge_fwd_giant(p, stream);
+}
+
+// ---- giant rows (in-degree > B200GAT_GIANT_DEGREE): even one CTA per (row, head) would leave a 40 k-edge row as the
+// tail of the launch, so these rows are cut into segments of B200GAT_GIANT_DEGREE edges, one CTA per (row, head, segment)
+// (grid.y = segment; CTAs without work exit after three loads), in three steps: (1) row max of the logits by atomicMax,
+// (2) exp / row sum / weighted aggregate per segment, added atomically into rowsum and the output row, (3) normalise
+// + bias.  The only rows whose summation order is not fixed.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// -> true when this CTA has a segment [kbeg, kend) of giant row i, head h
+__device__ __forceinline__ bool giant_unit(const int32_t* hub, const int32_t* ptr, int H, int64_t& i, int& h, int& kbeg, int& kend) {
+  i = __ldg(hub + blockIdx.x / H);
+  h = static_cast<int>(blockIdx.x % H);
+  const int beg = __ldg(ptr + i), end = __ldg(ptr + i + 1);
+  kbeg = beg + static_cast<int>(blockIdx.y) * B200GAT_GIANT_DEGREE;
+  kend = kbeg + B200GAT_GIANT_DEGREE < end ? kbeg + B200GAT_GIANT_DEGREE : end;
+  return end - beg > B200GAT_GIANT_DEGREE && kbeg < end;
+}
+
+__global__ void __launch_bounds__(256) edge_fwd_giant_max_kernel(const EdgeFwdParams p) {
+  __shared__ float sm_m[8];
+  int64_t i; int h, kbeg, kend;
+  if (!giant_unit(p.hub, p.rowptr, p.H, i, h, kbeg, kend)) return;
+  const int H = p.H, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float sd = __ldg(p.s_dst + i * H + h);
+  float m = -INFINITY;
+  for (int k = kbeg + threadIdx.x; k < kend; k += 256)
+    m = fmaxf(m, logit_act<true>(sd + __ldg(p.s_src + int64_t(__ldg(p.col + k)) * H + h), p.slope, p.act));
+  m = group_max<32>(m);
+  if (lane == 0) sm_m[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, sm_m[w2]);
+    atomic_max_float(p.rowmax + i * H + h, m);            // placeholder written by the row-per-group kernel: -inf
+  }
+  if (blockIdx.y == 0) {                                  // segment 0 clears the accumulation targets of step (2)
+    if (threadIdx.x == 0) p.rowsum[i * H + h] = 0.f;
+    if (p.heads_mode) {
+      for (int c = threadIdx.x; c < p.Cp; c += 256) p.o_heads[i * p.Dp + h * p.Cp + c] = 0.f;
+    } else {
+      for (int c = threadIdx.x; c < p.C; c += 256) p.out[i * p.ldo + h * p.C + c] = 0.f;
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
+  __shared__ float sm_l[8];
+  __shared__ float4 sm_acc[8][32 * NV];
+  int64_t i; int h, kbeg, kend;
+  if (!giant_unit(p.hub, p.rowptr, p.H, i, h, kbeg, kend)) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const float sd = __ldg(p.s_dst + i * H + h);
+  const float M = p.rowmax[i * H + h];                    // final: written by edge_fwd_giant_max_kernel
+  const char* wb[NV];
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + 4 * ((lane + v * 32 < Q) ? lane + v * 32 : Q - 1));
+  }
+  float l = 0.f;
+  for (int k0 = kbeg + w * 32; k0 < kend; k0 += 256) {
+    const int k = k0 + lane;
+    const bool ok = k < kend;
+    int j = static_cast<int>(i);
+    float pp = 0.f, pm = 0.f;
+    if (ok) {
+      j = __ldg(p.col + k);
+      pp = expf(logit_act<true>(sd + __ldg(p.s_src + int64_t(j) * H + h), p.slope, p.act) - M);
+      pm = p.mask ? pp * __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h) : pp;
+    }
+    l += pp;
+    const int cnt = (kend - k0) < 32 ? (kend - k0) : 32;
+    for (int t = 0; t < cnt; t += U) {
+      int jt[U];
+      float pt[U];
+      float4 wv[U][NV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        jt[u] = __shfl_sync(FULL, j, t + u);
+        pt[u] = __shfl_sync(FULL, pm, t + u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) wv[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          acc[v].x = fmaf(pt[u], wv[u][v].x, acc[v].x);
+          acc[v].y = fmaf(pt[u], wv[u][v].y, acc[v].y);
+          acc[v].z = fmaf(pt[u], wv[u][v].z, acc[v].z);
+          acc[v].w = fmaf(pt[u], wv[u][v].w, acc[v].w);
+        }
+      }
+    }
+  }
+  l = group_sum<32>(l);
+  if (lane == 0) sm_l[w] = l;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sm_acc[w][lane + 32 * v] = acc[v];
+  __syncthreads();
+  const int q = threadIdx.x;
+  if (q < Q) {
+    float4 o = sm_acc[0][q];
+#pragma unroll
+    for (int w2 = 1; w2 < 8; ++w2) {
+      const float4 a = sm_acc[w2][q];
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    const float ov[4] = {o.x, o.y, o.z, o.w};
+    float* dst = p.heads_mode ? p.o_heads + i * p.Dp + h * Cp + 4 * q : p.out + i * p.ldo + h * p.C + 4 * q;
+    const int lim = p.heads_mode ? Cp : p.C;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * q + u < lim) atomicAdd(dst + u, ov[u]);
+  }
+  if (threadIdx.x == 0) {
+    float L = sm_l[0];
+#pragma unroll
+    for (int w2 = 1; w2 < 8; ++w2) L += sm_l[w2];
+    atomicAdd(p.rowsum + i * H + h, L);
+  }
+}
+
+__global__ void __launch_bounds__(128) edge_fwd_giant_finish_kernel(const EdgeFwdParams p) {
+  const int H = p.H;
+  const int64_t i = __ldg(p.hub + blockIdx.x / H);
+  const int h = static_cast<int>(blockIdx.x % H);
+  float amax = 0.f;
+  if (__ldg(p.rowptr + i + 1) - __ldg(p.rowptr + i) > B200GAT_GIANT_DEGREE) {
+    const float inv = 1.f / (p.rowsum[i * H + h] + 1e-16f);
+    if (p.heads_mode) {
+      for (int c = threadIdx.x; c < p.Cp; c += 128) p.o_heads[i * p.Dp + h * p.Cp + c] *= inv;
+    } else {
+      for (int c = threadIdx.x; c < p.C; c += 128) {
+        float* dst = p.out + i * p.ldo + h * p.C + c;
+        const float r = *dst * inv + __ldg(p.bias + h * p.C + c);
+        *dst = r;
+        amax = fmaxf(amax, fabsf(r));
+      }
+    }
+  }
+  if (p.out_amax && !p.heads_mode) warp_atomic_amax(p.out_amax, amax);
+}
+
+static int launch_edge_fwd_giant(const EdgeFwdParams& p, cudaStream_t stream) {
+  if (!p.hub || p.nhub <= 0 || p.max_deg <= B200GAT_GIANT_DEGREE) return 0;
+  const int64_t nseg = ceil_div(p.max_deg, B200GAT_GIANT_DEGREE);
+  B200GAT_REQUIRE(nseg <= 65535, B200GAT_E_UNSUPPORTED, "edge_fwd: a row of %d edges is not supported", p.max_deg);
+  const dim3 grid(static_cast<unsigned>(p.nhub * p.H), static_cast<unsigned>(nseg));
+  edge_fwd_giant_max_kernel<<<grid, 256, 0, stream>>>(p);
+  int rc = check_launch("edge_fwd_giant_max_kernel");
+  if (rc) return rc;
+  const int Q = p.Cp / 4;
+  if (Q <= 32) edge_fwd_giant_acc_kernel<1><<<grid, 256, 0, stream>>>(p);
+  else if (Q <= 64) edge_fwd_giant_acc_kernel<2><<<grid, 256, 0, stream>>>(p);
+  else edge_fwd_giant_acc_kernel<4><<<grid, 256, 0, stream>>>(p);
+  if ((rc = check_launch("edge_fwd_giant_acc_kernel"))) return rc;
+  edge_fwd_giant_finish_kernel<<<static_cast<unsigned>(p.nhub * p.H), 128, 0, stream>>>(p);
+  return check_launch("edge_fwd_giant_finish_kernel");
 }
 
 // ---- row-wide schedule for NARROW heads (head width < 128 channels, 2..8 heads, at most 512 padded channels per row):
@@ -439,8 +615,8 @@ static int launch_edge_fwd_hub(const EdgeFwdParams& p, cudaStream_t stream) {
 // gathered row is one contiguous H*Cp*4-byte read and the col[] -> s_src -> exp -> gather dependent chain is paid once
 // per chunk of G edges instead of once per (chunk, head) with chunks of only Cp/4 edges.  The edge-parallel phase
 // computes the H softmax weights of each edge and parks them (and the edge's source id) in shared memory; in the
-// feature-parallel phase every lane reads the weight of ITS slot's head.  Measured motivation: the per-(row, head)
-// schedule ran the 4 x 47 layer of the 2.4 M-node graph at 2.8 TB/s against 4.8 TB/s for 4 x 128.
+// feature-parallel phase every lane reads the weight of ITS slot's head.  Used for streaming graphs (rows gathered
+// from HBM), where the longer contiguous reads and the 4x larger chunks pay.
 template <int G, int NV, int HH, bool HAS_MASK>
 __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -620,9 +796,9 @@ static int launch_edge_fwd_row(const EdgeFwdParams& p, bool streaming, cudaStrea
   const int64_t want = ceil_div(ceil_div(p.N, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  (void)streaming;                                        // only dispatched for streaming graphs (see b200gat_edge_fwd)
   if (p.mask) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
-  else if (streaming) edge_fwd_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
-  else edge_fwd_row_kernel<G, NV, HH, false><<<blocks, threads, 0, stream>>>(p);
+  else edge_fwd_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_row_kernel");
 }
 
@@ -679,6 +855,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->graph.num_hub_rows == 0 || a->graph.rowend, B200GAT_E_NULL, "edge_fwd: graph.rowend missing");
   p.hub = a->graph.hub_rows; p.nhub = a->graph.num_hub_rows;
   p.rowend = p.nhub > 0 ? a->graph.rowend : a->graph.rowptr + 1;
+  p.max_deg = static_cast<int>(a->graph.max_in_degree);
   if (a->out_amax) {
     cudaError_t ce = cudaMemsetAsync(a->out_amax, 0, sizeof(uint32_t), stream);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_fwd: memset: %s", cudaGetErrorString(ce));
@@ -686,7 +863,10 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
 
   const int Q = Cp / 4;
   const bool streaming = edge_schedule_streaming(a->graph.span, int64_t(H) * Cp * 4);
-  if (edge_fwd_row_supported(H, Q, p.act)) {
+  // streaming graphs only — measured on the L2-resident PPI-shaped batch (heads sweep, 50 -> H x 64) the per-(row, head)
+  // schedule is faster (H = 4: 112 vs 141 us, H = 8: 221 vs 366 us); on the 2.4 M-node graph's 4 x 47 layer the row-wide
+  // one wins (12.8 vs 15.6 ms)
+  if (streaming && edge_fwd_row_supported(H, Q, p.act)) {
     switch (H) {
       case 2: rc = dispatch_edge_fwd_row<2>(p, H * Q, streaming, stream); break;
       case 3: rc = dispatch_edge_fwd_row<3>(p, H * Q, streaming, stream); break;

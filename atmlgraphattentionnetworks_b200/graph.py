@@ -48,7 +48,7 @@ def build_csr(edge_index, num_nodes, validate=True):
         g.eid = torch.empty(ep, **i32)
         g.crow = torch.empty(ep, **i32)
         g.ceid = torch.empty(ep, **i32)
-        status = torch.zeros(4, **i32)          # {bad indices, span, rows / columns with degree > HUB_DEGREE}
+        status = torch.zeros(6, **i32)          # {bad indices, span, hub rows, max in-degree, hub columns, max out-degree}
         hub_cap = ep // _abi.HUB_DEGREE + 1
         hubs = torch.empty((2, hub_cap), **i32)
         ends = torch.empty((2, max(n, 1)), **i32)
@@ -62,15 +62,15 @@ def build_csr(edge_index, num_nodes, validate=True):
         _abi.launches += 5 if ep else 0
         g.span = -1
         g.hub_rows = g.hub_cols = g.rowend = g.colend = None
-        n_hub = [0, 0]
+        n_hub, max_deg = [0, 0], [0, 0]
         if validate:
             # scheduling by degree (b200gat_graph.hub_rows): list the rows / columns longer than HUB_DEGREE
             for which, ptr in enumerate((g.rowptr, g.colptr)):
                 rc = lib.b200gat_hub_rows(ptr.data_ptr(), n, hubs[which].data_ptr(), hub_cap,
-                                          status[2 + which:].data_ptr(), ends[which].data_ptr(), stream)
+                                          status[2 + 2 * which:].data_ptr(), ends[which].data_ptr(), stream)
                 _abi.check(rc, "b200gat_hub_rows")
             # one D2H read: index check, the locality statistic, the hub counts
-            bad, span, n_hub[0], n_hub[1] = (int(v) for v in status.tolist())
+            bad, span, n_hub[0], max_deg[0], n_hub[1], max_deg[1] = (int(v) for v in status.tolist())
             if bad:
                 raise IndexError(f"edge_index has {bad} entries outside [0, {n})")
             g.span = span
@@ -81,7 +81,7 @@ def build_csr(edge_index, num_nodes, validate=True):
                            g.hub_rows.data_ptr() if n_hub[0] else None, n_hub[0],
                            g.rowend.data_ptr() if n_hub[0] else None,
                            g.hub_cols.data_ptr() if n_hub[1] else None, n_hub[1],
-                           g.colend.data_ptr() if n_hub[1] else None)
+                           g.colend.data_ptr() if n_hub[1] else None, max_deg[0], max_deg[1])
     return g
 
 

@@ -26,7 +26,7 @@ from .gat import _call, _layer_struct, _ptr, _workspace
 # ------------------------------------------------------------------------------------------------ graph partition
 class RowPartition:
     __slots__ = ("num_nodes", "world", "rank", "block", "lo", "hi", "rowptr", "col", "eid", "colptr", "crow", "ceid",
-                 "hub_rows", "hub_cols", "rowend", "colend", "_struct")
+                 "hub_rows", "hub_cols", "rowend", "colend", "max_in_degree", "max_out_degree", "_struct")
 
     @property
     def n_own(self):
@@ -79,15 +79,18 @@ def build_row_partition(edge_index, num_nodes, world, rank):
     p._struct = None
     # scheduling by degree (include/b200gat.h: b200gat_graph.hub_rows): own rows / columns longer than HUB_DEGREE
     def hubs(ptr):
-        is_hub = (ptr[1:] - ptr[:-1]) > _abi.HUB_DEGREE
-        return torch.nonzero(is_hub).flatten().to(torch.int32), torch.where(is_hub, ptr[:-1], ptr[1:]).contiguous()
-    (p.hub_rows, p.rowend), (p.hub_cols, p.colend) = hubs(rowptr), hubs(colptr)
+        deg = ptr[1:] - ptr[:-1]
+        is_hub = deg > _abi.HUB_DEGREE
+        return (torch.nonzero(is_hub).flatten().to(torch.int32), torch.where(is_hub, ptr[:-1], ptr[1:]).contiguous(),
+                int(deg.max()) if deg.numel() else 0)
+    (p.hub_rows, p.rowend, p.max_in_degree), (p.hub_cols, p.colend, p.max_out_degree) = hubs(rowptr), hubs(colptr)
     if rowptr.is_cuda:
         nr, nc = int(p.hub_rows.numel()), int(p.hub_cols.numel())
         p._struct = _abi.Graph(hi - lo, int(col.numel()), rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
                                colptr.data_ptr(), crow.data_ptr(), ceid.data_ptr(), n,   # span: one big graph
                                p.hub_rows.data_ptr() if nr else None, nr, p.rowend.data_ptr() if nr else None,
-                               p.hub_cols.data_ptr() if nc else None, nc, p.colend.data_ptr() if nc else None)
+                               p.hub_cols.data_ptr() if nc else None, nc, p.colend.data_ptr() if nc else None,
+                               p.max_in_degree, p.max_out_degree)
     return p
 
 
@@ -192,7 +195,8 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
                              wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
                              g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
                              part.num_nodes, part.hub_cols.data_ptr() if part.hub_cols.numel() else None,
-                             int(part.hub_cols.numel()), part.colend.data_ptr() if part.hub_cols.numel() else None)
+                             int(part.hub_cols.numel()), part.colend.data_ptr() if part.hub_cols.numel() else None,
+                             part.max_out_degree)
     _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
     return g_wh, g_s_src, g_s_dst_full
 

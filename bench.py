@@ -37,6 +37,9 @@ UNIT = "edges/s"
 
 
 # ------------------------------------------------------------------------------------------------ workloads
+HEADS = 8   # --heads: the point of the heads sweep (BASELINE configs[3]: 1, 2, 4, 8, 16 heads x 64)
+
+
 def make_workload(name, seed, sample=None):
     """-> (data, spec, loss_fn, description).  `sample` bounds the CPU baseline (fraction of the batch)."""
     import torch.nn.functional as F
@@ -52,9 +55,9 @@ def make_workload(name, seed, sample=None):
         desc = "large power-law graph (2.4M nodes, 62M edges, 100 feats, 47 classes), 3-layer GAT 4 heads x 128"
     elif name == "heads":
         data = synth.ppi_shaped(seed=seed, keep_graphs=sample)
-        spec = [(50, 64, 8, True)]
+        spec = [(50, 64, HEADS, True)]
         loss_fn = lambda out, y: out.sum()                                     # noqa: E731
-        desc = "heads sweep point: one layer 50 -> 8 heads x 64 on the PPI-shaped batch"
+        desc = f"heads sweep point: one layer 50 -> {HEADS} heads x 64 on the PPI-shaped batch"
     elif name == "cifar":
         # BASELINE configs[2]: run_gnn_benchmark.py:35-66 — GATNet('GAT','CIFAR10',F): conv1 -> elu -> conv2 -> elu ->
         # per-graph mean -> lin1 -> relu -> lin2 -> log_softmax, nll_loss per graph; dropout 0.0 (GATNet.py:19-20)
@@ -227,12 +230,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ppi", choices=["ppi", "heads", "large", "cifar", "cora"])
+    ap.add_argument("--heads", type=int, default=8, help="--workload heads: number of heads (x 64 channels)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the resident train step in a CUDA graph and time replays (launch-bound workloads)")
     ap.add_argument("--cpu-sample-graphs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu runs): warm-up + steps, minimal JSON")
     args = ap.parse_args()
+    global HEADS
+    HEADS = args.heads
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

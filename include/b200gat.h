@@ -74,9 +74,12 @@ typedef struct {
   const int32_t* hub_cols; /* [num_hub_cols] source rows      with out-degree > B200GAT_HUB_DEGREE (any order) */
   int64_t num_hub_cols;
   const int32_t* colend;   /* [N] colptr[j + 1], but colptr[j] for the rows listed in hub_cols */
+  int64_t max_in_degree;   /* largest in- / out-degree (count[1] of b200gat_hub_rows); hub rows longer than */
+  int64_t max_out_degree;  /* B200GAT_GIANT_DEGREE are cut into segments of that many edges, one CTA per segment */
 } b200gat_graph;
 
 #define B200GAT_HUB_DEGREE 512
+#define B200GAT_GIANT_DEGREE 4096
 
 /* Layer geometry, GAT.py:8 (input_channels, output_channels, num_heads, concat). */
 typedef struct {
@@ -112,8 +115,8 @@ int b200gat_csr_build(const int64_t* edge_index, int64_t num_input_edges, int64_
 
 /* Lists the rows of a CSR / CSC pointer array whose degree exceeds B200GAT_HUB_DEGREE: list[0 .. *count) (device, any
  * order, at most `cap` entries written; cap >= ptr[num_rows] / B200GAT_HUB_DEGREE + 1 always suffices), *count (device
- * int32) = their number, ends[r] (device [num_rows]) = ptr[r + 1], or ptr[r] for a listed row.  The caller reads
- * *count back and passes it as num_hub_rows / num_hub_cols. */
+ * int32[2]) = {their number, the largest degree}, ends[r] (device [num_rows]) = ptr[r + 1], or ptr[r] for a listed row.
+ * The caller reads count back and passes it as num_hub_rows / max_in_degree (num_hub_cols / max_out_degree). */
 int b200gat_hub_rows(const int32_t* ptr, int64_t num_rows, int32_t* list, int64_t cap, int32_t* count, int32_t* ends,
                      void* stream);
 
@@ -219,6 +222,7 @@ typedef struct {
   int64_t span;                       /* as b200gat_graph.span for the gathered rows `g` (< 0: unknown) */
   const int32_t* hub_cols; int64_t num_hub_cols;   /* own source rows with out-degree > B200GAT_HUB_DEGREE (or NULL / 0) */
   const int32_t* colend;              /* [rows] as b200gat_graph.colend (required when num_hub_cols > 0) */
+  int64_t max_out_degree;             /* as b200gat_graph.max_out_degree for the own source rows */
 } b200gat_edge_bwd_csc_args;
 int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
 

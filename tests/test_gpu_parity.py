@@ -160,6 +160,22 @@ ORACLE_CASES = [
 
 @pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: c[0])
 def test_layer_matches_cpu_oracle(case):
+    _run_oracle_case(case, force_stream=False)
+
+
+# the schedules picked for graphs whose gathered rows stream from HBM (b200gat_graph.span large: edge_fwd_stream_kernel,
+# the row-wide edge_fwd of narrow heads, ...) on the same small cases: the cached CSR's span is overridden
+STREAM_CASES = [c for c in ORACLE_CASES if c[0] in ("ppi_l1_like", "large_l3_like", "heads8x64_hub", "heads2x64_drop_hub",
+                                                    "mean_h8c12_drop_hub", "mean_h3c33_hub", "c128_hub",
+                                                    "c20_cat_unaligned_out", "cora_l1_like_drop")]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: c[0])
+def test_streaming_schedule_matches_cpu_oracle(case):
+    _run_oracle_case(case, force_stream=True)
+
+
+def _run_oracle_case(case, force_stream):
     import GAT
     from oracle.gat_port import PortGraphAttentionLayer
     name, n, e, f, c, h, concat, p, hub = case
@@ -172,6 +188,8 @@ def test_layer_matches_cpu_oracle(case):
     if hub:
         ei[1, : e // 4] = 11
         ei[0, e // 4: e // 2] = 13                         # hub source too (CSC side)
+        ei[1, e // 2: e // 2 + 900] = 17                   # mid-size hubs (HUB_DEGREE < degree <= GIANT_DEGREE: one CTA
+        ei[0, e // 2 + 900: e // 2 + 1800] = 19            # per (row, head)); the two above are cut into segments
     x = torch.randn(n, f, generator=gen)
     gout = torch.randn(n, h * c if concat else c, generator=gen)
     mask = None
@@ -199,7 +217,14 @@ def test_layer_matches_cpu_oracle(case):
     if mask is not None:
         layer.mask_hook = lambda shape: mask
     xg = x.detach().clone().to(DEV).requires_grad_(True)
-    out = layer(xg, ei.to(DEV))
+    eig = ei.to(DEV)
+    if force_stream:
+        from atmlgraphattentionnetworks_b200.graph import GraphCache
+        layer.graph_cache = GraphCache()
+        layer.graph_cache.get(eig, n).c_struct().span = 1 << 40     # "every gathered row comes from HBM"
+    out = layer(xg, eig)
+    if force_stream:
+        assert layer.graph_cache.hits == 1
     out.backward(gout.to(DEV))
     got = packed_grads(layer, xg.grad)
     got["out"] = out.detach().cpu().numpy()
