@@ -303,6 +303,8 @@ struct EdgeBwdParams {
   // edge_bwd_hub_kernel, one CTA per (source row, head).  No compare, no extra register in the hot kernels.
   const int32_t* colend; const int32_t* hub; int64_t nhub;
   int max_deg;          // largest out-degree: source rows above B200GAT_GIANT_DEGREE are split into segments (grid.y)
+  uint32_t* amax;       // optional [2]: bit patterns of max|gWh| and max|g_s_src| (atomicMax; zeroed by the host) — saves
+                        // gt_amax_kernel's pass over gWh.  Not exact for giant rows (partial sums): the host ignores it then
 };
 
 // Sum U per-lane partials over the G lanes of a group and hand the total of edge u to the lane with rel == u.
@@ -390,6 +392,7 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
     off[v] = 4 * (live[v] ? gl + v * G : Q - 1);
   }
 
+  float amax_w = 0.f, amax_s = 0.f;
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
     const int64_t item = base + gi;
     const bool valid = item < p.items;
@@ -480,14 +483,26 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
     gsrc = group_sum<G>(gsrc);
     if (!valid) continue;
     if (gl == 0) p.g_s_src[j * H + h] = gsrc;
+    amax_s = fmaxf(amax_s, fabsf(gsrc));
 #pragma unroll
     for (int v = 0; v < NV; ++v)
-      if (live[v]) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off[v]) = acc[v];
+      if (live[v]) {
+        *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off[v]) = acc[v];
+        amax_w = fmaxf(amax_w, fmaxf(fmaxf(fabsf(acc[v].x), fabsf(acc[v].y)), fmaxf(fabsf(acc[v].z), fabsf(acc[v].w))));
+      }
+  }
+  if (p.amax) {
+    warp_atomic_amax(p.amax, amax_w);
+    warp_atomic_amax(p.amax + 1, amax_s);
   }
 }
 
+// 4 CTAs per SM (64 registers) for heads up to 256 channels: without the bound ptxas picks 64 or 80 registers depending
+// on details as small as the amax bookkeeping at the end of an item
 template <int G, int NV, bool HAS_MASK, bool HUB>
-__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, HAS_MASK, false, HUB>(p); }
+__global__ void __launch_bounds__(256, (NV <= 2 && !HAS_MASK) ? 4 : 2) edge_bwd_kernel(const EdgeBwdParams p) {
+  edge_bwd_body<G, NV, HAS_MASK, false, HUB>(p);
+}
 // other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
 template <int G, int NV>
 __global__ void __launch_bounds__(256) edge_bwd_act_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, true, true, true>(p); }
@@ -541,6 +556,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
   const int off = 4 * (live ? gl : Q - 1);
   const char* gb = reinterpret_cast<const char*>(p.g + off);
 
+  float amax_w = 0.f, amax_s = 0.f;
   for (int64_t base = warp * GPW; base < p.N; base += nwarps * GPW) {
     const int64_t j = base + gi < p.N ? base + gi : p.N - 1;
     const bool valid = base + gi < p.N;
@@ -636,10 +652,19 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
 #pragma unroll
       for (int h = 0; h < HH; ++h) p.g_s_src[j * HH + h] = gsrc[h];
     }
+#pragma unroll
+    for (int h = 0; h < HH; ++h) amax_s = fmaxf(amax_s, fabsf(gsrc[h]));
     if (live) {
 #pragma unroll
-      for (int h = 0; h < HH; ++h) *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off) = acc[h];
+      for (int h = 0; h < HH; ++h) {
+        *reinterpret_cast<float4*>(p.gwh + j * Dp + h * Cp + off) = acc[h];
+        amax_w = fmaxf(amax_w, fmaxf(fmaxf(fabsf(acc[h].x), fabsf(acc[h].y)), fmaxf(fabsf(acc[h].z), fabsf(acc[h].w))));
+      }
     }
+  }
+  if (p.amax) {
+    warp_atomic_amax(p.amax, amax_w);
+    warp_atomic_amax(p.amax + 1, amax_s);
   }
 }
 
@@ -693,6 +718,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
     live[v] = lane + v * 32 < Q;
     off[v] = 4 * (live[v] ? lane + v * 32 : Q - 1);
   }
+  float amax_w = 0.f, amax_s = 0.f;
   for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
     const int64_t j = __ldg(p.hub + item / H);
     const int h = static_cast<int>(item % H);
@@ -787,6 +813,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
       float* dst = p.gwh + j * Dp + h * Cp + 4 * q;
       if (giant) { atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w); }
       else *reinterpret_cast<float4*>(dst) = o;
+      amax_w = fmaxf(amax_w, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
     }
     if (threadIdx.x == 0) {
       float g = sm_g[0];
@@ -794,8 +821,13 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
       for (int w2 = 1; w2 < 8; ++w2) g += sm_g[w2];
       if (giant) atomicAdd(p.g_s_src + j * H + h, g);
       else p.g_s_src[j * H + h] = g;
+      amax_s = fmaxf(amax_s, fabsf(g));
     }
     __syncthreads();
+  }
+  if (p.amax) {                                           // (ignored by the host when giant rows exist)
+    warp_atomic_amax(p.amax, amax_w);
+    warp_atomic_amax(p.amax + 1, amax_s);
   }
 }
 
@@ -1052,7 +1084,7 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
 static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, const int32_t* crow, const int32_t* ceid,
                    const float* wh, const float* s_src, const float4* rowrec, const float* mask, const float* gsrc_rows,
                    int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, const int32_t* colend,
-                   const int32_t* hub, int64_t nhub, int64_t max_deg, cudaStream_t stream) {
+                   const int32_t* hub, int64_t nhub, int64_t max_deg, uint32_t* amax, cudaStream_t stream) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
   p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
@@ -1063,6 +1095,7 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
   B200GAT_REQUIRE(nhub >= 0 && (nhub == 0 || (hub && colend)), B200GAT_E_NULL, "edge_bwd: hub_cols / colend missing");
   p.hub = hub; p.nhub = nhub; p.colend = nhub > 0 ? colend : colptr + 1;
   p.max_deg = static_cast<int>(max_deg);
+  p.amax = amax;
   const int Q = g.Cp / 4;
   const bool streaming = edge_schedule_streaming(span, ldg * 4);
   int rc;
@@ -1091,7 +1124,7 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
 // (outputs are overwritten, not accumulated).  amax: the 5 slots described at FinishParams (planes mode only).
 static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, const float* a1, const float* a2,
                       const float* g_s_src, const float* g_s_dst, float* g_t, float* g_bw, float* g_a1, float* g_a2,
-                      float* g_b1, float* g_b2, void* gsplit, uint32_t* amax, cudaStream_t stream) {
+                      float* g_b1, float* g_b2, void* gsplit, uint32_t* amax, bool amax_from_csc, cudaStream_t stream) {
   const Geom g = geom_of(L);
   cudaError_t ce = cudaMemsetAsync(g_bw, 0, g.Dp * sizeof(float), stream);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(g_a1, 0, g.Dp * sizeof(float), stream);
@@ -1108,8 +1141,10 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
   if (gsplit) {
     const int64_t n_nh = rows * g.H;
     const int64_t want = ceil_div(rows * g.Dp, 256 * 16);
-    gt_amax_kernel<<<static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, stream>>>(
-        g_t, rows * g.Dp, g_s_src, g_s_dst, n_nh, a1, a2, f.Dp, amax);
+    // max|gWh| (and max|g_s_src|) came out of the CSC pass when amax_from_csc: only the small [N, H] / [Dp] arrays are read
+    const int64_t want_b = amax_from_csc ? ceil_div(n_nh, 256 * 4) : want;
+    gt_amax_kernel<<<static_cast<int>(want_b < cap ? (want_b > 0 ? want_b : 1) : cap), 256, 0, stream>>>(
+        g_t, amax_from_csc ? 0 : rows * g.Dp, g_s_src, g_s_dst, n_nh, a1, a2, f.Dp, amax);
     int rc = check_launch("gt_amax_kernel");
     if (rc) return rc;
     const Blob B = make_blob(gsplit, rows, g.Dp);
@@ -1159,7 +1194,7 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
     cudaError_t ce = cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
     return run_finish(L, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
-                      nullptr, nullptr, stream);
+                      nullptr, nullptr, false, stream);
   }
   B200GAT_REQUIRE(a->gout && a->wh && a->s_src && a->s_dst && a->rowmax && a->rowsum && a->a1 && a->a2 && a->g_t &&
                   a->bias && a->workspace, B200GAT_E_NULL, "edge_bwd: NULL pointer");
@@ -1202,10 +1237,12 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
   if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
                     a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols,
-                    a->graph.max_out_degree, stream)))
+                    a->graph.max_out_degree, gsplit ? amax : nullptr, stream)))
     return rc;
+  // giant source rows are accumulated from per-segment partial sums: their maxima are not the maxima of the sums
+  const bool amax_from_csc = gsplit && a->graph.max_out_degree <= B200GAT_GIANT_DEGREE;
   return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
-                    gsplit, amax, stream);
+                    gsplit, amax, amax_from_csc, stream);
 }
 
 // ---- staged entry points (destination-row partitioned multi-GPU execution: the caller runs the collectives between
@@ -1245,7 +1282,7 @@ extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* st
                   a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
   return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
                  reinterpret_cast<const float4*>(a->rowrec), a->mask, a->g, a->ldg, static_cast<int>(a->g_head_stride),
-                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, stream);
+                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, nullptr, stream);
 }
 
 extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream_) {
@@ -1260,5 +1297,5 @@ extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, vo
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
                   "edge_bwd_finish: wh / g_t / a1 / a2 must be 16-byte aligned");
   return run_finish(a->layer, a->num_rows, a->wh, a->a1, a->a2, a->g_s_src, a->g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2,
-                    a->g_b1, a->g_b2, nullptr, nullptr, stream);
+                    a->g_b1, a->g_b2, nullptr, nullptr, false, stream);
 }
