@@ -34,6 +34,32 @@ def test_row_partition_is_a_slice_of_the_canonical_csr(n, e, world):
     assert seen_rows == n
 
 
+def test_row_partition_degree_classes():
+    """hub rows / columns (degree > HUB_DEGREE) of every rank's block, their rowend / colend view and the largest degrees
+    (include/b200gat.h: b200gat_graph.hub_rows ...), against the canonical arrays."""
+    from atmlgraphattentionnetworks_b200._abi import HUB_DEGREE
+    n, e, world = 90, 5000, 3
+    rng = np.random.default_rng(5)
+    ei = rng.integers(0, n, size=(2, e))
+    ei[1, :1500] = 7                                           # hub destination (rank 0)
+    ei[0, 1500:2400] = 64                                      # hub source (rank 2)
+    want = csr_oracle(ei, n)
+    b = block_size(n, world)
+    found = [0, 0]
+    for r in range(world):
+        p = build_row_partition(torch.from_numpy(ei), n, world, r)
+        lo, hi = min(r * b, n), min((r + 1) * b, n)
+        for which, (ptr_k, hubs, ends, mx) in enumerate((("rowptr", p.hub_rows, p.rowend, p.max_in_degree),
+                                                         ("colptr", p.hub_cols, p.colend, p.max_out_degree))):
+            ptr = want[ptr_k][lo:hi + 1] - want[ptr_k][lo]
+            deg = np.diff(ptr)
+            assert np.array_equal(np.sort(hubs.numpy()), np.nonzero(deg > HUB_DEGREE)[0])
+            assert np.array_equal(ends.numpy().astype(np.int64), np.where(deg > HUB_DEGREE, ptr[:-1], ptr[1:]))
+            assert mx == deg.max()
+            found[which] += int(hubs.numel())
+    assert found == [1, 1]
+
+
 def test_gather_layout():
     assert gather_layout((100, 128, 4, True)) == (True, 512, 512, 128)       # gout gathered directly
     assert gather_layout((512, 47, 4, False)) == (False, 48, 48, 0)          # mean mode: one padded [C] row per node
