@@ -895,7 +895,7 @@ gt_amax_kernel(const float* __restrict__ gwh, int64_t n_nd, const float* __restr
 
 // one thread per FOUR adjacent columns (same head: c_pad % 4 == 0), a strip of rows per blockIdx.y
 template <bool PLANES>
-__global__ void __launch_bounds__(256) bwd_finish_kernel(const FinishParams p) {
+__global__ void __launch_bounds__(256, 4) bwd_finish_kernel(const FinishParams p) {
   const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= p.Dp) return;
   const int h = c / p.Cp;
@@ -939,12 +939,10 @@ __global__ void __launch_bounds__(256) bwd_finish_kernel(const FinishParams p) {
       t[u].z += gs[u] * a1c.z + gd[u] * a2c.z;
       t[u].w += gs[u] * a1c.w + gd[u] * a2c.w;
       if (PLANES) {
-        __align__(8) __half hv[4];
-        __align__(8) __half lv[4];
-        split_half(t[u].x * scale, hv[0], lv[0]);
-        split_half(t[u].y * scale, hv[1], lv[1]);
-        split_half(t[u].z * scale, hv[2], lv[2]);
-        split_half(t[u].w * scale, hv[3], lv[3]);
+        __align__(8) __half2 hv[2];
+        __align__(8) __half2 lv[2];
+        split_half2(t[u].x * scale, t[u].y * scale, hv[0], lv[0]);
+        split_half2(t[u].z * scale, t[u].w * scale, hv[1], lv[1]);
         *reinterpret_cast<uint2*>(p.hi + r * p.ldp + c) = *reinterpret_cast<const uint2*>(hv);
         *reinterpret_cast<uint2*>(p.lo + r * p.ldp + c) = *reinterpret_cast<const uint2*>(lv);
       } else {

@@ -562,10 +562,12 @@ split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t co
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(p + j) : 0.f;
     }
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
+    __align__(16) __half2 h[4];
+    __align__(16) __half2 l[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_half((ACT == ACT_ELU ? elu_fwd(v[j]) : v[j]) * s, h[j], l[j]);
+    for (int j = 0; j < 4; ++j)
+      split_half2((ACT == ACT_ELU ? elu_fwd(v[2 * j]) : v[2 * j]) * s, (ACT == ACT_ELU ? elu_fwd(v[2 * j + 1]) : v[2 * j + 1]) * s,
+                  h[j], l[j]);
     *reinterpret_cast<uint4*>(hi + r * ldp + c0) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + r * ldp + c0) = *reinterpret_cast<const uint4*>(l);
   }

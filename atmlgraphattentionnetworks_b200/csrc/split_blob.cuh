@@ -43,6 +43,13 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// two values at once: one packed convert per pair and plane (F2FP.F16.F32.PACK_AB) instead of one F2F per value
+__device__ __forceinline__ void split_half2(float x0, float x1, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hi);
+  lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+}
+
 // activations fused into operand loads / gradient passes (GATNet.py:63-75: F.elu between the layers)
 enum { ACT_NONE = 0, ACT_ELU = 1 };
 __device__ __forceinline__ float elu_fwd(float x) { return x > 0.f ? x : expm1f(x); }

@@ -18,6 +18,7 @@ CASES = [  # N, E, F, C, H, concat, world
     (700, 8000, 96, 47, 4, False, 3),
     (640, 6000, 33, 5, 3, True, 2),
     (512, 5000, 50, 7, 1, False, 8),
+    (3000, 40000, 32, 64, 2, True, 2),      # e // 5 = 8000 in-edges of node 17: a "giant" row (cut into segments)
 ]
 
 
@@ -41,7 +42,8 @@ def test_partitioned_stages_match_single_gpu(case):
         layer.bias.uniform_(-0.5, 0.5)
     x = torch.randn(n, f, device=DEV)
     ei = torch.randint(0, n, (2, e), device=DEV)
-    ei[1, : e // 5] = 17
+    ei[1, : e // 5] = 17                                    # hub destination (degree > HUB_DEGREE)
+    ei[0, e // 5: e // 5 + max(700, e // 8)] = 23           # hub source (CSC side); giant in the last case
     gout = torch.randn(n, h * c if concat else c, device=DEV)
     out_ref, gx_ref, grads_ref = _single_gpu(layer, x, ei, gout)
 
