@@ -115,6 +115,9 @@ class GraphCache:
             self.hits += 1
             return found
         self.misses += 1
+        # an older version of the SAME tensor object can never be hit again (the version counter only grows): drop it now,
+        # so a loader that refills one device buffer per batch recycles the CSR memory instead of growing the cache
+        self._entries = [ent for ent in self._entries if ent[0]() is not edge_index]
         g = build_csr(edge_index, num_nodes)
         self._entries.append((weakref.ref(edge_index), edge_index._version, num_nodes, g))
         if len(self._entries) > self.capacity:
