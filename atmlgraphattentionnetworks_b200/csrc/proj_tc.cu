@@ -712,13 +712,18 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 // GEMMs it is no faster than the single-CTA kernel (forward 229.9 vs 227 us, gX 298 vs 303, gW 271 vs 296) — at
 // ~1.56 PFLOP/s of fp16 MMA work those kernels already run at 92 % of the pool's measured cuBLAS bf16 burst rate
 // (1.69 PFLOP/s; the part is power-limited well below the nominal 2.25), so halving the operand bytes buys nothing.
-static bool use_pair(int64_t M, int bn) {
+// Re-measured after the store epilogue was coalesced (it had hidden the difference): with K >= 1024 the pair is ahead in
+// the backward GEMMs of the PPI-shaped layers (gX + gW 629 -> 597 us, 519 -> 475 us) and level in the forward; with K = 512
+// (2.4 M-node graph) it is 1-2 % behind.  Default: pairs for the backward GEMMs with K >= 1024; B200GAT_GEMM_PAIR=0|1 forces
+// either for every GEMM.
+static bool use_pair(int64_t M, int bn, int64_t K, bool backward) {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("B200GAT_GEMM_PAIR");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = !e ? 2 : ((e[0] == '1') ? 1 : 0);
   }
-  return on && bn == 256 && M >= 256;
+  if (!on || bn != 256 || M < 256) return false;
+  return on == 1 || (backward && K >= 1024);   // `backward`: the gX / gW GEMMs (B operand MN-major)
 }
 
 // C[M,N] (=, +bias | +=) A · B^T.  A is the blob of a [M,K] (K-major) or [K,M] (A_MN) tensor, B of a [N,K] (K-major)
@@ -736,7 +741,7 @@ static int gemm_blobs(const Blob& A, const Blob& B, int64_t M, int64_t N, int64_
   const int bn = N > 128 ? 256 : 128;
   CUtensorMap ah, al, bh, bl;
   int rc;
-  const bool pair = use_pair(M, bn);
+  const bool pair = use_pair(M, bn, K, B_MN);
   const int a_box = A_MN ? 64 : TC_BM, b_box = B_MN ? 64 : (pair ? bn / 2 : bn);
   if ((rc = make_map(&ah, A.hi(), A.rows, A.cols, A.ldp, a_box))) return rc;
   if ((rc = make_map(&al, A.lo(), A.rows, A.cols, A.ldp, a_box))) return rc;
