@@ -85,8 +85,8 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
     // tools/microbench/gather_bench.cu (PPI-shaped batch, same loop): NV=2: weights-first U=4 0.279 ms, early U=4 0.317,
     // early U=2 0.233 (a bare gather loop: 0.204); NV=1: weights-first U=8 is the best on the streaming graph.
     // Double-buffering the batches in registers was measured slower (80 registers: 3 instead of 4 CTAs per SM).
-    if constexpr (!HAS_MASK && NV == 2 && !STREAM) {
-      constexpr int U = 2;
+    if constexpr (!HAS_MASK && (NV == 2 || (NV == 1 && G == 32)) && !STREAM) {
+      constexpr int U = NV == 2 ? 2 : 4;
       for (int k0 = 0; k0 < maxdeg; k0 += G) {
         const int k = beg + k0 + gl;
         const bool ok = k < end;
