@@ -11,6 +11,9 @@
 // into one 16-byte gatherable word)  ->  edge_bwd_kernel (CSC: one lane group per (source row j, head h); Wh[j,h,:]
 // stays in registers, G[i] rows are gathered 128 bits per lane; gWh / g_s_src are written without atomics, g_s_dst is
 // the one cross-orientation reduction: [N,H] float atomics)  ->  bwd_finish_kernel (stream: gT in place + column sums).
+// CSC-pass variants: edge_bwd_mean_kernel (mean-over-heads layers: one lane group per source row,
+// G[i] gathered once for all heads), edge_bwd_hub_kernel (out-degree > 512: one CTA per (source row, head); > 4096: one
+// CTA per 4096-edge segment, partial sums added atomically), edge_bwd_act_kernel (LogSigmoid / Tanh logits).
 #include "common.cuh"
 #include "split_blob.cuh"
 #include "proj_tc.cuh"

@@ -12,6 +12,14 @@
 // FEATURE-parallel: the (j, p) pair of each edge is broadcast by width-G shuffles and every lane gathers its
 // 128-bit slices of Wh[j,h,:] (ld.global.nc.v4.f32) into NV float4 accumulators.  The softmax is online per chunk of
 // G edges (running max / sum; only rows longer than G ever rescale), so every row is walked exactly once.
+//
+// Kernels in this file, by degree class and regime:
+//   edge_fwd_kernel / edge_fwd_stream_kernel ... lane group per (row, head): L2-resident / HBM-streaming gathers
+//   edge_fwd_row_stream_kernel ................. lane group per ROW (all heads), narrow heads on streaming graphs
+//   edge_fwd_hub_kernel ........................ one CTA per (row, head) for 512 < in-degree <= 4096
+//   edge_fwd_giant_{max,acc,finish}_kernel ..... in-degree > 4096: one CTA per 4096-edge segment, atomics to combine
+//   edge_fwd_act_kernel ........................ LogSigmoid / Tanh logits (run_act_func_experiment.py)
+//   head_mean_kernel ........................... concat == False, H > 1 (GAT.py:65-66)
 #include "common.cuh"
 #include "split_blob.cuh"
 #include <math.h>
