@@ -376,7 +376,9 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   // edges gathered per step: bytes in flight decide the streaming-regime throughput (measured: 4 -> 8 gathers in
   // flight per lane took the large-graph forward from 2.9 to 3.7 TB/s); registers bound it for wide heads
   // (backward: 8 per step measured SLOWER than 4 on the large graph, 44.7 vs 41.0 ms — the dependent rowrec gather
-  //  and the longer transposing reduce outweigh the extra loads in flight)
+  //  and the longer transposing reduce outweigh the extra loads in flight.
+  //  Also measured: two gather batches sharing ONE 8-value transposing reduce (19 instead of 2 x 14 shuffle / select / add
+  //  instructions per 8 edges) — the four extra live partials spill at 64 registers: PPI edge_bwd 734 -> 756 us.)
   constexpr int U = NV <= 2 ? 4 : 2;
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;

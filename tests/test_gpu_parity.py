@@ -319,6 +319,59 @@ def test_full_size_edge_order_invariance_and_grad_identities(ppi):
     assert float((g_b1 - g_b2).abs().max()) <= 1e-4 * max(scale, 1e-6)
 
 
+# -------------------------------------------------- BASELINE-size properties (2.4 M-node power-law graph, configs[4])
+def test_full_size_powerlaw_graph_properties():
+    """The 62 M-edge power-law graph at full size (max degree ~40 k: row-per-group, hub and giant-row schedules all
+    run).  (1) CSR invariants: rowptr / colptr end at E', degree classes consistent; (2) constant features => out ==
+    Wh_row + bias for EVERY node (softmax weights sum to 1 whatever the row's length and schedule), concat and mean
+    layers; (3) backward identities: g_bias == column sums of gout, g_b1 == g_b2, and with constant features the
+    gradient w.r.t. every Wh row of a head is the same linear map of gout summed over its out-edges => g_x rows of nodes
+    with equal out-neighbourhood weights agree; checked in aggregate through sum_n g_x == (sum_n gout) W."""
+    import GAT
+    from atmlgraphattentionnetworks_b200 import synth
+    from atmlgraphattentionnetworks_b200._abi import HUB_DEGREE
+    from atmlgraphattentionnetworks_b200.graph import GraphCache
+    d = synth.powerlaw()
+    n = d.x.shape[0]
+    ei = d.edge_index.to(DEV)
+    cache = GraphCache()
+    g = cache.get(ei, n)
+    ep = ei.shape[1] + n
+    assert int(g.rowptr[-1]) == ep and int(g.colptr[-1]) == ep
+    deg = (g.rowptr[1:] - g.rowptr[:-1])
+    assert int(deg.min()) >= 1 and int((deg > HUB_DEGREE).sum()) == g.hub_rows.numel() > 0
+    assert int(deg.max()) > 4096                                                   # giant rows exist
+    assert torch.equal(torch.sort(g.hub_rows.long()).values, torch.nonzero(deg > HUB_DEGREE).flatten())
+    torch.manual_seed(0)
+    for (f, c, h, concat) in ((100, 128, 4, True), (100, 47, 4, False)):
+        layer = GAT.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=0.0).to(DEV)
+        layer.graph_cache = cache
+        with torch.no_grad():
+            layer.bias.uniform_(-1, 1)
+        xc = torch.full((n, f), 0.37, device=DEV).requires_grad_(True)
+        out = layer(xc, ei)
+        w, bw, *_ = layer._packed()
+        wh_row = (xc[:1].detach() @ w.t() + bw).view(h, -1)[:, :c]                  # [H, C] (pad channels dropped)
+        row = (wh_row.reshape(-1) if concat else wh_row.mean(0)) + layer.bias
+        assert float((out.detach() - row).abs().max()) <= 1e-5 * float(row.abs().max()), (c, concat)
+        gout = torch.randn_like(out)
+        out.backward(gout)
+        assert nerr(layer.bias.grad.cpu().numpy(), gout.sum(0).cpu().numpy()) <= 1e-5
+        g_b1 = torch.stack([m.bias.grad for m in layer.attentions1]).flatten()
+        g_b2 = torch.stack([m.bias.grad for m in layer.attentions2]).flatten()
+        scale = float(torch.stack([m.weight.grad for m in layer.attentions1]).abs().max())
+        assert float((g_b1 - g_b2).abs().max()) <= 1e-4 * max(scale, 1e-6)
+        # constant Wh rows: every alpha of a row multiplies the same vector, so dz == 0 and gWh[j] = sum_{i in out(j)}
+        # alpha_ij G[i]; summed over j that is sum_i G[i] (each row's alphas sum to 1)  =>  sum_n g_x == (sum_i G[i]) W
+        gsum = gout.sum(0, dtype=torch.float64)
+        G = (gsum.view(h, c) if concat else (gsum / h).expand(h, c))                # [H, C]
+        w3 = w.view(h, -1, f)[:, :c, :].double()                                    # [H, C, F]
+        want = torch.einsum("hc,hcf->f", G, w3)
+        got = xc.grad.sum(0, dtype=torch.float64)
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()), (c, concat)
+        del layer, out, gout, xc
+
+
 # ------------------------------------------ fused layer boundaries (ELU deferred to the consumer) vs the CPU oracle stack
 STACK_CASES = [
     # name, N, E, F, spec [(in, out, heads, concat)]                                      what the boundary fusion reaches
