@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -41,7 +41,8 @@ class ProjFwdArgs(C.Structure):
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
-                ("x_activation", C.c_int32), ("x_amax", C.c_void_p)]
+                ("x_activation", C.c_int32), ("x_amax", C.c_void_p),
+                ("wh_peers", C.c_void_p * 7), ("num_peers", C.c_int32)]
 
 
 class EdgeFwdArgs(C.Structure):

@@ -80,6 +80,7 @@ extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->x_activation == ACT_NONE || a->x_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
                   "proj_fwd: unknown x_activation %d", a->x_activation);
   if (proj_tc_fwd_supported(L, N)) return proj_tc_fwd(*a, stream);
+  B200GAT_REQUIRE(a->num_peers == 0, B200GAT_E_UNSUPPORTED, "proj_fwd: wh_peers needs the tensor-core path (shape too small)");
   rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream, a->x_activation);
   if (rc) return rc;
   return launch_logits(*a, stream);

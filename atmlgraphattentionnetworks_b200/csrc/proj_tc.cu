@@ -183,6 +183,9 @@ struct TcGemmParams {
   const float* inv_a; const float* inv_b;   // device scalars: 1/s of the two operand splits
   // fused attention-logit epilogue (EPI_LOGITS)
   const float* a1; const float* a2; const float* b1; const float* b2; float* s_src; float* s_dst; int H, Cp;
+  // projection fused with the all-gather of its output (b200gat_proj_fwd_args.wh_peers): every stored tile is also written
+  // to the same (row, column) of n_peer peer-mapped copies of C
+  float* peer_c[B200GAT_MAX_PEERS]; int n_peer;
 };
 
 enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2 };
@@ -505,10 +508,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 float* d = p.C + rr * p.ldc + col;
                 if (col + 4 <= p.N) {
                   *reinterpret_cast<float4*>(d) = v;
+                  for (int k = 0; k < p.n_peer; ++k)    // fused all-gather: the same 64-byte runs over NVLink
+                    *reinterpret_cast<float4*>(p.peer_c[k] + rr * p.ldc + col) = v;
                 } else if (col < p.N) {                 // the (rare) ragged group of a column tail
                   d[0] = v.x;
                   if (col + 1 < p.N) d[1] = v.y;
                   if (col + 2 < p.N) d[2] = v.z;
+                  for (int k = 0; k < p.n_peer; ++k) {
+                    float* dk = p.peer_c[k] + rr * p.ldc + col;
+                    dk[0] = v.x;
+                    if (col + 1 < p.N) dk[1] = v.y;
+                    if (col + 2 < p.N) dk[2] = v.z;
+                  }
                 }
               }
             }
@@ -804,6 +815,12 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   p.C = a.wh; p.ldc = Dp; p.bias = a.bw;
   p.a1 = a.a1; p.a2 = a.a2; p.b1 = a.b1; p.b2 = a.b2; p.s_src = a.s_src; p.s_dst = a.s_dst;
   p.H = static_cast<int>(H); p.Cp = static_cast<int>(Cp);
+  B200GAT_REQUIRE(a.num_peers >= 0 && a.num_peers <= B200GAT_MAX_PEERS, B200GAT_E_SHAPE, "proj_fwd: num_peers out of range");
+  p.n_peer = a.num_peers;
+  for (int k = 0; k < a.num_peers; ++k) {
+    B200GAT_REQUIRE(a.wh_peers[k] && aligned16(a.wh_peers[k]), B200GAT_E_ALIGN, "proj_fwd: wh_peers[%d] NULL or not 16-byte aligned", k);
+    p.peer_c[k] = a.wh_peers[k];
+  }
   const int bn = Dp > 128 ? 256 : 128;
   // heads must not straddle an epilogue thread's 128 columns, or be exactly one 256-wide tile
   const bool fuse_logits = (Cp <= 128 && 128 % Cp == 0) || (Cp == 256 && bn == 256);

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 9
+#define B200GAT_ABI_VERSION 10
 
 enum {
   B200GAT_OK = 0,
@@ -78,6 +78,7 @@ typedef struct {
   int64_t max_out_degree;  /* B200GAT_GIANT_DEGREE are cut into segments of that many edges, one CTA per segment */
 } b200gat_graph;
 
+#define B200GAT_MAX_PEERS 7   /* other GPUs of one NVSwitch node */
 #define B200GAT_HUB_DEGREE 512
 #define B200GAT_GIANT_DEGREE 4096
 
@@ -138,6 +139,14 @@ typedef struct {
   int32_t x_activation;                  /* B200GAT_ACT_*: the projection consumes act(x) */
   const uint32_t* x_amax;                /* optional: device word holding the bit pattern of an upper bound of max|x|
                                             (b200gat_edge_fwd's out_amax of the producing layer); saves one pass over x */
+  /* Projection fused with the all-gather of Wh (row-partitioned multi-GPU execution, GAT.py:42-52 on the own row block):
+   * with num_peers > 0 the GEMM's store epilogue ALSO writes every Wh tile into the other GPUs' memory over NVLink
+   * (peer-mapped pointers, e.g. torch symmetric memory), so the exchange overlaps the GEMM tile by tile instead of
+   * following it as a collective.  wh_peers[k] = address, in THIS process, of the place of this rank's row block inside
+   * peer k's full [P * block, Dp] buffer (same leading dimension as wh).  The caller synchronises the GPUs before anyone
+   * reads the gathered buffer.  Tensor-core path only (b200gat_proj_split_bytes() != 0), else B200GAT_E_UNSUPPORTED. */
+  float* wh_peers[B200GAT_MAX_PEERS];
+  int32_t num_peers;
 } b200gat_proj_fwd_args;
 size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of an x_split buffer for this geometry; 0 when the shape runs on the CUDA-core path (pass x_split = NULL) */
