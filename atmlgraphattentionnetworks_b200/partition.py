@@ -301,6 +301,8 @@ class PartitionedGATFunction(torch.autograd.Function):
         x_own = x_own.contiguous()
         w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
         with torch.cuda.device(x_own.device):
+            if peer is not None:          # nobody may still be reading this buffer (an earlier forward's edge kernel) when
+                peer.barrier()            # the first remote tile lands: one more signal-pad barrier, ~10 us
             wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer)
             if peer is not None:          # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
                 peer.barrier()
