@@ -497,6 +497,12 @@ def main():
                         "traffic": dom["dram_traffic_bytes"], "alg_bytes": dom["alg_bytes"]}
         roofline.update({"kernel": f"{dom['op']} layer {dom['layer']} ({dom['geom']})", "ms": dom["ms"],
                          "peak_source": peaks["source"] + " (of measured)"})
+        if args.workload != "large" and roofline["bound"] == "hbm":
+            # SURVEY.md §8d caveat 2: in the cached regime the HBM count is the compulsory traffic; every edge still pulls
+            # its row through L2 -> SM (4.4x the HBM bytes on the PPI-shaped layers), which is what bounds these kernels
+            roofline["regime"] = "cached: gathered rows are L2-resident, the kernel is bound by L2->SM gather traffic (DESIGN.md §5)"
+        elif roofline["bound"] == "hbm":
+            roofline["regime"] = "streaming: every gathered row comes from HBM"
     edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
     edge_bytes = sum(r["alg_bytes"] for r in kernels if r["op"].startswith("b200gat_edge"))
     edge_phase = {"per_rank": partitioned, "ms": edge_ms, "alg_bytes": edge_bytes, "GBps": edge_bytes / edge_ms / 1e6 if edge_ms else None,
