@@ -54,3 +54,29 @@ def test_reference_arm_prints_the_contract_line_without_a_gpu():
         assert key in line, key
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_graph_cache_keys_on_tensor_identity_and_version(monkeypatch):
+    """Host logic of graph.GraphCache (no GPU: the CSR build is stubbed): a hit needs the same tensor object at the same
+    in-place version; a refilled buffer (run_gnn_benchmark.py:60-63 style loaders) replaces its stale entry instead of
+    growing the cache; a new tensor object is a new graph."""
+    import torch
+    from atmlgraphattentionnetworks_b200 import graph
+    built = []
+    monkeypatch.setattr(graph, "build_csr", lambda ei, n, validate=True: built.append((id(ei), ei._version, n)) or object())
+    cache = graph.GraphCache(capacity=3)
+    ei = torch.zeros((2, 5), dtype=torch.int64)
+    a = cache.get(ei, 4)
+    assert cache.get(ei, 4) is a and (cache.hits, cache.misses) == (1, 1)
+    ei.add_(1)                                             # in-place refill bumps the version: rebuild, stale entry dropped
+    b = cache.get(ei, 4)
+    assert b is not a and cache.misses == 2 and len(cache._entries) == 1
+    assert cache.get(ei, 5) is not b and len(cache._entries) == 1      # other node count: also a different graph
+    others = [torch.zeros((2, 3), dtype=torch.int64) for _ in range(4)]
+    for t in others:
+        cache.get(t, 4)
+    assert len(cache._entries) == 3                        # capacity
+    del others, t
+    cache.get(ei, 5)
+    assert all(ref() is not None for ref, *_ in cache._entries)        # dead tensors are purged on access
+    assert len(built) == cache.misses
