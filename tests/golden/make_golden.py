@@ -42,6 +42,17 @@ LAYER_CASES = [
 ]
 
 
+# Degree classes (include/b200gat.h: B200GAT_HUB_DEGREE = 512, B200GAT_GIANT_DEGREE = 4096): graphs with a destination and a
+# source of 600-700 edges ("hub") and of ~5000 edges ("giant").  Written as hubref_*.npz: they pin the ORACLE on these
+# shapes (tests/test_oracle_cpu.py); the CUDA hub / giant schedules are then checked against the oracle on seeded graphs
+# of the same kind (tests/test_gpu_parity.py: the *_hub cases).
+HUBREF_CASES = [
+    ("h4c16_cat", 400, 6000, 12, 16, 4, True, 0.0, "hubs"),
+    ("h4c12_mean_drop", 400, 6000, 12, 12, 4, False, 0.6, "hubs"),
+    ("giant_h2c16_cat", 500, 12000, 8, 16, 2, True, 0.0, "giant"),
+    ("giant_h3c8_mean", 500, 12000, 8, 8, 3, False, 0.0, "giant"),
+]
+
 # run_act_func_experiment.py:13-74,111: the same layer with another logit activation.  name, N, E, F, C, H, concat, p, act
 ACT_CASES = [
     ("logsigmoid_h8c8_cat_drop", 120, 700, 33, 8, 8, True, 0.6, "log_sigmoid"),
@@ -64,6 +75,12 @@ def make_graph(name, n, e, special, gen):
         ei = ei[:, keep]
     if special == "hub":
         ei[1, : e // 2] = 7                              # one destination with ~450 in-edges
+    if special == "hubs":
+        ei[1, :700] = 7                                  # destination with 700 in-edges, source with 600 out-edges
+        ei[0, 700:1300] = 11
+    if special == "giant":
+        ei[1, :5000] = 3                                 # > 4096 in-edges / out-edges: cut into segments by the kernels
+        ei[0, 5000:9500] = 5
     return ei
 
 
@@ -175,6 +192,12 @@ def run_net(ref_net, dataset, f, n, e, graphs, seed, classes=7):
 
 def main():
     ref_gat, ref_net = ref_loader.load()
+    for case in HUBREF_CASES:
+        rec = run_layer(ref_gat, case)
+        np.savez_compressed(os.path.join(HERE, f"hubref_{case[0]}.npz"), **rec)
+        print("hubref", case[0], {k: v.shape for k, v in rec.items() if k in ("x", "edge_index", "out_f32")})
+    if "--only-hubref" in sys.argv:
+        return
     for case in LAYER_CASES:
         rec = run_layer(ref_gat, case)
         np.savez_compressed(os.path.join(HERE, f"layer_{case[0]}.npz"), **rec)

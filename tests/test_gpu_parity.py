@@ -10,8 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from util import (ACT_FILES, ACTIVATIONS, FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, load_packed, nerr,
-                  packed_grads)
+from util import (ACT_FILES, ACTIVATIONS, FP32_TOL, GRAD_KEYS, HUBREF_FILES, LAYER_FILES, NET_FILES, case_id, load,
+                  load_packed, nerr, packed_grads)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -77,7 +77,7 @@ def test_csr_build_rejects_out_of_range_indices():
 
 
 # ------------------------------------------------------------------------- layer fwd + bwd vs the reference fixtures
-@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES, ids=case_id)
+@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES + HUBREF_FILES, ids=case_id)
 def test_layer_matches_reference_fixture(path):
     g = load(path)
     layer = _product_layer(g)

@@ -6,15 +6,27 @@ import torch
 
 from oracle import closed_form, csr_oracle, ref_loader
 from oracle.gat_port import PortGATNet
-from util import (ACT_FILES, FP32_TOL, GRAD_KEYS, LAYER_FILES, NET_FILES, case_id, load, nerr, packed_grads,
+from util import (ACT_FILES, FP32_TOL, GRAD_KEYS, HUBREF_FILES, LAYER_FILES, NET_FILES, case_id, load, nerr, packed_grads,
                   port_layer_from_golden)
 
 
 def test_fixture_inventory():
-    assert len(LAYER_FILES) >= 18 and len(NET_FILES) >= 3 and len(ACT_FILES) >= 5
+    assert len(LAYER_FILES) >= 18 and len(NET_FILES) >= 3 and len(ACT_FILES) >= 5 and len(HUBREF_FILES) >= 4
 
 
-@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES, ids=case_id)
+def test_hub_fixtures_hold_the_degree_classes():
+    """the hubref fixtures really contain rows / columns above B200GAT_HUB_DEGREE and B200GAT_GIANT_DEGREE"""
+    from atmlgraphattentionnetworks_b200._abi import HUB_DEGREE
+    for path in HUBREF_FILES:
+        g = load(path)
+        n = g["x"].shape[0]
+        indeg = np.bincount(g["edge_index"][1], minlength=n) + 1
+        outdeg = np.bincount(g["edge_index"][0], minlength=n) + 1
+        lim = 4096 if "giant" in case_id(path) else HUB_DEGREE
+        assert indeg.max() > lim and outdeg.max() > lim, case_id(path)
+
+
+@pytest.mark.parametrize("path", LAYER_FILES + ACT_FILES + HUBREF_FILES, ids=case_id)
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_port_matches_reference_fixture(path, prec):
     g = load(path)
@@ -36,7 +48,7 @@ def test_port_matches_reference_fixture(path, prec):
         assert nerr(got[k], g[k + "_" + prec]) <= tol, k
 
 
-@pytest.mark.parametrize("path", LAYER_FILES, ids=case_id)
+@pytest.mark.parametrize("path", LAYER_FILES + HUBREF_FILES, ids=case_id)
 def test_closed_form_matches_reference_fixture(path):
     g = load(path)
     out, cache = closed_form.forward(g["x"], g["edge_index"], g["W"], g["bw"], g["a1"], g["b1"], g["a2"], g["b2"],
