@@ -97,6 +97,11 @@ class GATLayerFunction(torch.autograd.Function):
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
         ctx.graph, ctx.geom, ctx.mask, ctx.act, ctx.logit = graph, geom, mask, (bool(act_in), bool(act_out)), logit
+        # the kernels read the packed storage through raw pointers and the per-head Parameters alias it through `.data =`,
+        # which does not share version counters: remember the Parameters' versions so that an in-place update between this
+        # forward and its backward (optimizer.step, load_state_dict, ...) is an error, as it is in the reference
+        ctx.param_versions = tuple(p._version for p in params)
+        ctx.params = params
         ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads,
                               x_split)
         ctx.mark_non_differentiable(out_amax)
@@ -107,6 +112,9 @@ class GATLayerFunction(torch.autograd.Function):
         x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, fwd_out, x_split = ctx.saved_tensors
         graph, (f_in, c, h, concat), mask = ctx.graph, ctx.geom, ctx.mask
         act_in, act_out = ctx.act
+        if tuple(p._version for p in ctx.params) != ctx.param_versions:
+            raise RuntimeError("one of the variables needed for gradient computation has been modified by an inplace "
+                               "operation: a GraphAttentionLayer parameter changed between forward and backward")
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]

@@ -100,14 +100,22 @@ class GraphCache:
         self.hits = 0
         self.misses = 0
 
+    @staticmethod
+    def _version(t):
+        # tensors created under torch.inference_mode() (a common eval loop does batch.to(device) inside it) do not track a
+        # version counter and raise on ._version; they cannot be modified in place outside inference mode either, so
+        # identity alone keys them
+        return None if t.is_inference() else t._version
+
     def get(self, edge_index, num_nodes):
         keep = []
         found = None
+        version = self._version(edge_index)
         for ref, ver, n, g in self._entries:
             t = ref()
             if t is None:
                 continue
-            if t is edge_index and ver == edge_index._version and n == num_nodes:
+            if t is edge_index and ver == version and n == num_nodes:
                 found = g
             keep.append((ref, ver, n, g))
         self._entries = keep
@@ -119,7 +127,7 @@ class GraphCache:
         # so a loader that refills one device buffer per batch recycles the CSR memory instead of growing the cache
         self._entries = [ent for ent in self._entries if ent[0]() is not edge_index]
         g = build_csr(edge_index, num_nodes)
-        self._entries.append((weakref.ref(edge_index), edge_index._version, num_nodes, g))
+        self._entries.append((weakref.ref(edge_index), version, num_nodes, g))
         if len(self._entries) > self.capacity:
             self._entries.pop(0)
         return g

@@ -19,14 +19,12 @@ def shard_graphs(num_graphs, world_size, rank):
 
 
 def row_partition(num_nodes, world_size):
-    """Contiguous, near-equal destination-row blocks: [(begin, end)] per rank."""
-    base, rem = divmod(num_nodes, world_size)
-    out, lo = [], 0
-    for r in range(world_size):
-        hi = lo + base + (1 if r < rem else 0)
-        out.append((lo, hi))
-        lo = hi
-    return out
+    """Contiguous destination-row blocks of the large-graph scheme: [(begin, end)] per rank.  ONE block definition for the
+    whole package: blocks of ceil(N / P) rows (partition.block_size), the last ones shorter or empty — exactly the rows
+    partition.build_row_partition gives rank r and the layout of the all-gathered [P * block, D] buffers."""
+    from .partition import block_size
+    b = block_size(num_nodes, world_size)
+    return [(min(r * b, num_nodes), min((r + 1) * b, num_nodes)) for r in range(world_size)]
 
 
 class GradBucket:

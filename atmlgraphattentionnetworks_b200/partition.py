@@ -298,6 +298,9 @@ class PartitionedGATFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group, peer=None):
+        if x_own.shape[0] != part.n_own:
+            raise ValueError(f"x_own has {x_own.shape[0]} rows, the partition's own block [{part.lo}, {part.hi}) has "
+                             f"{part.n_own} (blocks are ceil(N / P) rows: partition.block_size)")
         x_own = x_own.contiguous()
         w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
         with torch.cuda.device(x_own.device):
@@ -313,7 +316,11 @@ class PartitionedGATFunction(torch.autograd.Function):
             out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask)
         n = part.n_own
         ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
-        ctx.save_for_backward(x_own, w, a1, a2, bias, wh_pad[:n], s_src_pad[:n], s_dst, rowmax, rowsum,
+        # peer mode: wh_pad is a view of the layer's persistent symmetric buffer, which the NEXT forward through this layer
+        # overwrites through raw pointers (no autograd version bump) — an eval forward, a second micro-batch or activation
+        # checkpointing between this forward and its backward would silently corrupt the saved Wh.  Keep a private copy.
+        wh_saved = wh_pad[:n].clone() if peer is not None else wh_pad[:n]
+        ctx.save_for_backward(x_own, w, a1, a2, bias, wh_saved, s_src_pad[:n], s_dst, rowmax, rowsum,
                               out if o_heads is None else o_heads)
         return out
 

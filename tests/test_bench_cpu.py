@@ -80,3 +80,17 @@ def test_graph_cache_keys_on_tensor_identity_and_version(monkeypatch):
     cache.get(ei, 5)
     assert all(ref() is not None for ref, *_ in cache._entries)        # dead tensors are purged on access
     assert len(built) == cache.misses
+
+
+def test_graph_cache_accepts_inference_mode_tensors(monkeypatch):
+    """A tensor created under torch.inference_mode() (an eval loop doing batch.to(device) inside it) has no version
+    counter: the cache keys it on identity alone instead of raising."""
+    import torch
+    from atmlgraphattentionnetworks_b200 import graph
+    monkeypatch.setattr(graph, "build_csr", lambda ei, n, validate=True: object())
+    cache = graph.GraphCache()
+    with torch.inference_mode():
+        ei = torch.zeros((2, 5), dtype=torch.int64)
+        a = cache.get(ei, 4)
+        assert cache.get(ei, 4) is a
+    assert cache.get(ei, 4) is a and (cache.hits, cache.misses) == (2, 1)

@@ -116,8 +116,13 @@ def test_partition_helpers():
     parts = row_partition(2_400_000, 8)
     assert parts[0] == (0, 300_000) and parts[-1][1] == 2_400_000
     parts = row_partition(10, 4)
-    assert parts == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert parts == [(0, 3), (3, 6), (6, 9), (9, 10)]         # ceil blocks: ONE definition with partition.block_size
     assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    import numpy as np
+    from atmlgraphattentionnetworks_b200.partition import build_row_partition
+    ei = torch.from_numpy(np.random.default_rng(0).integers(0, 10, size=(2, 30)))
+    assert [(p.lo, p.hi) for p in (build_row_partition(ei, 10, 4, r) for r in range(4))] == parts
+    assert row_partition(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
 
 
 def test_grad_bucket_views_single_process():
