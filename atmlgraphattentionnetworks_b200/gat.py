@@ -37,6 +37,27 @@ def _call(name, fn, args, stream, tag):
     _abi.timing.append((name, tag, start, end))
 
 
+class _timed:
+    """`with _timed("nccl_all_gather_wh", tag):` — when _abi.timing is a list, bracket a region of the current stream (a
+    collective, a barrier) with CUDA events exactly like an ABI call, so bench.py can name each exchange's exposed time."""
+
+    def __init__(self, name, tag):
+        self.name, self.tag = name, tag
+
+    def __enter__(self):
+        if _abi.timing is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _abi.timing is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _abi.timing.append((self.name, self.tag, self.start, end))
+        return False
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 

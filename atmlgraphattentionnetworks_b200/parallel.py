@@ -66,16 +66,12 @@ class GradBucket:
         return self._slots[id(p)]
 
 
-def all_reduce_packed_grads(params, group=None, weight=None):
-    """Data-parallel gradient exchange without a staging copy: the layer's backward hands every per-head gradient back
-    as a VIEW of its packed output buffers (gat.py), so with `zero_grad(set_to_none=True)` the .grad tensors of a step
-    are views of a handful of base buffers (7 per GAT layer).  Those bases are scaled with one multi-tensor kernel and
-    all-reduced inside one NCCL group (one fused launch) — no flat bucket, no accumulate-into-bucket kernels.
-    Average over ranks by default; `weight` = n_r / N for node-level mean losses.  Returns the number of buffers."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return 0
-    # group the gradients by STORAGE (autograd detaches the views it adopts, so ._base is gone): every storage a .grad
-    # lives in is one of the backward's dedicated packed buffers (or a plain parameter's own gradient) and is reduced whole
+def packed_grad_buffers(params):
+    """The distinct storages the .grad tensors of `params` live in, each as one flat tensor.  The layer's backward hands
+    every per-head gradient back as a VIEW of its packed output buffers (gat.py), so with `zero_grad(set_to_none=True)`
+    the gradients of a step are views of a handful of base buffers (7 per GAT layer) plus the plain parameters' own."""
+    # group by STORAGE (autograd detaches the views it adopts, so ._base is gone): every storage a .grad lives in is one of
+    # the backward's dedicated packed buffers (or a plain parameter's own gradient) and is reduced whole
     bases, seen = [], set()
     for p in params:
         g = p.grad
@@ -86,10 +82,28 @@ def all_reduce_packed_grads(params, group=None, weight=None):
             continue
         seen.add(st.data_ptr())
         bases.append(torch.empty(0, dtype=g.dtype, device=g.device).set_(st))
+    return bases
+
+
+def scale_packed_grads(params, weight):
+    """Multiply every gradient buffer of `params` by `weight` with one multi-tensor kernel (the rank's share of the global
+    mean: 1 / P for equal shards, n_r / N for node-level mean losses).  -> the buffers."""
+    bases = packed_grad_buffers(params)
+    if bases:
+        torch._foreach_mul_(bases, float(weight))
+    return bases
+
+
+def all_reduce_packed_grads(params, group=None, weight=None):
+    """Data-parallel gradient exchange without a staging copy: the packed gradient buffers of the step
+    (packed_grad_buffers) are scaled with one multi-tensor kernel and all-reduced inside one NCCL group (one fused
+    launch) — no flat bucket, no accumulate-into-bucket kernels.  Average over ranks by default; `weight` = n_r / N for
+    node-level mean losses.  Returns the number of buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    bases = scale_packed_grads(params, (1.0 / dist.get_world_size(group)) if weight is None else float(weight))
     if not bases:
         return 0
-    scale = (1.0 / dist.get_world_size(group)) if weight is None else float(weight)
-    torch._foreach_mul_(bases, scale)
     coalesce = None
     if dist.get_backend(group) == "nccl":             # gloo (the CPU tests) has no coalescing: plain loop there
         try:

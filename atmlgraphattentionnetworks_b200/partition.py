@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _abi
-from .gat import _call, _layer_struct, _ptr, _workspace
+from .gat import _call, _layer_struct, _ptr, _timed, _workspace
 
 
 # ------------------------------------------------------------------------------------------------ graph partition
@@ -305,14 +305,18 @@ class PartitionedGATFunction(torch.autograd.Function):
         w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
         with torch.cuda.device(x_own.device):
             if peer is not None:          # nobody may still be reading this buffer (an earlier forward's edge kernel) when
-                peer.barrier()            # the first remote tile lands: one more signal-pad barrier, ~10 us
+                with _timed("peer_barrier", geom):   # the first remote tile lands: one more signal-pad barrier, ~10 us
+                    peer.barrier()
             wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer)
             if peer is not None:          # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
-                peer.barrier()
+                with _timed("peer_barrier", geom):
+                    peer.barrier()
                 wh_full = peer.tensor
             else:
-                wh_full = all_gather_rows(wh_pad, group)
-            s_src_full = all_gather_rows(s_src_pad, group)
+                with _timed("all_gather_wh", geom):
+                    wh_full = all_gather_rows(wh_pad, group)
+            with _timed("all_gather_s_src", geom):
+                s_src_full = all_gather_rows(s_src_pad, group)
             out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask)
         n = part.n_own
         ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
@@ -331,10 +335,13 @@ class PartitionedGATFunction(torch.autograd.Function):
         gout = gout.contiguous()
         with torch.cuda.device(gout.device):
             rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block)
-            g_full = all_gather_rows(g_rows, group)
-            rowrec_full = all_gather_rows(rowrec, group)
+            with _timed("all_gather_g", geom):
+                g_full = all_gather_rows(g_rows, group)
+            with _timed("all_gather_rowrec", geom):
+                rowrec_full = all_gather_rows(rowrec, group)
             g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask)
-            g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
+            with _timed("reduce_scatter_g_s_dst", geom):
+                g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
             g_bw, g_a1, g_a2, g_b1, g_b2 = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh)
             g_x, g_w = stage_proj_bwd(geom, g_wh, x_own, w, ctx.needs_input_grad[0])
         return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None, None

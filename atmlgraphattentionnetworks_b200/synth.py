@@ -69,6 +69,27 @@ def cifar_shaped(seed=0, num_graphs=128, num_features=5, k=8, num_classes=10):
     return SimpleNamespace(x=x, edge_index=edge_index, y=y, batch=batch, num_graphs=num_graphs, name="cifar")
 
 
+def select_graphs(data, graph_ids):
+    """Re-collate the graphs `graph_ids` of a block-diagonal batch (nodes numbered graph-contiguously, edges never cross
+    graphs) into a batch of their own: what a data-parallel rank owns of a global batch (parallel.shard_graphs)."""
+    ids = torch.as_tensor(list(graph_ids), dtype=torch.int64)
+    g_total = int(data.num_graphs)
+    new_id = torch.full((g_total,), -1, dtype=torch.int64)
+    new_id[ids] = torch.arange(ids.numel())
+    node_keep = new_id[data.batch] >= 0
+    order = torch.argsort(new_id[data.batch][node_keep], stable=True)      # nodes grouped by NEW graph id
+    old_nodes = torch.nonzero(node_keep).flatten()[order]
+    remap = torch.full((data.x.shape[0],), -1, dtype=torch.int64)
+    remap[old_nodes] = torch.arange(old_nodes.numel())
+    ei = data.edge_index
+    edge_keep = node_keep[ei[1]]
+    out = SimpleNamespace(x=data.x[old_nodes].contiguous(), edge_index=remap[ei[:, edge_keep]].contiguous(),
+                          batch=new_id[data.batch][old_nodes].contiguous(), num_graphs=int(ids.numel()), name=data.name)
+    y = data.y
+    out.y = (y[ids] if y.shape[0] == g_total and y.shape[0] != data.x.shape[0] else y[old_nodes]).contiguous()
+    return out
+
+
 def powerlaw(seed=0, num_nodes=2_400_000, num_edges=62_000_000, num_features=100, num_classes=47):
     """Both endpoints = perm[floor(N * U^2)] (Zipf-1/2 popularity; in-degree tail exponent ~3)."""
     g = torch.Generator().manual_seed(seed)

@@ -1,25 +1,34 @@
 """bench.py — the reference's headline metric on the B200-native path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ppi|cifar|cora|heads|large]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload all|ppi|large|cifar|cora|heads]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 Metric (BASELINE.json): GAT layer fwd+bwd edges/s — unit of work = one processed edge of E' = E + N (self loops are
 real work) per layer; a "step" is one full train step (zero_grad, forward, loss, backward, gradient all-reduce when
 N > 1, Adam step — run_inductive.py:75-85) of the workload's model over one synthetic batch;
-value = n_gpus * sum_layers E' / t_step.  Default workload = BASELINE.json configs[1]: the PPI-shaped inductive batch
-(24 graphs, 56,944 nodes, 818,716 edges, 50 feats, 121 labels), 3-layer GAT 4/4/6 heads x 256.
+value = sum over ranks and layers of E' / t_step.
 
-One JSON line on stdout (rank 0).  `value` times the step with inputs resident in HBM and the CSR cached (the same
-edge_index object every step, as in run_inductive.py:77); `e2e` times the same step from PINNED HOST buffers: H2D of
-x / edge_index / y, CSR build, train step, D2H of the loss — every step.  `roofline` is the dominant ABI op of the step,
-timed live with CUDA events around each C-ABI call; `kernels` lists every op.  `cpu_baseline` / `--impl reference` time
-the CPU oracle port of the reference (oracle/gat_port.py; the reference itself needs torch_geometric, which is not
-installable here, and /root/reference does not exist on the GPU box) on a bounded sample of the same workload.
+ONE JSON line on stdout (rank 0).  Its top-level keys are the HEADLINE workload = BASELINE.json configs[1]: the PPI-shaped
+inductive batch (24 graphs, 56,944 nodes, 818,716 edges, 50 feats, 121 labels), 3-layer GAT 4/4/6 heads x 256 (`value` =
+inputs resident in HBM, CSR cached; `e2e` = the same step from PINNED HOST buffers: H2D of x / edge_index / y, CSR build,
+train step, D2H of the loss, every step).  With the default `--workload all` the same line also carries one sub-record per
+other BASELINE config, each measured the same way in the same process:
+    "large"  configs[4]  2.4 M-node power-law graph, 3-layer GAT 4 x 128: 1 GPU resident; row-partitioned at N > 1 (strong)
+    "cifar"  configs[2]  CIFAR10-superpixel-shaped batches through GATNet('GAT','CIFAR10',5): 128 and 512 graphs at N = 1;
+                         data parallel strong (128 graphs split over the ranks) and weak (128 per rank) at N > 1
+    "cora"   configs[0]  Cora-shaped graph through GATNet('GAT','Cora',1433), dropout 0.6 active (replicas only: N = 1)
+    "heads"  configs[3]  one 50 -> H x 64 layer on the PPI-shaped batch, H = 1, 2, 4, 8, 16 (replicas only: N = 1)
+`roofline` is the dominant C-ABI op of a workload's step, timed live with CUDA events around each C-ABI call; `kernels` lists
+every op; at N > 1 `check` compares the distributed step-0 loss and gradients with the same global batch run on ONE GPU.
+`cpu_baseline` / `--impl reference` time the reference's own GAT.py / GATNet.py (unmodified, staged by
+oracle/stage_reference.py under oracle/_ref/, running on oracle/pyg_standin; kind "reference") — or the oracle port when
+the staged files are absent (kind "port") — on the host cores.
 """
 import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -34,14 +43,14 @@ from atmlgraphattentionnetworks_b200 import synth  # noqa: E402
 
 METRIC = "gat_layer_fwd_bwd_edges_per_s"
 UNIT = "edges/s"
+ALL_WORKLOADS = ("ppi", "large", "cifar", "cora", "heads")
+HEAD_POINTS = (1, 2, 4, 8, 16)          # BASELINE configs[3]
+L2_BYTES = 126 << 20
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-HEADS = 8   # --heads: the point of the heads sweep (BASELINE configs[3]: 1, 2, 4, 8, 16 heads x 64)
-
-
-def make_workload(name, seed, sample=None):
-    """-> (data, spec, loss_fn, description).  `sample` bounds the CPU baseline (fraction of the batch)."""
+def make_workload(name, seed, sample=None, heads=8, num_graphs=128):
+    """-> (data, spec, loss_fn, description).  `sample` bounds the CPU legs (a part of the batch / a scaled graph)."""
     import torch.nn.functional as F
     if name == "ppi":
         data = synth.ppi_shaped(seed=seed, keep_graphs=sample)
@@ -49,22 +58,24 @@ def make_workload(name, seed, sample=None):
         loss_fn = lambda out, y: F.binary_cross_entropy_with_logits(out, y)   # noqa: E731
         desc = "PPI-shaped inductive batch (24 graphs, 56944 nodes, 818716 edges, 50 feats, 121 labels), 3-layer GAT 4/4/6 heads x 256/256/121"
     elif name == "large":
-        data = synth.powerlaw(seed=seed) if sample is None else synth.powerlaw(seed=seed, num_nodes=75_000, num_edges=1_937_500)
+        data = synth.powerlaw(seed=seed) if sample is None else synth.powerlaw(seed=seed, num_nodes=2_400_000 // sample,
+                                                                               num_edges=62_000_000 // sample)
         spec = synth.LARGE_STACK
         loss_fn = lambda out, y: F.nll_loss(F.log_softmax(out, dim=1), y)     # noqa: E731
         desc = "large power-law graph (2.4M nodes, 62M edges, 100 feats, 47 classes), 3-layer GAT 4 heads x 128"
     elif name == "heads":
         data = synth.ppi_shaped(seed=seed, keep_graphs=sample)
-        spec = [(50, 64, HEADS, True)]
+        spec = [(50, 64, heads, True)]
         loss_fn = lambda out, y: out.sum()                                     # noqa: E731
-        desc = f"heads sweep point: one layer 50 -> {HEADS} heads x 64 on the PPI-shaped batch"
+        desc = f"heads sweep point: one layer 50 -> {heads} heads x 64 on the PPI-shaped batch"
     elif name == "cifar":
         # BASELINE configs[2]: run_gnn_benchmark.py:35-66 — GATNet('GAT','CIFAR10',F): conv1 -> elu -> conv2 -> elu ->
         # per-graph mean -> lin1 -> relu -> lin2 -> log_softmax, nll_loss per graph; dropout 0.0 (GATNet.py:19-20)
-        data = synth.cifar_shaped(seed=seed, num_graphs=128 if sample is None else 16)
+        data = synth.cifar_shaped(seed=seed, num_graphs=num_graphs if sample is None else sample)
         spec = [(5, 8, 8, True), (64, 8, 8, True)]
         loss_fn = lambda out, y: F.nll_loss(out, y)                            # noqa: E731
-        desc = "CIFAR10-superpixel-shaped batch (128 graphs x ~117 nodes, kNN k=8, 5 feats, 10 classes), GATNet('GAT','CIFAR10',5)"
+        desc = (f"CIFAR10-superpixel-shaped batch ({num_graphs} graphs x ~117 nodes, kNN k=8, 5 feats, 10 classes), "
+                "GATNet('GAT','CIFAR10',5)")
     elif name == "cora":
         # BASELINE configs[0]: run_inductive.py:75-85 — GATNet('GAT','Cora',1433) in training mode (feature dropout 0.6 and
         # attention dropout 0.6 are active, as in the reference's train step), nll_loss over all nodes
@@ -79,6 +90,26 @@ def make_workload(name, seed, sample=None):
 
 def layer_edges(data):
     return int(data.edge_index.shape[1] + data.x.shape[0])
+
+
+def working_set_bytes(spec, n, ep, cached):
+    return sum(algorithmic_bytes(op, n, ep, f, c, h, concat, li > 0, cached)[0]
+               for li, (f, c, h, concat) in enumerate(spec)
+               for op in ("b200gat_proj_fwd", "b200gat_edge_fwd", "b200gat_edge_bwd", "b200gat_proj_bwd"))
+
+
+def describe_config(name, desc, data, spec, world, mode):
+    """The `config` object of a line: the WORKLOAD only, so the b200 arm and the reference arm print the same dict."""
+    n, ep = int(data.x.shape[0]), layer_edges(data)
+    ws = working_set_bytes(spec, n, ep, cached=name != "large")
+    flush = ws < 2 * L2_BYTES
+    return {"workload": desc, "nodes": n, "input_edges": int(data.edge_index.shape[1]),
+            "edges_per_layer_incl_self_loops": ep, "layers": len(spec),
+            "step": "zero_grad + fwd + loss + bwd + grad all-reduce (N > 1) + fused Adam (lr 5e-3, wd 5e-4)",
+            "parallelism": mode if world > 1 else "single GPU",
+            "l2": (f"per-step working set {ws / 1e6:.0f} MB < 2 x L2 (126 MB): L2 flushed (256 MB memset) before every timed step, "
+                   "steps timed one by one with CUDA events" if flush else
+                   f"inputs larger than L2 (per-step working set {ws / 1e9:.2f} GB vs 126 MB L2); no explicit flush")}, flush
 
 
 # ------------------------------------------------------------------------------------ algorithmic bytes (SURVEY §8d)
@@ -117,6 +148,13 @@ def measured_peaks():
         return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), bf16_sustained=float(p["bf16_tflops_sustained"]),
                     source="MEASURED_PEAKS.json")
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def git_sha():
+    try:
+        return subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip() or None
+    except Exception:   # pragma: no cover
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -172,21 +210,36 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
-def cpu_reference_leg(workload, steps, warmup, sample):
-    """The reference's CPU PyTorch path (oracle port of GAT.py, same op sequence, autograd backward) on all host
-    cores, on a bounded sample of the workload.  -> (edges/s, seconds per step, description)."""
-    from oracle.gat_port import PortGATNet, PortStack
+# ------------------------------------------------------------------------------------------------ CPU legs
+CPU_SAMPLES = {"ppi": 2, "heads": 2, "cifar": 16, "cora": None, "large": 128}   # graphs kept / scale divisor
+
+
+def cpu_reference_leg(workload, steps, warmup, sample, heads=8):
+    """The reference's CPU PyTorch path on all host cores: its own GAT.py / GATNet.py (oracle/_ref or /root/reference, on
+    oracle/pyg_standin) when present, else the oracle port (same op sequence, autograd backward).
+    -> (edges/s, seconds per step, sample description, kind)."""
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
-    data, spec, loss_fn, _ = make_workload(workload, 0, sample=sample)
+    data, spec, loss_fn, _ = make_workload(workload, 0, sample=sample, heads=heads)
+    kind = "reference" if ref_loader.available() else "port"
     torch.manual_seed(0)
     if workload in ("cifar", "cora"):
-        net = PortGATNet("GAT", "CIFAR10" if workload == "cifar" else "Cora", data.x.shape[1]).train()
+        ds = "CIFAR10" if workload == "cifar" else "Cora"
+        if kind == "reference":
+            net = ref_loader.load()[1].GATNet("GAT", ds, data.x.shape[1]).train()
+        else:
+            from oracle.gat_port import PortGATNet
+            net = PortGATNet("GAT", ds, data.x.shape[1]).train()
         model = lambda x, ei: net(data)                                        # noqa: E731
-        opt = torch.optim.Adam(net.parameters(), lr=5e-3, weight_decay=5e-4)
+        params = list(net.parameters())
     else:
-        model = PortStack(spec, dropout=0.0)
-        opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4)
+        if kind == "reference":
+            stack = ref_loader.RefStack(spec, dropout=0.0)
+        else:
+            from oracle.gat_port import PortStack
+            stack = PortStack(spec, dropout=0.0)
+        model, params = stack, list(stack.parameters())
+    opt = torch.optim.Adam(params, lr=5e-3, weight_decay=5e-4)
     ep = layer_edges(data)
 
     def step():
@@ -194,29 +247,500 @@ def cpu_reference_leg(workload, steps, warmup, sample):
         loss = loss_fn(model(data.x, data.edge_index), data.y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    what = (f"{data.num_graphs} of 24 graphs of the PPI-shaped batch" if workload in ("ppi", "heads") else
-            f"{data.num_graphs} of 128 graphs of the CIFAR-shaped batch" if workload == "cifar" else
-            "the whole Cora-shaped graph" if workload == "cora" else
-            "1/32-scale graph from the same power-law generator")
-    desc = f"{what}: {data.x.shape[0]} nodes, {ep} edges incl. self loops, {len(spec)} layers, {steps} steps after {warmup} warm-up"
-    return len(spec) * ep / dt, dt, desc
+    if workload in ("ppi", "heads"):
+        what = "the whole PPI-shaped batch (24 graphs)" if sample is None else f"{data.num_graphs} of 24 graphs of the PPI-shaped batch"
+    elif workload == "cifar":
+        what = f"{data.num_graphs} graphs of the CIFAR-shaped batch"
+    elif workload == "cora":
+        what = "the whole Cora-shaped graph"
+    else:
+        what = "the whole 2.4M-node graph" if sample is None else f"1/{sample}-scale graph from the same power-law generator"
+    impl = ("the reference's own GAT.py / GATNet.py (unmodified) on oracle/pyg_standin" if kind == "reference" else
+            "oracle/gat_port.py (port of GAT.py: same op sequence, autograd backward)")
+    desc = (f"{what}: {data.x.shape[0]} nodes, {ep} edges incl. self loops, {len(spec)} layers, {steps} steps after "
+            f"{warmup} warm-up; {impl}")
+    return len(spec) * ep / dt, dt, desc, kind
 
 
-# ------------------------------------------------------------------------------------------------ main
+def cpu_baseline_record(workload, heads=8):
+    sample = CPU_SAMPLES[workload]
+    steps, warm = (2, 1) if workload == "large" else (3, 1)
+    val, dt, desc, kind = cpu_reference_leg(workload, steps, warm, sample, heads=heads)
+    return {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc, "s_per_step": dt}
+
+
+# ------------------------------------------------------------------------------------------------ output
+_REAL_STDOUT = 1
+
+
 def _emit(line):
     """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 while the bench runs (NCCL prints
     its version banner there) is diverted to stderr so that the line stays machine-readable."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-_REAL_STDOUT = 1
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ one GPU workload
+class Env:
+    def __init__(self, rank, local_rank, world, dev):
+        self.rank, self.local_rank, self.world, self.dev = rank, local_rank, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = torch.tensor([float(v)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class Runner:
+    """One workload on this rank's GPU: model, optimizer, host / device buffers and the train step."""
+
+    def __init__(self, name, env, *, heads=8, num_graphs=128, dp="weak", capturable=False):
+        from types import SimpleNamespace
+        from atmlgraphattentionnetworks_b200.gatnet import GATNet, GATStack
+        from atmlgraphattentionnetworks_b200.parallel import GradBucket, shard_graphs
+        self.name, self.env, self.heads = name, env, heads
+        world, rank, dev = env.world, env.rank, env.dev
+        self.partitioned = name == "large" and world > 1
+        self.dp = dp if (world > 1 and not self.partitioned) else None
+        # graph batches, weak: every rank owns its own batch of independent graphs (seed = rank), model replicated;
+        # strong: the seed-0 global batch is split by graph (parallel.shard_graphs);
+        # one large graph (N > 1): strong scaling — destination-row partition, Wh all-gather per layer.
+        seed = rank if self.dp == "weak" else 0
+        data, spec, loss_fn, desc = make_workload(name, seed=seed, heads=heads, num_graphs=num_graphs)
+        self.global_data = data
+        mode = (f"row{world} (destination-row partition, all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
+                if self.partitioned else
+                f"dp{world} {self.dp} (independent graphs per rank, one-group NCCL all-reduce of the packed gradient buffers)")
+        self.config, self.flush = describe_config(name, desc, data, spec, world, mode)
+        if self.dp == "strong":
+            data = synth.select_graphs(data, shard_graphs(data.num_graphs, world, rank))
+        self.data, self.spec, self.loss_fn = data, spec, loss_fn
+        self.n, self.ep = data.x.shape[0], layer_edges(data)
+        torch.manual_seed(0)
+        self.is_net = name in ("cifar", "cora")
+        if self.is_net:
+            self.net = GATNet("GAT", "CIFAR10" if name == "cifar" else "Cora", data.x.shape[1]).to(dev).train()
+            batch_d = data.batch.to(dev) if hasattr(data, "batch") else None
+            self.model = lambda x, ei: self.net(SimpleNamespace(x=x, edge_index=ei, batch=batch_d, num_graphs=data.num_graphs))
+            self.module = self.net
+        else:
+            self.module = GATStack(spec, dropout=0.0).to(dev)
+            self.model = self.module
+        self.params = list(self.module.parameters())
+        # gradients are set to None every step and autograd adopts the kernels' packed output buffers as .grad without a
+        # copy; N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (all_reduce_packed_grads).
+        # The row-partitioned large graph keeps the flat bucket (its stage functions build gradients through torch ops).
+        self.bucket = GradBucket(self.params) if self.partitioned else None
+        self.opt = torch.optim.Adam(self.params, lr=5e-3, weight_decay=5e-4, fused=True,   # run_inductive.py:18-19,65
+                                    capturable=capturable)
+        self.part = None
+        if self.partitioned:
+            from atmlgraphattentionnetworks_b200.partition import PartitionedGATStack, build_row_partition
+            self.part = build_row_partition(data.edge_index.to(dev), self.n, world, rank)
+            self.pmodel = PartitionedGATStack(self.module)
+            self.x_h = data.x[self.part.lo:self.part.hi].contiguous().pin_memory()
+            self.y_h = data.y[self.part.lo:self.part.hi].contiguous().pin_memory()
+            self.ei_h = torch.zeros((2, 0), dtype=torch.int64).pin_memory()    # the partitioned graph is static and resident
+            torch.cuda.empty_cache()
+        else:
+            self.x_h, self.ei_h, self.y_h = data.x.pin_memory(), data.edge_index.pin_memory(), data.y.pin_memory()
+        self.x_d, self.ei_d, self.y_d = self.x_h.to(dev), self.ei_h.to(dev), self.y_h.to(dev)
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if self.flush else None
+
+    # -------------------------------------------------------------------------------------------- the step
+    def forward_backward(self, x, ei, y):
+        """zero_grad + forward + loss + backward + gradient exchange; -> loss (this rank's share in partitioned mode)"""
+        from atmlgraphattentionnetworks_b200.parallel import all_reduce_packed_grads
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+        if self.partitioned:
+            out = self.pmodel(x, self.part)
+            # global mean loss = sum over ranks of (own sum / N); parameter gradients are then SUMMED over ranks
+            loss = torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(out, dim=1), y, reduction="sum") / self.n
+            loss.backward()
+            self.bucket.all_reduce_mean(weight=1.0)
+        else:
+            loss = self.loss_fn(self.model(x, ei), y)
+            loss.backward()
+            if self.env.world > 1:
+                all_reduce_packed_grads(self.params)
+        return loss
+
+    def train_step(self, x, ei, y):
+        loss = self.forward_backward(x, ei, y)
+        self.opt.step()
+        return loss
+
+    def resident_step(self):
+        return self.train_step(self.x_d, self.ei_d, self.y_d)
+
+    def total_edges(self):
+        """edges all ranks process per step (sum over layers)"""
+        per_rank = len(self.spec) * self.ep
+        if self.partitioned:
+            return per_rank
+        if self.dp == "strong":
+            return len(self.spec) * layer_edges(self.global_data)
+        return per_rank * self.env.world
+
+    # -------------------------------------------------------------------------------------------- timing
+    def timed(self, fn, steps):
+        """ms per step, max over ranks.  Back to back between one event pair — or, for workloads whose working set fits
+        L2, step by step with an L2 flush before each (outside the event pair)."""
+        env = self.env
+        env.barrier()
+        if self.flush_buf is None:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                fn()
+            e.record()
+            env.barrier()
+            return env.max_over_ranks(s.elapsed_time(e)) / steps
+        pairs = []
+        for _ in range(steps):
+            self.flush_buf.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            pairs.append((s, e))
+        env.barrier()
+        return env.max_over_ranks(sum(s.elapsed_time(e) for s, e in pairs)) / steps
+
+    # -------------------------------------------------------------------------------------------- N > 1 correctness
+    def check(self):
+        """Step-0 loss and gradients of the distributed run against the SAME global batch on one GPU (rank 0 runs every
+        rank's share sequentially through the single-GPU path, seed-fixed weights, before any optimizer step)."""
+        import torch.distributed as dist
+        env = self.env
+        world, dev = env.world, env.dev
+        loss = self.forward_backward(self.x_d, self.ei_d, self.y_d).detach().clone()
+        if self.partitioned:
+            dist.all_reduce(loss)                         # sum of the ranks' shares of the global mean
+            got = self.bucket.flat.clone()
+        else:
+            loss = loss / world
+            dist.all_reduce(loss)                         # mean of the ranks' (equal-size shard) mean losses
+            got = torch.cat([p.grad.flatten() for p in self.params])
+        rec = None
+        if env.rank == 0:
+            from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
+            from atmlgraphattentionnetworks_b200.parallel import shard_graphs
+            for p in self.params:
+                p.grad = None
+            want_loss, want = 0.0, None
+            if self.partitioned:
+                d = self.global_data
+                x, ei, y = d.x.to(dev), d.edge_index.to(dev), d.y.to(dev)
+                l1 = self.loss_fn(self.module(x, ei), y)
+                l1.backward()
+                want_loss = float(l1.detach())
+                want = torch.cat([p.grad.flatten() for p in self.params]).clone()
+                del x, ei, y, l1
+            else:
+                for r in range(world):
+                    if self.dp == "weak":
+                        d, _, _, _ = make_workload(self.name, seed=r, heads=self.heads, num_graphs=self.global_data.num_graphs)
+                    else:
+                        d = synth.select_graphs(self.global_data, shard_graphs(self.global_data.num_graphs, world, r))
+                    x, ei, y = d.x.to(dev), d.edge_index.to(dev), d.y.to(dev)
+                    if self.is_net:
+                        from types import SimpleNamespace
+                        out = self.net(SimpleNamespace(x=x, edge_index=ei, batch=d.batch.to(dev), num_graphs=d.num_graphs))
+                    else:
+                        out = self.module(x, ei)
+                    l1 = self.loss_fn(out, y) / world
+                    l1.backward()                          # gradients accumulate over the shards
+                    want_loss += float(l1.detach())
+                want = torch.cat([p.grad.flatten() for p in self.params]).clone()
+            for p in self.params:
+                p.grad = None
+            if self.bucket is not None:                    # re-attach the flat bucket's views
+                for p in self.bucket.params:
+                    p.grad = self.bucket._slot(p)
+            GLOBAL_CACHE.clear()
+            torch.cuda.empty_cache()
+            loss_rel = abs(float(loss) - want_loss) / max(abs(want_loss), 1e-30)
+            grad_rel = float((got - want).abs().max() / want.abs().max().clamp(min=1e-30))
+            rec = {"ok": bool(loss_rel <= 1e-5 and grad_rel <= 2e-5), "loss_distributed": float(loss), "loss_one_gpu": want_loss,
+                   "loss_rel_err": loss_rel, "grad_max_rel_err": grad_rel, "tolerance": {"loss_rel": 1e-5, "grad_max_rel": 2e-5},
+                   "what": ("step-0 loss and all parameter gradients after the exchange vs the same global batch on rank 0's GPU alone "
+                            "(single-GPU path, same seed-fixed weights)")}
+        env.barrier()
+        return rec
+
+    # -------------------------------------------------------------------------------------------- e2e
+    def time_e2e(self, steps, reps=3):
+        """pinned host buffers in, loss out, every step (new tensors => CSR rebuilt every step).  The host->device copy of
+        step k+1 is issued on a copy stream while step k computes (what a data loader with a prefetch depth of one does):
+        every step still copies its own inputs from pinned host memory inside the timed region, builds its CSR from the
+        fresh edge_index, and reads its loss back."""
+        from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
+        copy_stream = torch.cuda.Stream()
+        # two static sets of device buffers (no per-step allocation on the copy stream: cross-stream frees make the caching
+        # allocator synchronise); the in-place copy bumps edge_index's version counter, so the graph cache misses and the
+        # CSR is rebuilt for every batch
+        slots = [(torch.empty_like(self.x_d), torch.empty_like(self.ei_d), torch.empty_like(self.y_d)) for _ in range(2)]
+        consumed = [None, None]          # event: the step that read slot k has finished
+        loss_h = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+        def upload(k):
+            """batch k: pinned host -> device slot k % 2, then graph ingestion (GAT.py:38 + the CSR / CSC / degree-class
+            build: b200gat_csr_build, b200gat_hub_rows, one status read) — on the copy stream, while step k - 1 computes."""
+            x, ei, y = slots[k % 2]
+            with torch.cuda.stream(copy_stream):
+                if consumed[k % 2] is not None:
+                    copy_stream.wait_event(consumed[k % 2])
+                x.copy_(self.x_h, non_blocking=True)
+                ei.copy_(self.ei_h, non_blocking=True)
+                y.copy_(self.y_h, non_blocking=True)
+                if not self.partitioned:
+                    GLOBAL_CACHE.get(ei, self.n)       # the layers of step k find this batch's CSR in the cache
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return (x, ei, y), done
+
+        def e2e_run(nsteps):
+            nxt = upload(0)
+            pending = None                       # (event, pinned scalar) of the previous step's loss
+            losses = []
+            for k in range(nsteps):
+                (x, ei, y), done = nxt
+                torch.cuda.current_stream().wait_event(done)
+                loss = self.train_step(x, ei, y)
+                loss_h[k % 2].copy_(loss.detach(), non_blocking=True)      # device -> pinned host, read one step later
+                ev = torch.cuda.Event()
+                ev.record()
+                consumed[k % 2] = ev
+                if k + 1 < nsteps:
+                    nxt = upload(k + 1)          # overlaps step k on the GPU (the host blocks on the ingestion status read)
+                if pending is not None:
+                    pending[0].synchronize()
+                    losses.append(float(pending[1]))
+                pending = (ev, loss_h[k % 2])
+            pending[0].synchronize()
+            losses.append(float(pending[1]))
+            assert len(losses) == nsteps and all(v == v for v in losses)
+        e2e_run(3)                           # warm-up: also fills the copy stream's allocator pool (CSR arrays, sort workspace)
+        flush, self.flush_buf = self.flush_buf, None     # e2e streams fresh inputs from the host every step: no flush needed
+        try:
+            ms = statistics.median(self.timed(lambda: e2e_run(steps), 1) / steps for _ in range(reps))
+        finally:
+            self.flush_buf = flush
+        h2d = self.x_h.numel() * 4 + self.ei_h.numel() * 8 + self.y_h.numel() * self.y_h.element_size()
+        del slots
+        return ms, h2d
+
+    # -------------------------------------------------------------------------------------------- per-op breakdown
+    def per_op(self, reps, traffic_name):
+        from atmlgraphattentionnetworks_b200 import _abi
+        from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
+        GLOBAL_CACHE.clear()
+        self.resident_step()
+        _abi.timing = []
+        for _ in range(reps):
+            self.resident_step()
+        torch.cuda.synchronize()
+        per_raw = {}
+        for name, geom, s, e in _abi.timing:
+            per_raw.setdefault((name, geom), []).append(s.elapsed_time(e))
+        _abi.timing = None
+        per, coll = {}, {}
+        for (name, geom), ts in per_raw.items():
+            if not name.startswith("b200gat_"):          # collectives / barriers of the partitioned path
+                per_step = sum(ts) / reps
+                coll[name] = coll.get(name, 0.0) + per_step
+                continue
+            # staged backward (partitioned mode): prep + csc + finish = edge_bwd
+            key = ("b200gat_edge_bwd" if name.startswith("b200gat_edge_bwd") else name, geom)
+            per[key] = [a + b for a, b in zip(per[key], ts)] if key in per else list(ts)
+        n_loc = self.part.n_own if self.partitioned else self.n
+        ep_loc = int(self.part.col.numel() + self.part.crow.numel()) // 2 if self.partitioned else self.ep
+        peaks = measured_peaks()
+        cached = self.name != "large"
+        kernels = []
+        for li, (f, c, h, concat) in enumerate(self.spec):
+            for op in ("b200gat_proj_fwd", "b200gat_edge_fwd", "b200gat_edge_bwd", "b200gat_proj_bwd"):
+                ts = per.get((op, (f, c, h, bool(concat))), [])
+                if not ts:
+                    continue
+                if len(ts) > reps:      # two layers of one geometry (CIFAR conv... never equal today) — split evenly
+                    ts = ts[:reps]
+                ms = statistics.median(ts)
+                need_gx = li > 0
+                nbytes, bound = algorithmic_bytes(op, n_loc, ep_loc, f, c, h, concat, need_gx, cached=cached)
+                rec = {"op": op, "layer": li, "geom": f"{f}->{h}x{c}{'cat' if concat else 'mean'}", "ms": ms,
+                       "alg_bytes": nbytes, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / peaks["hbm"]}
+                fl = gemm_flops(op, n_loc, f, c, h, need_gx)
+                if fl:
+                    rec["TFLOPs"] = fl / ms / 1e9
+                kernels.append(rec)
+        dom = max(kernels, key=lambda r: r["ms"]) if kernels else None
+        # measured DRAM traffic of each op: one committed `ncu --set full` capture of this workload (tools/ncu_traffic.py),
+        # stamped with the git SHA of the kernels it was taken from
+        traffic, traffic_src = {}, None
+        tpath = os.path.join(ROOT, "profiles", f"traffic_{traffic_name}.json")
+        if os.path.isfile(tpath) and not self.partitioned:
+            tj = json.load(open(tpath))
+            traffic = tj.get("ops", {})
+            traffic_src = {"file": f"profiles/traffic_{traffic_name}.json", "capture": tj.get("source"), "git_sha": tj.get("git_sha")}
+        for rec in kernels:
+            t = traffic.get(f"{rec['op']}:{rec['layer']}")
+            rec["dram_traffic_bytes"] = t["dram_bytes"] if t else None
+        roofline = None
+        if dom is not None:
+            if dom["op"].startswith("b200gat_edge"):
+                roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": dom["GBps"] / peaks["hbm"], "traffic": dom["dram_traffic_bytes"],
+                            "alg_bytes": dom["alg_bytes"]}
+            else:
+                roofline = {"bound": "tensor", "achieved": dom.get("TFLOPs", 0.0), "peak": peaks["bf16_sustained"],
+                            "unit": "TFLOP/s", "frac": dom.get("TFLOPs", 0.0) / peaks["bf16_sustained"],
+                            "traffic": dom["dram_traffic_bytes"], "alg_bytes": dom["alg_bytes"],
+                            "note": "3 fp16 MMA passes per fp32-accurate product: frac is bounded by 0.33 (DESIGN.md §4.3)"}
+            roofline.update({"kernel": f"{dom['op']} layer {dom['layer']} ({dom['geom']})", "ms": dom["ms"],
+                             "peak_source": peaks["source"] + " (of measured)", "traffic_source": traffic_src})
+            if cached and roofline["bound"] == "hbm":
+                # SURVEY.md §8d caveat 2: in the cached regime the HBM count is the compulsory traffic; every edge still
+                # pulls its row through L2 -> SM (4.4x the HBM bytes on the PPI-shaped layers), which bounds these kernels
+                roofline["regime"] = "cached: gathered rows are L2-resident, the kernel is bound by L2->SM gather traffic (DESIGN.md §5)"
+            elif roofline["bound"] == "hbm":
+                roofline["regime"] = "streaming: every gathered row comes from HBM"
+        edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
+        edge_bytes = sum(r["alg_bytes"] for r in kernels if r["op"].startswith("b200gat_edge"))
+        edge_phase = {"per_rank": self.partitioned, "ms": edge_ms, "alg_bytes": edge_bytes,
+                      "GBps": edge_bytes / edge_ms / 1e6 if edge_ms else None,
+                      "frac_of_measured_hbm": edge_bytes / edge_ms / 1e6 / peaks["hbm"] if edge_ms else None,
+                      "frac_of_nominal_8TBps": edge_bytes / edge_ms / 1e6 / 8000.0 if edge_ms else None,
+                      "edges_per_s": len(self.spec) * ep_loc / (edge_ms / 1e3) if edge_ms else None}
+        return kernels, roofline, edge_phase, (coll or None)
+
+    def close(self):
+        from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
+        GLOBAL_CACHE.clear()
+        for k in list(self.__dict__):
+            if k not in ("name", "env"):
+                delattr(self, k)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp="weak", e2e=True, cpu=True, breakdown=True,
+                 cuda_graph=False, traffic_name=None):
+    """-> the record of one workload (all ranks take part; only rank 0's record is complete)."""
+    from atmlgraphattentionnetworks_b200 import _abi
+    t_wall = time.perf_counter()
+    run = Runner(name, env, heads=heads, num_graphs=num_graphs, dp=dp, capturable=cuda_graph)
+    rec = {"config": run.config, "n_gpus": env.world, "steps": steps, "warmup": warmup,
+           "scaling": "strong" if (run.partitioned or run.dp == "strong") else "weak"}
+    if env.world > 1:
+        rec["check"] = run.check()
+    for _ in range(warmup):
+        run.resident_step()
+    resident = run.resident_step
+    launches_per_replay = None
+    if cuda_graph:
+        # whole-step capture (SURVEY.md §8f row 3): zero_grad + forward + loss + backward + fused Adam of the resident
+        # batch become ONE graph launch; the CSR is cached (no host sync inside), every buffer comes from the graph's pool
+        assert env.world == 1, "--cuda-graph is a single-GPU mode"
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                run.resident_step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        run.opt.zero_grad(set_to_none=True)
+        l0 = _abi.launch_count()
+        with torch.cuda.graph(graph):
+            run.resident_step()
+        launches_per_replay = _abi.launch_count() - l0
+        resident = graph.replay
+        for _ in range(3):
+            resident()
+    launches0 = _abi.launch_count()
+    with ClockSampler(env.local_rank) as clocks:
+        ms_step = run.timed(resident, steps)
+    launches = _abi.launch_count() - launches0
+    if launches_per_replay is not None:
+        launches = launches_per_replay * steps
+    rec.update({"ms_per_step": ms_step, "value": run.total_edges() / (ms_step / 1e3), "unit": UNIT, "gpu_launches": launches,
+                "cuda_graph": bool(cuda_graph), "clocks": clocks.summary()})
+    if args.profile:
+        run.close()
+        return rec
+    if e2e:
+        e2e_steps = max(steps // 2, 3)
+        ms_e2e, h2d = run.time_e2e(e2e_steps)
+        rec["e2e"] = {"value": run.total_edges() / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                      "includes": ("every step: H2D of its batch from pinned host and graph ingestion (CSR/CSC build, 2 radix sorts, "
+                                   "degree classes) on a copy stream one batch ahead, train step, loss D2H into pinned memory read "
+                                   "one step behind" if not run.partitioned else
+                                   "every step: H2D of the own rows of x / y from pinned host, train step, loss D2H (the partitioned "
+                                   "graph is static and resident)")}
+    if breakdown:
+        kernels, roofline, edge_phase, coll = run.per_op(5, traffic_name or name)
+        rec.update({"roofline": roofline, "edge_phase": edge_phase, "kernels": kernels})
+        if coll is not None:
+            rec["collectives_ms_per_step"] = coll
+            rec["collectives_note"] = ("CUDA events around each collective on the compute stream (serialised with the kernels: "
+                                       "the time is fully exposed)")
+        ksum = sum(r["ms"] for r in kernels)
+        rec["abi_ops_ms_sum"] = ksum
+        rec["step_over_abi_ops"] = ms_step / ksum if ksum else None
+    spec_n = (len(run.spec), run.ep)
+    run.close()
+    if cpu and env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
+        rec["cpu_baseline"] = cpu_baseline_record(name, heads=heads)
+    rec["wall_s"] = time.perf_counter() - t_wall
+    log(f"{name}{'' if name != 'heads' else heads}: {ms_step:.3f} ms/step, {rec['value'] / 1e6:.1f} M edges/s "
+        f"({spec_n[0]} layers x {spec_n[1]} edges), wall {rec['wall_s']:.1f} s")
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------ main
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the b200 arm's config (rank 0 only)."""
+    name = "ppi" if args.workload == "all" else args.workload
+    sample = None if name in ("ppi", "cifar", "cora", "heads") else CPU_SAMPLES[name]   # the large graph cannot run at full size
+    if args.cpu_sample_graphs and name in ("ppi", "heads"):
+        sample = args.cpu_sample_graphs
+    data, spec, _, desc = make_workload(name, 0, heads=args.heads)
+    world = max(args.gpus, 1)
+    mode = f"dp{world} weak (independent graphs per rank, one-group NCCL all-reduce of the packed gradient buffers)"
+    config, _ = describe_config(name, desc, data, spec, world, mode)
+    del data
+    val, dt, sdesc, kind = cpu_reference_leg(name, args.steps, args.warmup, sample, heads=args.heads)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sdesc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    _emit(line)
 
 
 def main():
@@ -229,314 +753,96 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ppi", choices=["ppi", "heads", "large", "cifar", "cora"])
-    ap.add_argument("--heads", type=int, default=8, help="--workload heads: number of heads (x 64 channels)")
+    ap.add_argument("--workload", default="all", choices=["all"] + list(ALL_WORKLOADS))
+    ap.add_argument("--heads", type=int, default=8, help="--workload heads: number of heads (x 64 channels); 0 = the whole sweep")
+    ap.add_argument("--graphs", type=int, default=128, help="--workload cifar: graphs per batch")
+    ap.add_argument("--dp", default="weak", choices=["weak", "strong"], help="--workload cifar at N > 1")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the resident train step in a CUDA graph and time replays (launch-bound workloads)")
-    ap.add_argument("--cpu-sample-graphs", type=int, default=2)
+    ap.add_argument("--cpu-sample-graphs", type=int, default=0,
+                    help="--impl reference on ppi / heads: keep only this many of the 24 graphs (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu runs): warm-up + steps, minimal JSON")
     args = ap.parse_args()
-    global HEADS
-    HEADS = args.heads
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        sample = max(args.cpu_sample_graphs, 4) if args.workload != "large" else 1
-        val, dt, desc = cpu_reference_leg(args.workload, args.steps, max(args.warmup, 1), sample)
-        _, _, _, wdesc = make_workload(args.workload, 0, sample=sample)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wdesc, "cpu_sample": desc},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": desc},
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        _emit(line)
+        if rank == 0:
+            reference_arm(args)
         return 0
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the GAT hot path has no CPU fallback); use --impl reference for the CPU leg")
     import torch.distributed as dist
-    from atmlgraphattentionnetworks_b200 import _abi
-    from atmlgraphattentionnetworks_b200.gatnet import GATNet, GATStack
-    from atmlgraphattentionnetworks_b200.graph import GLOBAL_CACHE
-    from atmlgraphattentionnetworks_b200.parallel import GradBucket, all_reduce_packed_grads
-
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus} (launch with torchrun)"
-
-    # graph batches: weak scaling — every rank owns its own batch of independent graphs (seed = rank), model replicated.
-    # one large graph (--workload large, N > 1): strong scaling — destination-row partition, Wh all-gather per layer.
-    partitioned = args.workload == "large" and world > 1
-    data, spec, loss_fn, wdesc = make_workload(args.workload, seed=0 if partitioned else rank)
-    ep = layer_edges(data)
-    n = data.x.shape[0]
-    torch.manual_seed(0)
-    is_net = args.workload in ("cifar", "cora")
-    if is_net:
-        from types import SimpleNamespace
-        net = GATNet("GAT", "CIFAR10" if args.workload == "cifar" else "Cora", data.x.shape[1]).to(dev).train()
-        batch_d = data.batch.to(dev) if hasattr(data, "batch") else None
-        model = lambda x, ei: net(SimpleNamespace(x=x, edge_index=ei, batch=batch_d, num_graphs=data.num_graphs))   # noqa: E731
-        model.parameters = net.parameters
-    else:
-        model = GATStack(spec, dropout=0.0).to(dev)
-    # gradients are set to None every step and autograd adopts the kernels' packed output buffers as .grad without a copy;
-    # N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (parallel.all_reduce_packed_grads).
-    # The row-partitioned large graph keeps the flat bucket (its stage functions build gradients through torch ops).
-    bucket = GradBucket(model.parameters()) if (world > 1 and args.workload == "large") else None
-    params = list(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=5e-4, fused=True,   # run_inductive.py:18-19,65
-                           capturable=args.cuda_graph)
-    part = None
-    if partitioned:
-        from atmlgraphattentionnetworks_b200.partition import PartitionedGATStack, build_row_partition
-        part = build_row_partition(data.edge_index.to(dev), n, world, rank)
-        pmodel = PartitionedGATStack(model)
-        x_h, y_h = data.x[part.lo:part.hi].contiguous().pin_memory(), data.y[part.lo:part.hi].contiguous().pin_memory()
-        ei_h = torch.zeros((2, 0), dtype=torch.int64).pin_memory()      # the partitioned graph is static and resident
-        torch.cuda.empty_cache()
-    else:
-        x_h, ei_h, y_h = data.x.pin_memory(), data.edge_index.pin_memory(), data.y.pin_memory()
-    x_d, ei_d, y_d = x_h.to(dev), ei_h.to(dev), y_h.to(dev)
-
-    def train_step(x, ei, y):
-        if bucket is not None:
-            bucket.zero()
-        else:
-            opt.zero_grad(set_to_none=True)
-        if partitioned:
-            out = pmodel(x, part)
-            # global mean loss = sum over ranks of (own sum / N); parameter gradients are then SUMMED over ranks
-            loss = torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(out, dim=1), y, reduction="sum") / n
-            loss.backward()
-            bucket.all_reduce_mean(weight=1.0)
-        else:
-            out = model(x, ei)
-            loss = loss_fn(out, y)
-            loss.backward()
-            if world > 1:
-                all_reduce_packed_grads(params)
-        opt.step()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(steps):
-            fn()
-        e.record()
-        barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
-
+    env = Env(rank, local_rank, world, dev)
     warmup = max(args.warmup, 3)
-    # ---- resident leg ----
-    for _ in range(warmup):
-        train_step(x_d, ei_d, y_d)
-    resident = lambda: train_step(x_d, ei_d, y_d)                               # noqa: E731
-    launches_per_replay = None
-    if args.cuda_graph:
-        # whole-step capture: zero_grad + forward + loss + backward + fused Adam of the resident
-        # batch become ONE graph launch; the CSR is cached (no host sync inside), every buffer comes from the graph's pool
-        assert world == 1, "--cuda-graph is a single-GPU mode"
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                train_step(x_d, ei_d, y_d)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
-        l0 = _abi.launch_count()
-        with torch.cuda.graph(graph):
-            static_loss = train_step(x_d, ei_d, y_d)
-        launches_per_replay = _abi.launch_count() - l0
-        resident = graph.replay
-        for _ in range(3):
-            resident()
-    launches0 = _abi.launch_count()
-    with ClockSampler(local_rank) as clocks:
-        ms_step = timed(resident, args.steps)
-    launches = _abi.launch_count() - launches0
-    if launches_per_replay is not None:
-        launches = launches_per_replay * args.steps
+    everything = args.workload == "all"
+    head_name = "ppi" if everything else args.workload
+
     if args.profile:
+        rec = run_workload(head_name, env, args.steps, warmup, args, heads=args.heads or 8, num_graphs=args.graphs, dp=args.dp,
+                           cuda_graph=args.cuda_graph)
         if rank == 0:
-            _emit({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches})
+            _emit({"profile_run": True, "ms_per_step": rec["ms_per_step"], "gpu_launches": rec["gpu_launches"]})
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- end-to-end leg: pinned host buffers in, loss out, every step (new tensors => CSR rebuilt every step) ----
-    # The host->device copy of step k+1 is issued on a copy stream while step k computes (what a data loader with a
-    # prefetch depth of one does): every step still copies its own inputs from pinned host memory inside the timed
-    # region, builds its CSR from the fresh edge_index, and reads its loss back.
-    copy_stream = torch.cuda.Stream()
-    # two static sets of device buffers (no per-step allocation on the copy stream: cross-stream frees make the caching
-    # allocator synchronise, which cost 4 ms per step next to NCCL); the in-place copy bumps edge_index's version
-    # counter, so the graph cache misses and the CSR is rebuilt for every batch
-    slots = [(torch.empty_like(x_d), torch.empty_like(ei_d), torch.empty_like(y_d)) for _ in range(2)]
-    consumed = [None, None]          # event: the step that read slot k has finished
+    def heads_sweep():
+        points = []
+        for h in HEAD_POINTS:
+            r = run_workload("heads", env, args.steps, warmup, args, heads=h, e2e=False, traffic_name=f"heads{h}")
+            pt = {"heads": h, "ms_per_step": r["ms_per_step"], "value": r["value"], "abi_ops_ms_sum": r.get("abi_ops_ms_sum"),
+                  "step_over_abi_ops": r.get("step_over_abi_ops"), "gpu_launches": r["gpu_launches"],
+                  "edge_phase_frac_of_measured_hbm": (r.get("edge_phase") or {}).get("frac_of_measured_hbm"),
+                  "kernels": [{k: v for k, v in kr.items() if k in ("op", "ms", "GBps", "frac_hbm", "TFLOPs")} for kr in r.get("kernels", [])],
+                  "cpu_baseline": r.get("cpu_baseline")}
+            points.append(pt)
+        return {"config": {"workload": "heads sweep as in run_heads_experiment.py: one layer 50 -> H x 64 on the PPI-shaped batch, H = 1, 2, 4, 8, 16"},
+                "unit": UNIT, "points": points}
 
-    loss_h = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    def upload(k):
-        """batch k: pinned host -> device slot k % 2, then graph ingestion (GAT.py:38 + the CSR / CSC / degree-class build:
-        b200gat_csr_build, b200gat_hub_rows, one status read) — all on the copy stream, while step k - 1 computes."""
-        x, ei, y = slots[k % 2]
-        with torch.cuda.stream(copy_stream):
-            if consumed[k % 2] is not None:
-                copy_stream.wait_event(consumed[k % 2])
-            x.copy_(x_h, non_blocking=True)
-            ei.copy_(ei_h, non_blocking=True)
-            y.copy_(y_h, non_blocking=True)
-            if not partitioned:
-                GLOBAL_CACHE.get(ei, n)       # the layers of step k find this batch's CSR in the cache
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-        return (x, ei, y), done
-
-    def e2e_run(steps):
-        nxt = upload(0)
-        pending = None                       # (event, pinned scalar) of the previous step's loss
-        losses = []
-        for k in range(steps):
-            (x, ei, y), done = nxt
-            torch.cuda.current_stream().wait_event(done)
-            loss = train_step(x, ei, y)
-            loss_h[k % 2].copy_(loss.detach(), non_blocking=True)      # device -> pinned host, read one step later
-            ev = torch.cuda.Event()
-            ev.record()
-            consumed[k % 2] = ev
-            if k + 1 < steps:
-                nxt = upload(k + 1)          # overlaps step k on the GPU (the host blocks on the ingestion status read)
-            if pending is not None:
-                pending[0].synchronize()
-                losses.append(float(pending[1]))
-            pending = (ev, loss_h[k % 2])
-        pending[0].synchronize()
-        losses.append(float(pending[1]))
-        assert len(losses) == steps and all(v == v for v in losses)
-    e2e_run(4)                           # warm-up: also fills the copy stream's allocator pool (CSR arrays, sort workspace)
-    e2e_steps = max(args.steps // 2, 3)
-    # median of three timed repetitions (host-side jitter of the per-step synchronisations is +-1 ms run to run)
-    ms_e2e = statistics.median(timed(lambda: e2e_run(e2e_steps), 1) / e2e_steps for _ in range(3))
-    h2d = x_h.numel() * 4 + ei_h.numel() * 8 + y_h.numel() * y_h.element_size()
-
-    # ---- per-op breakdown (CUDA events around each C-ABI call) ----
-    GLOBAL_CACHE.clear()
-    train_step(x_d, ei_d, y_d)
-    _abi.timing = []
-    reps = 5
-    for _ in range(reps):
-        train_step(x_d, ei_d, y_d)
-    torch.cuda.synchronize()
-    per_raw = {}
-    for name, geom, s, e in _abi.timing:
-        per_raw.setdefault((name, geom), []).append(s.elapsed_time(e))
-    _abi.timing = None
-    per = {}
-    for (name, geom), ts in per_raw.items():      # staged backward (partitioned mode): prep + csc + finish = edge_bwd
-        key = ("b200gat_edge_bwd" if name.startswith("b200gat_edge_bwd") else name, geom)
-        per[key] = [a + b for a, b in zip(per[key], ts)] if key in per else list(ts)
-    n_loc = part.n_own if partitioned else n
-    ep_loc = int(part.col.numel() + part.crow.numel()) // 2 if partitioned else ep
-    peaks = measured_peaks()
-    kernels = []
-    for li, (f, c, h, concat) in enumerate(spec):
-        for op in ("b200gat_proj_fwd", "b200gat_edge_fwd", "b200gat_edge_bwd", "b200gat_proj_bwd"):
-            ts = per.get((op, (f, c, h, bool(concat))), [])
-            if not ts:
-                continue
-            ms = statistics.median(ts)
-            need_gx = li > 0
-            nbytes, bound = algorithmic_bytes(op, n_loc, ep_loc, f, c, h, concat, need_gx, cached=args.workload != "large")
-            rec = {"op": op, "layer": li, "geom": f"{f}->{h}x{c}{'cat' if concat else 'mean'}", "ms": ms,
-                   "alg_bytes": nbytes, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / peaks["hbm"]}
-            fl = gemm_flops(op, n_loc, f, c, h, need_gx)
-            if fl:
-                rec["TFLOPs"] = fl / ms / 1e9
-            kernels.append(rec)
-    dom = max(kernels, key=lambda r: r["ms"]) if kernels else None
-    # measured DRAM traffic of each op (one committed `ncu --set full` capture of this workload, tools/ncu_traffic.py)
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.isfile(tpath) and not partitioned:
-        traffic = json.load(open(tpath)).get("ops", {})
-    for rec in kernels:
-        t = traffic.get(f"{rec['op']}:{rec['layer']}")
-        rec["dram_traffic_bytes"] = t["dram_bytes"] if t else None
-    roofline = None
-    if dom is not None:
-        if dom["op"].startswith("b200gat_edge"):
-            roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": dom["GBps"] / peaks["hbm"], "traffic": dom["dram_traffic_bytes"],
-                        "alg_bytes": dom["alg_bytes"]}
+    if head_name == "heads" and not args.heads:
+        head = heads_sweep()
+        head.update({"ms_per_step": head["points"][-1]["ms_per_step"], "value": head["points"][-1]["value"], "gpu_launches":
+                     head["points"][-1]["gpu_launches"], "n_gpus": world, "steps": args.steps, "warmup": warmup, "scaling": "weak"})
+    else:
+        head = run_workload(head_name, env, args.steps, warmup, args, heads=args.heads or 8, num_graphs=args.graphs, dp=args.dp,
+                            cuda_graph=args.cuda_graph)
+    subs = {}
+    if everything:
+        sub_steps = min(args.steps, 10)
+        subs["large"] = run_workload("large", env, sub_steps, 3, args)
+        if world == 1:
+            subs["cifar"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=128)
+            subs["cifar"]["batch512"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=512, cpu=False,
+                                                     traffic_name="cifar512")
+            subs["cora"] = run_workload("cora", env, args.steps, warmup, args)
+            subs["heads"] = heads_sweep()
         else:
-            roofline = {"bound": "tensor", "achieved": dom.get("TFLOPs", 0.0), "peak": peaks["bf16_sustained"],
-                        "unit": "TFLOP/s", "frac": dom.get("TFLOPs", 0.0) / peaks["bf16_sustained"],
-                        "traffic": dom["dram_traffic_bytes"], "alg_bytes": dom["alg_bytes"]}
-        roofline.update({"kernel": f"{dom['op']} layer {dom['layer']} ({dom['geom']})", "ms": dom["ms"],
-                         "peak_source": peaks["source"] + " (of measured)"})
-        if args.workload != "large" and roofline["bound"] == "hbm":
-            # SURVEY.md §8d caveat 2: in the cached regime the HBM count is the compulsory traffic; every edge still pulls
-            # its row through L2 -> SM (4.4x the HBM bytes on the PPI-shaped layers), which is what bounds these kernels
-            roofline["regime"] = "cached: gathered rows are L2-resident, the kernel is bound by L2->SM gather traffic (DESIGN.md §5)"
-        elif roofline["bound"] == "hbm":
-            roofline["regime"] = "streaming: every gathered row comes from HBM"
-    edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
-    edge_bytes = sum(r["alg_bytes"] for r in kernels if r["op"].startswith("b200gat_edge"))
-    edge_phase = {"per_rank": partitioned, "ms": edge_ms, "alg_bytes": edge_bytes, "GBps": edge_bytes / edge_ms / 1e6 if edge_ms else None,
-                  "frac_of_measured_hbm": edge_bytes / edge_ms / 1e6 / peaks["hbm"] if edge_ms else None,
-                  "frac_of_nominal_8TBps": edge_bytes / edge_ms / 1e6 / 8000.0 if edge_ms else None,
-                  "edges_per_s": len(spec) * ep_loc / (edge_ms / 1e3) if edge_ms else None}
+            subs["cifar"] = {"dp_strong": run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, dp="strong"),
+                             "dp_weak": run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, dp="weak")}
+            subs["cora"] = subs["heads"] = {"skipped": "replicas only: the workload does not shard (DESIGN.md §6); see the N = 1 line"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
-
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
-        val, dt, desc = cpu_reference_leg(args.workload, 3, 1, args.cpu_sample_graphs if args.workload != "large" else 1)
-        cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc,
-               "s_per_step": dt}
-    total_edges = len(spec) * ep * (1 if partitioned else world)
-    line = {
-        "metric": METRIC, "value": total_edges / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wdesc,
-                   "parallelism": (f"row{world} (destination-row partition, NCCL all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
-                                   if partitioned else f"dp{world} (independent graph batches per rank, one-group NCCL all-reduce of the packed gradient buffers)"),
-                   "edges_per_layer_incl_self_loops": ep, "input_edges": int(data.edge_index.shape[1]), "nodes": n,
-                   "layers": len(spec), "step": "zero_grad + fwd + loss + bwd + grad all-reduce + fused Adam",
-                   "cuda_graph": bool(args.cuda_graph),
-                   "l2": "inputs larger than L2 (per-step working set ~2 GB vs 126 MB L2); no explicit flush"},
-        "e2e": {"value": total_edges / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "includes": "every step: H2D of its batch from pinned host and graph ingestion (CSR/CSC build, 2 radix sorts, degree classes) on a copy stream one batch ahead, train step, loss D2H into pinned memory read one step behind"},
-        "gpu_launches": launches, "roofline": roofline, "edge_phase": edge_phase, "kernels": kernels,
-        "cpu_baseline": cpu, "clocks": clocks.summary(),
-    }
+    line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head.get("scaling", "weak"),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "git_sha": git_sha()}
+    for k in ("config", "e2e", "gpu_launches", "roofline", "edge_phase", "kernels", "abi_ops_ms_sum", "step_over_abi_ops",
+              "collectives_ms_per_step", "collectives_note", "check", "cpu_baseline", "clocks", "cuda_graph", "points"):
+        if k in head:
+            line[k] = head[k]
+    line.update(subs)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

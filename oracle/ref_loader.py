@@ -1,13 +1,28 @@
-"""Import the reference's GAT.py / GATNet.py UNMODIFIED from /root/reference on top of oracle/pyg_standin.
+"""Import the reference's GAT.py / GATNet.py UNMODIFIED on top of oracle/pyg_standin.
 
-Test infrastructure (see oracle/__init__.py).  /root/reference only exists in the build container, so this
-module is used by tests/golden/make_golden.py and by CPU tests that skip when the reference is absent.
+Test infrastructure (see oracle/__init__.py).  The files come from /root/reference where it exists (the build
+container) and otherwise from oracle/_ref/, the git-ignored byte-for-byte staging copy that oracle/stage_reference.py
+makes so that the reference itself — not only the port — can run on the GPU box (bench.py --impl reference,
+cpu_baseline kind "reference").  Used by tests/golden/make_golden.py, bench.py's CPU legs and the CPU tests.
 """
 import importlib.util
 import os
 import sys
 
-REFERENCE_DIR = os.environ.get("B200GAT_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _reference_dir():
+    env = os.environ.get("B200GAT_REFERENCE_DIR")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "GAT.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_DIR = _reference_dir()
 _STANDIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pyg_standin")
 _cache = {}
 
@@ -66,3 +81,26 @@ def load_act_experiment():
     finally:
         sys.path.remove(_STANDIN)
     return _cache["act"]
+
+
+class RefStack:
+    """Bench-only composition of the REFERENCE's own GraphAttentionLayer (GAT.py:8) + F.elu between layers, for the
+    PPI-shaped / large-graph configs (the reference has no 3-layer model).  spec = [(in, out, heads, concat)]."""
+
+    def __new__(cls, spec, dropout=0.0):
+        import torch
+        ref_gat, _ = load()
+
+        class _Stack(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.convs = torch.nn.ModuleList(
+                    [ref_gat.GraphAttentionLayer(i, o, num_heads=h, concat=c, dropout=dropout) for (i, o, h, c) in spec])
+
+            def forward(self, x, edge_index):
+                for k, conv in enumerate(self.convs):
+                    x = conv(x, edge_index)
+                    if k + 1 < len(self.convs):
+                        x = torch.nn.functional.elu(x)
+                return x
+        return _Stack()

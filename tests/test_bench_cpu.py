@@ -52,7 +52,9 @@ def test_reference_arm_prints_the_contract_line_without_a_gpu():
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_loader
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["nodes"] > 0 and "workload" in line["config"] and "l2" in line["config"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
