@@ -1,0 +1,218 @@
+"""GPU parity at the REAL geometry of every BASELINE.json config (run on the B200 box with -m gpu): the CUDA path, through
+the drop-in modules, against the CPU oracle port (oracle/gat_port.py — same op sequence as the reference's GAT.py /
+GATNet.py, pinned by tests/golden) in fp32 (what the reference's arithmetic gives) and f64 (truth), end to end:
+
+  (i)   the PPI 3-layer stack at full widths 50 -> 4x256 -> 4x256 -> 6x121 (K = 1024 GEMMs, CTA-pair backward GEMMs, fused
+        ELU boundaries, mean-over-heads last layer) on a 4-of-24-graph sub-batch of the PPI-shaped batch;
+  (ii)  all five heads-sweep points 50 -> H x 64, H = 1, 2, 4, 8, 16, on the same sub-batch;
+  (iii) GATNet('GAT','Cora',1433) at full size (2,708 nodes, F = 1433), eval path (fused boundary) and training path;
+  (iv)  GATNet('GAT','CIFAR10',5) on 128- and 512-graph batches (the reference's own batch size, run_gnn_benchmark.py:29);
+  (v)   the 3-layer stack of the 2.4 M-node config on the 1/32-scale power-law graph (75 k nodes, 1.94 M edges, hub and
+        giant rows present) with the streaming schedules forced.
+
+Bar (as in test_gpu_parity.py): max|a-b| <= 1e-5 max|b| against f64 truth, widened to 4x the fp32 port's own distance to
+f64 where that is larger; gradients of the attention parameters, which are sums of dz cancelling inside every softmax row,
+are judged on the scale of the same head's attentions1 weight gradient.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from util import FP32_SUM_ULPS, FP32_TOL, attention_term_sums, nerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _compare(got, want32, want, label, terms=None):
+    """terms: util.attention_term_sums of the f64 oracle run — the attention-parameter gradients are sums over all nodes
+    that cancel by large factors in deep layers; they may additionally differ by FP32_SUM_ULPS of the summed magnitudes"""
+    for k in want:
+        floor = nerr(want32[k], want[k])
+        tol = max(FP32_TOL, 4.0 * floor)
+        if ".attentions" in k:
+            conv, _, rest = k.partition(".attentions")
+            head = rest.split(".")[1]
+            scale = max(float(np.abs(want[k]).max()), float(np.abs(want[f"{conv}.attentions1.{head}.weight"]).max()))
+            err = float(np.abs(got[k] - want[k]).max())
+            slack = FP32_SUM_ULPS * terms[k] if terms and k in terms else 0.0
+            assert err <= max(2e-5, 4.0 * floor) * scale + slack, (label, k, err / max(scale, 1e-30), floor, slack)
+        else:
+            assert nerr(got[k], want[k]) <= tol, (label, k, nerr(got[k], want[k]), floor)
+
+
+def _stack_case(spec, data, gout_seed, force_stream=False):
+    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    from atmlgraphattentionnetworks_b200.graph import GraphCache
+    from oracle.gat_port import PortStack
+    torch.manual_seed(11)
+    ref = PortStack(spec, dropout=0.0)
+    with torch.no_grad():
+        for conv in ref.convs:
+            conv.bias.uniform_(-0.5, 0.5)
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+    d_last = spec[-1][1] * (spec[-1][2] if spec[-1][3] else 1)
+    gout = torch.randn(data.x.shape[0], d_last, generator=torch.Generator().manual_seed(gout_seed))
+    need_gx = spec[0][0] <= 128            # the input gradient of a wide first layer is not part of any BASELINE model
+
+    terms = {}
+
+    def run_port(dt):
+        m = PortStack(spec, dropout=0.0).to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in state.items()})
+        if dt == torch.float64:
+            terms.update({"_live": attention_term_sums(m)})
+        xr = data.x.detach().clone().to(dt).requires_grad_(need_gx)
+        o = m(xr, data.edge_index)
+        o.backward(gout.to(dt))
+        res = {"out": o.detach().numpy()}
+        if need_gx:
+            res["g_x"] = xr.grad.numpy()
+        res.update({k: p.grad.numpy() for k, p in m.named_parameters()})
+        return res
+    want32, want = run_port(torch.float32), run_port(torch.float64)
+    model = GATStack(spec, dropout=0.0)
+    model.load_state_dict(state)
+    model = model.to(DEV).train()
+    xg = data.x.detach().clone().to(DEV).requires_grad_(need_gx)
+    eig = data.edge_index.to(DEV)
+    if force_stream:
+        cache = GraphCache()
+        cache.get(eig, data.x.shape[0]).c_struct().span = 1 << 40          # "every gathered row comes from HBM"
+        for conv in model.convs:
+            conv.graph_cache = cache
+    out = model(xg, eig)
+    out.backward(gout.to(DEV))
+    got = {"out": out.detach().cpu().numpy()}
+    if need_gx:
+        got["g_x"] = xg.grad.cpu().numpy()
+    got.update({k: p.grad.cpu().numpy() for k, p in model.named_parameters()})
+    return got, want32, want, terms["_live"]
+
+
+# ------------------------------------------------------------------------------------------------ (i) PPI stack
+def test_ppi_stack_full_widths_matches_cpu_oracle():
+    from atmlgraphattentionnetworks_b200 import synth
+    data = synth.ppi_shaped(keep_graphs=4)                  # 8,203 nodes, 126,165 edges incl. self loops
+    got, want32, want, terms = _stack_case(synth.PPI_STACK, data, gout_seed=1)
+    _compare(got, want32, want, "ppi_stack", terms)
+
+
+# ------------------------------------------------------------------------------------------------ (ii) heads sweep
+@pytest.mark.parametrize("heads", [1, 2, 4, 8, 16])
+def test_heads_sweep_point_matches_cpu_oracle(heads):
+    from atmlgraphattentionnetworks_b200 import synth
+    data = synth.ppi_shaped(keep_graphs=4)
+    got, want32, want, terms = _stack_case([(50, 64, heads, True)], data, gout_seed=heads)
+    _compare(got, want32, want, f"heads{heads}", terms)
+
+
+# ------------------------------------------------------------------------------------------------ (iii), (iv) GATNet
+def _gatnet_case(dataset, data, train, monkeypatch):
+    import GATNet
+    from oracle.gat_port import PortGATNet
+    if train:
+        # training path (no fused boundary; GATNet.py:78-86) with every dropout turned into the identity on both sides:
+        # "dropout disabled or identical masks supplied" (north-star)
+        monkeypatch.setattr(torch.nn.functional, "dropout", lambda x, p=0.5, training=True, inplace=False: x)
+    torch.manual_seed(4)
+    ref = PortGATNet("GAT", dataset, data.x.shape[1])
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+
+    terms = {}
+
+    def run_port(dt):
+        m = PortGATNet("GAT", dataset, data.x.shape[1]).to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in state.items()})
+        m.train(train)
+        if dt == torch.float64:
+            terms.update({"_live": attention_term_sums(m)})
+        d = SimpleNamespace(x=data.x.to(dt), edge_index=data.edge_index, batch=getattr(data, "batch", None))
+        o = m(d)
+        torch.nn.functional.nll_loss(o, data.y).backward()
+        res = {"out": o.detach().numpy()}
+        res.update({k: p.grad.numpy() for k, p in m.named_parameters()})
+        return res
+    want32, want = run_port(torch.float32), run_port(torch.float64)
+    net = GATNet.GATNet("GAT", dataset, data.x.shape[1])
+    net.load_state_dict(state)
+    net = net.to(DEV)
+    net.train(train)
+    if train:
+        net.conv1.dropout_val = net.conv2.dropout_val = 0.0
+    d = SimpleNamespace(x=data.x.to(DEV), edge_index=data.edge_index.to(DEV),
+                        batch=data.batch.to(DEV) if hasattr(data, "batch") else None, num_graphs=data.num_graphs)
+    o = net(d)
+    torch.nn.functional.nll_loss(o, data.y.to(DEV)).backward()
+    got = {"out": o.detach().cpu().numpy()}
+    got.update({k: p.grad.cpu().numpy() for k, p in net.named_parameters()})
+    _compare(got, want32, want, f"{dataset}_{'train' if train else 'eval'}", terms["_live"])
+
+
+@pytest.mark.parametrize("train", [False, True], ids=["eval_fused", "train_path"])
+def test_gatnet_cora_full_size_matches_cpu_oracle(train, monkeypatch):
+    from atmlgraphattentionnetworks_b200 import synth
+    _gatnet_case("Cora", synth.cora_shaped(), train, monkeypatch)
+
+
+@pytest.mark.parametrize("graphs", [128, 512])
+def test_gatnet_cifar_batches_match_cpu_oracle(graphs, monkeypatch):
+    from atmlgraphattentionnetworks_b200 import synth
+    _gatnet_case("CIFAR10", synth.cifar_shaped(num_graphs=graphs), True, monkeypatch)
+
+
+def test_gatnet_cifar_f3_batch_matches_cpu_oracle(monkeypatch):
+    """run_gnn_benchmark.py:41 feeds 3 features (RGB means), BASELINE.json says 5: both"""
+    from atmlgraphattentionnetworks_b200 import synth
+    _gatnet_case("CIFAR10", synth.cifar_shaped(num_graphs=128, num_features=3), False, monkeypatch)
+
+
+# ------------------------------------------------------------------------------------------------ (v) power-law stack
+def test_powerlaw_stack_scaled_graph_streaming_hub_giant_matches_cpu_oracle():
+    from atmlgraphattentionnetworks_b200 import synth
+    from atmlgraphattentionnetworks_b200._abi import HUB_DEGREE
+    data = synth.powerlaw(num_nodes=75_000, num_edges=1_937_500)
+    n = data.x.shape[0]
+    indeg = torch.bincount(data.edge_index[1], minlength=n) + 1
+    outdeg = torch.bincount(data.edge_index[0], minlength=n) + 1
+    assert int(indeg.max()) > 4096 and int(outdeg.max()) > 4096 and int((indeg > HUB_DEGREE).sum()) > 5   # all three degree classes
+    got, want32, want, terms = _stack_case(synth.LARGE_STACK, data, gout_seed=5, force_stream=True)
+    _compare(got, want32, want, "powerlaw_stack", terms)
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel emulation
+def test_two_shards_through_the_packed_gradient_exchange_match_the_whole_batch():
+    """Data parallelism over graph batches, emulated on one GPU: the two shards of a PPI-shaped batch run one after the
+    other through the real kernels, their packed gradient buffers are scaled exactly as parallel.all_reduce_packed_grads
+    scales them (n_r / N for the node-level mean loss) and summed (what the NCCL all-reduce does); the result must match
+    the whole batch on one GPU at 1e-5."""
+    from atmlgraphattentionnetworks_b200 import synth
+    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    from atmlgraphattentionnetworks_b200.parallel import packed_grad_buffers, scale_packed_grads, shard_graphs
+    import torch.nn.functional as F
+    data = synth.ppi_shaped(keep_graphs=6)
+    spec = [(50, 64, 4, True), (256, 64, 4, True), (256, 121, 6, False)]
+    torch.manual_seed(0)
+    model = GATStack(spec, dropout=0.0).to(DEV)
+    params = list(model.parameters())
+    n = data.x.shape[0]
+
+    def grads_of(d, weight):
+        for p in params:
+            p.grad = None
+        loss = F.binary_cross_entropy_with_logits(model(d.x.to(DEV), d.edge_index.to(DEV)), d.y.to(DEV))
+        loss.backward()
+        bases = scale_packed_grads(params, weight)
+        assert 0 < len(bases) <= 7 * len(spec) + 1 and len(packed_grad_buffers(params)) == len(bases)
+        return float(loss) * weight, torch.cat([p.grad.flatten() for p in params]).clone()
+    want_loss, want = grads_of(data, 1.0)
+    total_loss, total = 0.0, torch.zeros_like(want)
+    for r in range(2):
+        shard = synth.select_graphs(data, shard_graphs(data.num_graphs, 2, r))
+        loss_r, g_r = grads_of(shard, shard.x.shape[0] / n)
+        total_loss += loss_r
+        total += g_r
+    assert abs(total_loss - want_loss) <= 1e-5 * abs(want_loss)
+    assert float((total - want).abs().max()) <= 1e-5 * float(want.abs().max())

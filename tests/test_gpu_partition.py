@@ -91,12 +91,14 @@ def test_partitioned_stages_match_single_gpu(case):
             assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 1e-5, k
 
 
-def _nccl_worker(rank, world, port, results):
+def _nccl_worker(rank, world, port, results, second_forward=False):
     import torch.distributed as dist
     import GAT
     from atmlgraphattentionnetworks_b200 import partition as pt
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if second_forward:
+        os.environ["B200GAT_PEER_PUSH"] = "1"           # the fused projection + peer-memory all-gather of Wh
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -110,6 +112,13 @@ def _nccl_worker(rank, world, port, results):
     part = pt.build_row_partition(ei, n, world, rank)
     xo = x[part.lo:part.hi].clone().requires_grad_(True)
     out = pt.partitioned_layer_forward(layer, xo, part)
+    if second_forward:
+        # a SECOND forward through the same layer before the first one's backward (an eval forward, a second micro-batch,
+        # activation checkpointing): it overwrites the layer's persistent symmetric Wh buffer, which the first forward's
+        # backward must not depend on
+        with torch.no_grad():
+            pt.partitioned_layer_forward(layer, torch.randn_like(xo), part)
+        results["peer"] = getattr(layer, "_peer_buf", (None, None))[1] is not None
     out.backward(gout[part.lo:part.hi])
     flat = torch.cat([p.grad.flatten() for p in layer.parameters()])
     dist.all_reduce(flat)
@@ -137,4 +146,20 @@ def test_partitioned_layer_nccl():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, port, results), nprocs=2, join=True)
+    assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_partitioned_layer_peer_push_second_forward_before_backward():
+    """forward A, forward B, backward A in peer-push mode gives A's gradients (the saved Wh is a private copy, not a view
+    of the symmetric buffer the second forward overwrites)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, results, True), nprocs=2, join=True)
     assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
