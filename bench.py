@@ -287,7 +287,8 @@ def _emit(line):
 
 
 def log(*a):
-    print("[bench]", *a, file=sys.stderr, flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ one GPU workload
