@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -33,6 +33,19 @@ class Layer(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class Dropout(C.Structure):
+    """b200gat_dropout: in-kernel attention dropout (p, device pointer to two uint64 seed words)"""
+    _fields_ = [("p", C.c_float), ("reserved", C.c_float), ("seed", C.c_void_p)]
+
+
+def dropout_struct(drop):
+    """drop: None or (p, seed tensor int64[2] on the device) -> Dropout"""
+    if drop is None:
+        return Dropout(0.0, 0.0, None)
+    p, seed = drop
+    return Dropout(float(p), 0.0, seed.data_ptr())
+
+
 class ProjFwdArgs(C.Structure):
     _fields_ = [("layer", Layer), ("num_nodes", C.c_int64),
                 ("x", C.c_void_p), ("ldx", C.c_int64),
@@ -50,7 +63,8 @@ class EdgeFwdArgs(C.Structure):
                 ("wh", C.c_void_p), ("s_src", C.c_void_p), ("s_dst", C.c_void_p), ("bias", C.c_void_p),
                 ("mask", C.c_void_p),
                 ("out", C.c_void_p), ("ldo", C.c_int64),
-                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p), ("out_amax", C.c_void_p)]
+                ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p), ("out_amax", C.c_void_p),
+                ("dropout", Dropout)]
 
 
 class EdgeBwdArgs(C.Structure):
@@ -64,7 +78,8 @@ class EdgeBwdArgs(C.Structure):
                 ("g_t", C.c_void_p), ("g_bw", C.c_void_p), ("g_a1", C.c_void_p), ("g_a2", C.c_void_p),
                 ("g_b1", C.c_void_p), ("g_b2", C.c_void_p), ("g_bias", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("out_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
+                ("out_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t),
+                ("dropout", Dropout), ("edge_scratch", C.c_void_p), ("edge_scratch_bytes", C.c_size_t)]
 
 
 class EdgeBwdPrepArgs(C.Structure):
@@ -82,7 +97,7 @@ class EdgeBwdCscArgs(C.Structure):
                 ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
                 ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64),
                 ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p),
-                ("max_out_degree", C.c_int64)]
+                ("max_out_degree", C.c_int64), ("dropout", Dropout)]
 
 
 class EdgeBwdFinishArgs(C.Structure):
@@ -103,12 +118,13 @@ class ProjBwdArgs(C.Structure):
 
 
 ACT_NONE, ACT_ELU = 0, 1
-LOGIT_LEAKY_RELU, LOGIT_LOGSIGMOID, LOGIT_TANH = 0, 1, 2
+LOGIT_LEAKY_RELU, LOGIT_LOGSIGMOID, LOGIT_TANH, LOGIT_HEAD_SOFTMAX = 0, 1, 2, 3
 
 _SIGNATURES = {
     "b200gat_abi_version": (C.c_int, []),
     "b200gat_launch_count": (C.c_uint64, []),
     "b200gat_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "b200gat_dropout_mask": (C.c_int, [C.POINTER(Dropout), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200gat_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b200gat_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 +
                           [C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -70,6 +70,20 @@ bool edge_schedule_streaming(int64_t span, int64_t row_bytes) {
   return (span + 1) * row_bytes > l2_bytes() / 2;
 }
 
+int make_dropout(const float* mask, const b200gat_dropout& d, DropoutSpec* out) {
+  out->mask = mask; out->seed = nullptr; out->threshold = 0u; out->scale = 1.f;
+  if (mask) return 0;                                   // the tensor wins
+  B200GAT_REQUIRE(d.p >= 0.f && d.p <= 1.f, B200GAT_E_SHAPE, "dropout: p = %g outside [0, 1]", double(d.p));
+  if (d.p <= 0.f) return 0;
+  B200GAT_REQUIRE(d.seed != nullptr, B200GAT_E_NULL, "dropout: p > 0 needs the device seed words");
+  out->seed = d.seed;
+  if (d.p >= 1.f) { out->threshold = 0xFFFFFFFFu; out->scale = 0.f; return 0; }   // everything dropped
+  const double t = double(d.p) * 4294967296.0;
+  out->threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+  out->scale = 1.f / (1.f - d.p);
+  return 0;
+}
+
 }  // namespace b200gat
 
 extern "C" int b200gat_abi_version(void) { return B200GAT_ABI_VERSION; }

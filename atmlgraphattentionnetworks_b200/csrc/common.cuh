@@ -33,7 +33,7 @@ inline int validate_layer(const b200gat_layer& L) {
                   "layer: c_pad must be round_up(out_channels, 4)");
   B200GAT_REQUIRE(L.c_pad <= 512, B200GAT_E_UNSUPPORTED, "layer: out_channels > 512 per head is not supported");
   B200GAT_REQUIRE(L.heads <= 1024, B200GAT_E_UNSUPPORTED, "layer: more than 1024 heads is not supported");
-  B200GAT_REQUIRE(L.logit_activation >= B200GAT_LOGIT_LEAKY_RELU && L.logit_activation <= B200GAT_LOGIT_TANH,
+  B200GAT_REQUIRE(L.logit_activation >= B200GAT_LOGIT_LEAKY_RELU && L.logit_activation <= B200GAT_LOGIT_HEAD_SOFTMAX,
                   B200GAT_E_UNSUPPORTED, "layer: unknown logit_activation %d", L.logit_activation);
   return 0;
 }
@@ -75,6 +75,72 @@ __device__ __forceinline__ float logit_act_grad(float z, float slope, int act) {
   if (act == B200GAT_LOGIT_TANH) { const float t = tanhf(z); return 1.f - t * t; }
   if (act == B200GAT_LOGIT_LOGSIGMOID) return 1.f / (1.f + expf(z));                     // sigmoid(-z)
   return z > 0.f ? 1.f : slope;
+}
+
+// ---- attention dropout (GAT.py:61): keep-multiplier of coefficient (edge e, head h), e = position in the ORIGINAL
+// [edges ; loops] order.  Either read from a caller-supplied [E', H] tensor (parity tests) or generated in the kernel:
+// Philox4x32-10, key = seed[0], counter = (e, h / 4, seed[1]), word h % 4; keep iff word >= p * 2^32.  The forward (CSR
+// order) and the backward (CSC order) regenerate the identical multiplier from (seed, e, h): no [E', H] tensor exists.
+struct DropoutSpec {
+  const float* mask;       // tensor mode, or nullptr
+  const uint64_t* seed;    // Philox mode (mask == nullptr): DEVICE pointer to two words, or nullptr (dropout off)
+  uint32_t threshold;      // keep iff word >= threshold
+  float scale;             // 1 / (1 - p); 0 when p >= 1
+  __host__ __device__ bool active() const { return mask != nullptr || seed != nullptr; }
+};
+// host: validate the ABI's (mask, b200gat_dropout) pair
+int make_dropout(const float* mask, const b200gat_dropout& d, DropoutSpec* out);
+
+struct DropoutKey { uint32_t k0, k1, c2, c3; };
+__device__ __forceinline__ DropoutKey dropout_key(const DropoutSpec& d) {
+  DropoutKey k{0u, 0u, 0u, 0u};
+  if (d.mask == nullptr && d.seed != nullptr) {
+    const unsigned long long s0 = __ldg(reinterpret_cast<const unsigned long long*>(d.seed));
+    const unsigned long long s1 = __ldg(reinterpret_cast<const unsigned long long*>(d.seed) + 1);
+    k.k0 = static_cast<uint32_t>(s0); k.k1 = static_cast<uint32_t>(s0 >> 32);
+    k.c2 = static_cast<uint32_t>(s1); k.c3 = static_cast<uint32_t>(s1 >> 32);
+  }
+  return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// call only when d.active()
+__device__ __forceinline__ float dropout_mult(const DropoutSpec& d, const DropoutKey& key, int e, int h, int H) {
+  if (d.mask) return __ldg(d.mask + int64_t(e) * H + h);
+  const uint4 r = philox4x32_10(static_cast<uint32_t>(e), static_cast<uint32_t>(h) >> 2, key.c2, key.c3, key.k0, key.k1);
+  const int s = h & 3;
+  const uint32_t w = s == 0 ? r.x : (s == 1 ? r.y : (s == 2 ? r.z : r.w));
+  return w >= d.threshold ? d.scale : 0.f;
+}
+
+// B200GAT_LOGIT_HEAD_SOFTMAX (run_act_func_experiment.py:111, nn.Softmax() on the [E', H] logits = softmax over the HEADS
+// of one edge): e_h = exp(z_h - max_h' z_h') / sum_h' exp(z_h' - max), z_h' = a[h' * a_stride] + b[h'].  The two rows are the
+// destination's s_dst values (stride 1, or stride 4 inside the backward's 16-byte row records) and the source's s_src.
+__device__ __forceinline__ float head_softmax(const float* a, int a_stride, const float* b, int h, int H) {
+  float mx = -INFINITY;
+  for (int t = 0; t < H; ++t) mx = fmaxf(mx, __ldg(a + t * a_stride) + __ldg(b + t));
+  float sum = 0.f, mine = 0.f;
+  for (int t = 0; t < H; ++t) {
+    const float v = expf(__ldg(a + t * a_stride) + __ldg(b + t) - mx);
+    sum += v;
+    if (t == h) mine = v;
+  }
+  return mine / sum;
+}
+// e = f(s_dst[i,h] + s_src[j,h]) for any logit activation; sd = s_dst[i,h] (already loaded by the caller)
+template <bool GENERIC>
+__device__ __forceinline__ float edge_logit(const float* s_dst_row, const float* s_src_row, float sd, int h, int H,
+                                            float slope, int act) {
+  if (GENERIC && act == B200GAT_LOGIT_HEAD_SOFTMAX) return head_softmax(s_dst_row, 1, s_src_row, h, H);
+  return logit_act<GENERIC>(sd + __ldg(s_src_row + h), slope, act);
 }
 
 template <int G>

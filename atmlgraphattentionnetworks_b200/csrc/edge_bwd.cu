@@ -298,7 +298,8 @@ struct EdgeBwdParams {
   int H, Cp, Dp;
   float slope; int act;
   const int32_t* colptr; const int32_t* crow; const int32_t* ceid;
-  const float* wh; const float* s_src; const float4* rowrec; const float* mask;
+  const float* wh; const float* s_src; const float4* rowrec;
+  DropoutSpec drop;                        // attention dropout: mask tensor or in-kernel Philox (common.cuh)
   const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
   float* gwh;                              // [N, Dp]
   float* g_s_src; float* g_s_dst;          // [N, H]; g_s_dst is zero-initialised and accumulated atomically
@@ -307,6 +308,8 @@ struct EdgeBwdParams {
   // edge_bwd_hub_kernel, one CTA per (source row, head).  No compare, no extra register in the hot kernels.
   const int32_t* colend; const int32_t* hub; int64_t nhub;
   int max_deg;          // largest out-degree: source rows above B200GAT_GIANT_DEGREE are split into segments (grid.y)
+  float* de;            // B200GAT_LOGIT_HEAD_SOFTMAX only: [E', H] d loss / d e per CSC entry (the heads of an edge are coupled:
+                        // dz is formed by head_softmax_bwd_kernel); the CSC pass then leaves g_s_src = 0 and g_s_dst untouched
   uint32_t* amax;       // optional [2]: bit patterns of max|gWh| and max|g_s_src| (atomicMax; zeroed by the host) — saves
                         // gt_amax_kernel's pass over gWh.  Not exact for giant rows (partial sums): the host ignores it then
 };
@@ -398,6 +401,7 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
     off[v] = 4 * (live[v] ? gl + v * G : Q - 1);
   }
 
+  const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
   float amax_w = 0.f, amax_s = 0.f;
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
     const int64_t item = base + gi;
@@ -432,9 +436,14 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
         i = __ldg(p.crow + k);
         const float4 rr = __ldg(p.rowrec + int64_t(i) * H + h);   // {s_dst, rowmax, 1/(rowsum+eps), Drow}
         const float z = rr.x + ss;
-        dslope = logit_act_grad<GENERIC>(z, slope, act);
-        alpha = expf(logit_act<GENERIC>(z, slope, act) - rr.y) * rr.z;
-        if (HAS_MASK && (!GENERIC || p.mask)) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
+        if (GENERIC && act == B200GAT_LOGIT_HEAD_SOFTMAX) {
+          const float e = head_softmax(reinterpret_cast<const float*>(p.rowrec + int64_t(i) * H), 4, p.s_src + j * H, h, H);
+          alpha = expf(e - rr.y) * rr.z;
+        } else {
+          dslope = logit_act_grad<GENERIC>(z, slope, act);
+          alpha = expf(logit_act<GENERIC>(z, slope, act) - rr.y) * rr.z;
+        }
+        if (HAS_MASK && (!GENERIC || p.drop.active())) mk = dropout_mult(p.drop, dkey, __ldg(p.ceid + k), h, H);
         at = alpha * mk;
         dr = rr.w;
       }
@@ -481,9 +490,13 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
         if (rel >= 0 && rel < U) dot_mine = got;
       }
       if (ok) {
-        const float dz = alpha * (mk * dot_mine - dr) * dslope;
-        gsrc += dz;
-        atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+        if (GENERIC && act == B200GAT_LOGIT_HEAD_SOFTMAX) {
+          p.de[int64_t(k) * H + h] = alpha * (mk * dot_mine - dr);        // d loss / d e; dz needs the edge's other heads
+        } else {
+          const float dz = alpha * (mk * dot_mine - dr) * dslope;
+          gsrc += dz;
+          atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+        }
       }
     }
     gsrc = group_sum<G>(gsrc);
@@ -562,6 +575,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
   const int off = 4 * (live ? gl : Q - 1);
   const char* gb = reinterpret_cast<const char*>(p.g + off);
 
+  const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
   float amax_w = 0.f, amax_s = 0.f;
   for (int64_t base = warp * GPW; base < p.N; base += nwarps * GPW) {
     const int64_t j = base + gi < p.N ? base + gi : p.N - 1;
@@ -590,14 +604,14 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
       if (ok) {
         i = __ldg(p.crow + k);
         const float4* rec = p.rowrec + int64_t(i) * HH;
-        const float* mrow = HAS_MASK ? p.mask + int64_t(__ldg(p.ceid + k)) * HH : nullptr;
+        const int eid_k = HAS_MASK ? __ldg(p.ceid + k) : 0;
 #pragma unroll
         for (int h = 0; h < HH; ++h) {
           const float4 rr = __ldg(rec + h);               // {s_dst, rowmax, 1/(rowsum+eps), Drow}
           const float z = rr.x + ss[h];
           const float alpha = expf(leaky(z, slope) - rr.y) * rr.z;
           const float ad = alpha * (z > 0.f ? 1.f : slope);
-          const float mk = HAS_MASK ? __ldg(mrow + h) : 1.f;
+          const float mk = HAS_MASK ? dropout_mult(p.drop, dkey, eid_k, h, HH) : 1.f;
           at[h] = alpha * mk;
           ca[h] = ad * mk;
           cb[h] = ad * rr.w;
@@ -681,7 +695,7 @@ static int launch_edge_bwd_mean(const EdgeBwdParams& p, cudaStream_t stream) {
   const int64_t want = ceil_div(ceil_div(p.N, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  if (p.mask) edge_bwd_mean_kernel<G, HH, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.drop.active()) edge_bwd_mean_kernel<G, HH, true><<<blocks, threads, 0, stream>>>(p);
   else edge_bwd_mean_kernel<G, HH, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_mean_kernel");
 }
@@ -724,6 +738,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
     live[v] = lane + v * 32 < Q;
     off[v] = 4 * (live[v] ? lane + v * 32 : Q - 1);
   }
+  const DropoutKey dkey = dropout_key(p.drop);
   float amax_w = 0.f, amax_s = 0.f;
   for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
     const int64_t j = __ldg(p.hub + item / H);
@@ -756,9 +771,14 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
         i = __ldg(p.crow + k);
         const float4 rr = __ldg(p.rowrec + int64_t(i) * H + h);   // {s_dst, rowmax, 1/(rowsum+eps), Drow}
         const float z = rr.x + ss;
-        dslope = logit_act_grad<true>(z, slope, act);
-        alpha = expf(logit_act<true>(z, slope, act) - rr.y) * rr.z;
-        if (p.mask) mk = __ldg(p.mask + int64_t(__ldg(p.ceid + k)) * H + h);
+        if (act == B200GAT_LOGIT_HEAD_SOFTMAX) {
+          const float e = head_softmax(reinterpret_cast<const float*>(p.rowrec + int64_t(i) * H), 4, p.s_src + j * H, h, H);
+          alpha = expf(e - rr.y) * rr.z;
+        } else {
+          dslope = logit_act_grad<true>(z, slope, act);
+          alpha = expf(logit_act<true>(z, slope, act) - rr.y) * rr.z;
+        }
+        if (p.drop.active()) mk = dropout_mult(p.drop, dkey, __ldg(p.ceid + k), h, H);
         at = alpha * mk;
         dr = rr.w;
       }
@@ -798,9 +818,13 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
         if (rel >= 0 && rel < U) dot_mine = got;
       }
       if (ok) {
-        const float dz = alpha * (mk * dot_mine - dr) * dslope;
-        gsrc += dz;
-        atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+        if (act == B200GAT_LOGIT_HEAD_SOFTMAX) {
+          p.de[int64_t(k) * H + h] = alpha * (mk * dot_mine - dr);
+        } else {
+          const float dz = alpha * (mk * dot_mine - dr) * dslope;
+          gsrc += dz;
+          atomicAdd(p.g_s_dst + int64_t(i) * H + h, dz);
+        }
       }
     }
     gsrc = group_sum<32>(gsrc);
@@ -977,6 +1001,41 @@ __global__ void __launch_bounds__(256, 4) bwd_finish_kernel(const FinishParams p
   }
 }
 
+// ---- second pass of B200GAT_LOGIT_HEAD_SOFTMAX: e_h = softmax_h(z_h) couples the heads of an edge,
+//     dz_h = e_h (de_h - sum_h' e_h' de_h'),   g_s_src[j,h] += dz_h,   g_s_dst[i,h] += dz_h
+// one thread per CSC entry (its source row j by binary search in colptr: robust to any degree skew), all heads in a loop.
+__global__ void __launch_bounds__(256) head_softmax_bwd_kernel(const EdgeBwdParams p, int64_t num_entries) {
+  const int H = p.H;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < num_entries; k += int64_t(gridDim.x) * blockDim.x) {
+    int64_t lo = 0, hi = p.N;                             // largest j with colptr[j] <= k
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(p.colptr + mid) <= k) lo = mid; else hi = mid;
+    }
+    const int64_t j = lo;
+    const int64_t i = __ldg(p.crow + k);
+    const float* sd = reinterpret_cast<const float*>(p.rowrec + i * H);     // .x of every 16-byte record: stride 4
+    const float* ss = p.s_src + j * H;
+    const float* de = p.de + k * H;
+    float mx = -INFINITY;
+    for (int t = 0; t < H; ++t) mx = fmaxf(mx, __ldg(sd + 4 * t) + __ldg(ss + t));
+    float sum = 0.f, dot = 0.f;
+    for (int t = 0; t < H; ++t) {
+      const float v = expf(__ldg(sd + 4 * t) + __ldg(ss + t) - mx);
+      sum += v;
+      dot = fmaf(v, de[t], dot);
+    }
+    const float inv = 1.f / sum;
+    const float s = dot * inv;                            // sum_h e_h de_h
+    for (int t = 0; t < H; ++t) {
+      const float e = expf(__ldg(sd + 4 * t) + __ldg(ss + t) - mx) * inv;
+      const float dz = e * (de[t] - s);
+      atomicAdd(p.g_s_src + j * H + t, dz);
+      atomicAdd(p.g_s_dst + i * H + t, dz);
+    }
+  }
+}
+
 template <int G, int NV>
 static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t stream) {
   constexpr int GPW = 32 / G;
@@ -989,8 +1048,8 @@ static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t 
   (void)streaming;
   const bool hub = p.nhub > 0;
   if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_bwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
-  else if (p.mask && hub) edge_bwd_kernel<G, NV, true, true><<<blocks, threads, 0, stream>>>(p);
-  else if (p.mask) edge_bwd_kernel<G, NV, true, false><<<blocks, threads, 0, stream>>>(p);
+  else if (p.drop.active() && hub) edge_bwd_kernel<G, NV, true, true><<<blocks, threads, 0, stream>>>(p);
+  else if (p.drop.active()) edge_bwd_kernel<G, NV, true, false><<<blocks, threads, 0, stream>>>(p);
   else if (hub) edge_bwd_kernel<G, NV, false, true><<<blocks, threads, 0, stream>>>(p);
   else edge_bwd_kernel<G, NV, false, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_kernel");
@@ -1087,20 +1146,24 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
 // stage 2: the CSC pass over `rows` source rows.  wh / s_src / gwh / g_s_src are indexed by the LOCAL source row;
 // crow holds GLOBAL destination ids indexing rowrec / g / g_s_dst (identical spaces on a single GPU).
 static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, const int32_t* crow, const int32_t* ceid,
-                   const float* wh, const float* s_src, const float4* rowrec, const float* mask, const float* gsrc_rows,
+                   const float* wh, const float* s_src, const float4* rowrec, const DropoutSpec& drop, const float* gsrc_rows,
                    int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, const int32_t* colend,
-                   const int32_t* hub, int64_t nhub, int64_t max_deg, uint32_t* amax, cudaStream_t stream) {
+                   const int32_t* hub, int64_t nhub, int64_t max_deg, uint32_t* amax, cudaStream_t stream,
+                   float* de = nullptr, int64_t num_entries = 0) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
   p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
   p.colptr = colptr; p.crow = crow; p.ceid = ceid;
-  p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.mask = mask;
+  p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.drop = drop;
   p.g = gsrc_rows; p.ldg = ldg; p.hs = hs;
   p.gwh = gwh; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
   B200GAT_REQUIRE(nhub >= 0 && (nhub == 0 || (hub && colend)), B200GAT_E_NULL, "edge_bwd: hub_cols / colend missing");
   p.hub = hub; p.nhub = nhub; p.colend = nhub > 0 ? colend : colptr + 1;
   p.max_deg = static_cast<int>(max_deg);
   p.amax = amax;
+  p.de = de;
+  B200GAT_REQUIRE(p.act != B200GAT_LOGIT_HEAD_SOFTMAX || de, B200GAT_E_UNSUPPORTED,
+                  "edge_bwd: the across-heads softmax logit activation needs the per-edge scratch buffer (b200gat_edge_bwd only)");
   const int Q = g.Cp / 4;
   const bool streaming = edge_schedule_streaming(span, ldg * 4);
   int rc;
@@ -1122,7 +1185,13 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
   else if (Q <= 64) rc = launch_edge_bwd<32, 2>(p, streaming, stream);
   else rc = launch_edge_bwd<32, 4>(p, streaming, stream);
   if (rc) return rc;
-  return launch_edge_bwd_hub(p, stream);
+  if ((rc = launch_edge_bwd_hub(p, stream))) return rc;
+  if (p.act == B200GAT_LOGIT_HEAD_SOFTMAX && num_entries > 0) {
+    const int64_t want = ceil_div(num_entries, 256), cap = int64_t(sm_count()) * 8;
+    head_softmax_bwd_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(p, num_entries);
+    rc = check_launch("head_softmax_bwd_kernel");
+  }
+  return rc;
 }
 
 // stage 3: gT (fp32 in place, or as the operand split `gsplit` when given) + parameter column sums over `rows` rows
@@ -1205,10 +1274,15 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
                   a->bias && a->workspace, B200GAT_E_NULL, "edge_bwd: NULL pointer");
   B200GAT_REQUIRE(g.concat_like ? (a->out != nullptr) : (a->o_heads != nullptr), B200GAT_E_NULL,
                   "edge_bwd: forward output (out / o_heads) missing");
-  B200GAT_REQUIRE(!a->mask || a->graph.ceid, B200GAT_E_NULL, "edge_bwd: mask needs graph.ceid");
+  DropoutSpec drop;
+  if ((rc = make_dropout(a->mask, a->dropout, &drop))) return rc;
+  B200GAT_REQUIRE(!drop.active() || a->graph.ceid, B200GAT_E_NULL, "edge_bwd: dropout needs graph.ceid");
   B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd: leading dimension < D_out");
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
                   "edge_bwd: wh / g_t / a1 / a2 must be 16-byte aligned");
+  B200GAT_REQUIRE(L.logit_activation != B200GAT_LOGIT_HEAD_SOFTMAX ||
+                  (a->edge_scratch && a->edge_scratch_bytes >= size_t(a->graph.num_edges) * g.H * sizeof(float)),
+                  B200GAT_E_WORKSPACE, "edge_bwd: edge_scratch of E' * H * 4 bytes is required for the across-heads softmax logits");
   const BwdWorkspace w = plan_bwd(L, N);
   B200GAT_REQUIRE(a->workspace_bytes >= w.total, B200GAT_E_WORKSPACE, "edge_bwd: workspace %zu < %zu bytes",
                   a->workspace_bytes, w.total);
@@ -1240,12 +1314,13 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   const float* grows = direct ? a->gout : gp;
   const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
   const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
-  if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, a->mask, grows, ldg, hs,
+  if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, drop, grows, ldg, hs,
                     a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols,
-                    a->graph.max_out_degree, gsplit ? amax : nullptr, stream)))
+                    a->graph.max_out_degree, gsplit ? amax : nullptr, stream, a->edge_scratch, a->graph.num_edges)))
     return rc;
   // giant source rows are accumulated from per-segment partial sums: their maxima are not the maxima of the sums
-  const bool amax_from_csc = gsplit && a->graph.max_out_degree <= B200GAT_GIANT_DEGREE;
+  // (and with the across-heads softmax g_s_src is only complete after the second pass)
+  const bool amax_from_csc = gsplit && a->graph.max_out_degree <= B200GAT_GIANT_DEGREE && L.logit_activation != B200GAT_LOGIT_HEAD_SOFTMAX;
   return run_finish(L, N, a->wh, a->a1, a->a2, g_s_src, g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
                     gsplit, amax, amax_from_csc, stream);
 }
@@ -1282,11 +1357,13 @@ extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* st
   if (a->num_rows == 0) return 0;
   B200GAT_REQUIRE(a->colptr && a->crow && a->wh && a->s_src && a->rowrec && a->g && a->g_wh && a->g_s_src && a->g_s_dst,
                   B200GAT_E_NULL, "edge_bwd_csc: NULL pointer");
-  B200GAT_REQUIRE(!a->mask || a->ceid, B200GAT_E_NULL, "edge_bwd_csc: mask needs ceid");
+  DropoutSpec drop;
+  if ((rc = make_dropout(a->mask, a->dropout, &drop))) return rc;
+  B200GAT_REQUIRE(!drop.active() || a->ceid, B200GAT_E_NULL, "edge_bwd_csc: dropout needs ceid");
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_wh) && aligned16(a->g) && aligned16(a->rowrec) && a->ldg % 4 == 0 &&
                   a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
   return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
-                 reinterpret_cast<const float4*>(a->rowrec), a->mask, a->g, a->ldg, static_cast<int>(a->g_head_stride),
+                 reinterpret_cast<const float4*>(a->rowrec), drop, a->g, a->ldg, static_cast<int>(a->g_head_stride),
                  a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, nullptr, stream);
 }
 

@@ -31,7 +31,8 @@ struct EdgeFwdParams {
   int H, C, Cp, Dp;
   float slope; int act;
   const int32_t* rowptr; const int32_t* col; const int32_t* eid;
-  const float* wh; const float* s_src; const float* s_dst; const float* bias; const float* mask;
+  const float* wh; const float* s_src; const float* s_dst; const float* bias;
+  DropoutSpec drop;   // attention dropout (GAT.py:61): mask tensor or in-kernel Philox (common.cuh)
   float* out; int64_t ldo;
   float* rowmax; float* rowsum; float* o_heads;
   int heads_mode;   // 1: write per-head aggregate to o_heads (mean over heads done by head_mean_kernel)
@@ -64,6 +65,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   int off[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) off[v] = 4 * ((gl + v * G < Q) ? gl + v * G : Q - 1);
+  const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
 
   float amax = 0.f;
   for (int64_t base = warp * GPW; base < p.items; base += nwarps * GPW) {
@@ -113,7 +115,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         };
         load_batch(0);
         float e = -INFINITY;
-        if (ok) e = logit_act<GENERIC>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
+        if (ok) e = logit_act<GENERIC>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);   // (!HAS_MASK path: never GENERIC)
         const float m_new = fmaxf(m, group_max<G>(e));
         if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
           const float scale = expf(m - m_new);
@@ -151,7 +153,8 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         float e = -INFINITY;
         if (ok) {
           j = __ldg(p.col + k);
-          e = logit_act<GENERIC>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
+          if constexpr (GENERIC) e = edge_logit<true>(p.s_dst + i * H, p.s_src + int64_t(j) * H, sd, h, H, slope, act);
+          else e = leaky(sd + __ldg(ssrc_h + int64_t(j) * H), slope);
         }
         const float m_new = fmaxf(m, group_max<G>(e));
         if (k0 > 0 && m_new != m) {           // group-uniform; exp(-inf) = 0 covers the "nothing accumulated yet" case
@@ -167,7 +170,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
         if (ok) {
           pp = expf(e - m);
           pm = pp;
-          if (HAS_MASK && (!GENERIC || p.mask)) pm *= __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h);
+          if (HAS_MASK && (!GENERIC || p.drop.active())) pm *= dropout_mult(p.drop, dkey, __ldg(p.eid + k), h, H);
         }
         l += pp;
         const int cnt = (maxdeg - k0) < G ? (maxdeg - k0) : G;
@@ -285,7 +288,7 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_fwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
-  else if (p.mask) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+  else if (p.drop.active()) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
   else if (streaming && G >= 16) edge_fwd_stream_kernel<(G >= 16 ? G : 32), (G >= 16 ? NV : 1)><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_kernel");
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
   int off[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) off[v] = 4 * ((lane + v * 32 < Q) ? lane + v * 32 : Q - 1);
+  const DropoutKey dkey = dropout_key(p.drop);
   float amax = 0.f;
   for (int64_t item = blockIdx.x; item < p.nhub * H; item += gridDim.x) {
     const int64_t i = __ldg(p.hub + item / H);
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
       float e = -INFINITY;
       if (ok) {
         j = __ldg(p.col + k);
-        e = logit_act<true>(sd + __ldg(ssrc_h + int64_t(j) * H), slope, act);
+        e = edge_logit<true>(p.s_dst + i * H, p.s_src + int64_t(j) * H, sd, h, H, slope, act);
       }
       const float m_new = fmaxf(m, group_max<32>(e));
       if (m_new != m) {                                   // exp(-inf) = 0 covers the first chunk
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
       float pp = 0.f, pm = 0.f;
       if (ok) {
         pp = expf(e - m);
-        pm = p.mask ? pp * __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h) : pp;
+        pm = p.drop.active() ? pp * dropout_mult(p.drop, dkey, __ldg(p.eid + k), h, H) : pp;
       }
       l += pp;
       const int cnt = (end - k0) < 32 ? (end - k0) : 32;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_max_kernel(const EdgeFwdPa
   const float sd = __ldg(p.s_dst + i * H + h);
   float m = -INFINITY;
   for (int k = kbeg + threadIdx.x; k < kend; k += 256)
-    m = fmaxf(m, logit_act<true>(sd + __ldg(p.s_src + int64_t(__ldg(p.col + k)) * H + h), p.slope, p.act));
+    m = fmaxf(m, edge_logit<true>(p.s_dst + i * H, p.s_src + int64_t(__ldg(p.col + k)) * H, sd, h, H, p.slope, p.act));
   m = group_max<32>(m);
   if (lane == 0) sm_m[w] = m;
   __syncthreads();
@@ -506,6 +510,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdPa
   const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
   const float sd = __ldg(p.s_dst + i * H + h);
   const float M = p.rowmax[i * H + h];                    // final: written by edge_fwd_giant_max_kernel
+  const DropoutKey dkey = dropout_key(p.drop);
   const char* wb[NV];
   float4 acc[NV];
 #pragma unroll
@@ -521,8 +526,8 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdPa
     float pp = 0.f, pm = 0.f;
     if (ok) {
       j = __ldg(p.col + k);
-      pp = expf(logit_act<true>(sd + __ldg(p.s_src + int64_t(j) * H + h), p.slope, p.act) - M);
-      pm = p.mask ? pp * __ldg(p.mask + int64_t(__ldg(p.eid + k)) * H + h) : pp;
+      pp = expf(edge_logit<true>(p.s_dst + i * H, p.s_src + int64_t(j) * H, sd, h, H, p.slope, p.act) - M);
+      pm = p.drop.active() ? pp * dropout_mult(p.drop, dkey, __ldg(p.eid + k), h, H) : pp;
     }
     l += pp;
     const int cnt = (kend - k0) < 32 ? (kend - k0) : 32;
@@ -657,6 +662,7 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
     wb[v] = reinterpret_cast<const char*>(p.wh + off[v]);
   }
 
+  const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
   float amax = 0.f;
   for (int64_t base = warp * GPW; base < p.N; base += nwarps * GPW) {
     const bool valid = base + gi < p.N;
@@ -683,13 +689,13 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
       float e[HH];
 #pragma unroll
       for (int h = 0; h < HH; ++h) e[h] = -INFINITY;
-      const float* mrow = nullptr;
+      int eid_k = 0;
       if (ok) {
         j = __ldg(p.col + k);
         const float* sj = p.s_src + int64_t(j) * HH;
 #pragma unroll
         for (int h = 0; h < HH; ++h) e[h] = leaky(sd[h] + __ldg(sj + h), slope);
-        if (HAS_MASK) mrow = p.mask + int64_t(__ldg(p.eid + k)) * HH;
+        if (HAS_MASK) eid_k = __ldg(p.eid + k);
       }
       js[gl] = j;
 #pragma unroll
@@ -704,7 +710,7 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
         float pp = 0.f, pm = 0.f;
         if (ok) {
           pp = expf(e[h] - m_new);
-          pm = HAS_MASK ? pp * __ldg(mrow + h) : pp;
+          pm = HAS_MASK ? pp * dropout_mult(p.drop, dkey, eid_k, h, HH) : pp;
         }
         l[h] += pp;
         ps[gl * HH + h] = pm;
@@ -805,7 +811,7 @@ static int launch_edge_fwd_row(const EdgeFwdParams& p, bool streaming, cudaStrea
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   (void)streaming;                                        // only dispatched for streaming graphs (see b200gat_edge_fwd)
-  if (p.mask) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.drop.active()) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_row_kernel");
 }
@@ -842,7 +848,9 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->wh && a->s_src && a->s_dst && a->bias && a->out && a->rowmax && a->rowsum, B200GAT_E_NULL,
                   "edge_fwd: NULL pointer");
   B200GAT_REQUIRE(!heads_mode || a->o_heads, B200GAT_E_NULL, "edge_fwd: o_heads is required when !concat && heads > 1");
-  B200GAT_REQUIRE(!a->mask || a->graph.eid, B200GAT_E_NULL, "edge_fwd: mask needs graph.eid");
+  DropoutSpec drop;
+  if ((rc = make_dropout(a->mask, a->dropout, &drop))) return rc;
+  B200GAT_REQUIRE(!drop.active() || a->graph.eid, B200GAT_E_NULL, "edge_fwd: dropout needs graph.eid");
   B200GAT_REQUIRE(a->ldo >= d_out, B200GAT_E_SHAPE, "edge_fwd: ldo < D_out");
   B200GAT_REQUIRE(aligned16(a->wh) && (!heads_mode || aligned16(a->o_heads)), B200GAT_E_ALIGN,
                   "edge_fwd: wh / o_heads must be 16-byte aligned");
@@ -853,7 +861,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   p.H = H; p.C = C; p.Cp = Cp; p.Dp = H * Cp;
   p.slope = L.negative_slope; p.act = L.logit_activation;
   p.rowptr = a->graph.rowptr; p.col = a->graph.col; p.eid = a->graph.eid;
-  p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.bias = a->bias; p.mask = a->mask;
+  p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.bias = a->bias; p.drop = drop;
   p.out = a->out; p.ldo = a->ldo; p.rowmax = a->rowmax; p.rowsum = a->rowsum; p.o_heads = a->o_heads;
   p.heads_mode = heads_mode ? 1 : 0;
   p.vec_out = (!heads_mode && C % 4 == 0 && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;
@@ -901,4 +909,30 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
     rc = check_launch("head_mean_kernel");
   }
   return rc;
+}
+
+// ---- the in-kernel dropout multipliers as a tensor (include/b200gat.h: b200gat_dropout_mask) ----
+namespace b200gat {
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const DropoutSpec d, int64_t total, int H, float* __restrict__ out) {
+  const DropoutKey key = dropout_key(d);
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = t / H;
+    out[t] = dropout_mult(d, key, static_cast<int>(e), static_cast<int>(t - e * H), H);
+  }
+}
+}  // namespace b200gat
+
+extern "C" int b200gat_dropout_mask(const b200gat_dropout* d, int64_t num_edges, int64_t heads, float* mask, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200GAT_REQUIRE(d && mask, B200GAT_E_NULL, "dropout_mask: NULL pointer");
+  B200GAT_REQUIRE(num_edges >= 0 && heads > 0 && num_edges < (int64_t(1) << 31), B200GAT_E_SHAPE, "dropout_mask: bad sizes");
+  DropoutSpec spec;
+  int rc = make_dropout(nullptr, *d, &spec);
+  if (rc) return rc;
+  B200GAT_REQUIRE(spec.active(), B200GAT_E_SHAPE, "dropout_mask: p must be > 0");
+  const int64_t total = num_edges * heads;
+  if (total == 0) return 0;
+  const int64_t want = ceil_div(total, 256), cap = int64_t(sm_count()) * 8;
+  dropout_mask_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(spec, total, static_cast<int>(heads), mask);
+  return check_launch("dropout_mask_kernel");
 }

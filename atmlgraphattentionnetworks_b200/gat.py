@@ -62,6 +62,22 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def dropout_mask_tensor(p, seed, num_edges, heads):
+    """The keep-multipliers the kernels generate for (p, seed) as an [E', H] tensor in ORIGINAL edge order
+    (b200gat_dropout_mask) — for tests and debugging; the training path never materialises it."""
+    out = torch.empty((int(num_edges), int(heads)), dtype=torch.float32, device=seed.device)
+    with torch.cuda.device(seed.device):
+        d = _abi.dropout_struct((p, seed))
+        _abi.check(_abi.lib().b200gat_dropout_mask(ctypes.byref(d), int(num_edges), int(heads), out.data_ptr(),
+                                                   torch.cuda.current_stream(seed.device).cuda_stream), "b200gat_dropout_mask")
+    return out
+
+
+def _split_mask(mask):
+    """mask argument of the stage functions -> (tensor or None, (p, seed) or None)"""
+    return (None, mask) if isinstance(mask, tuple) else (mask, None)
+
+
 class GATLayerFunction(torch.autograd.Function):
     """x [N,F], bias [D_out], the layer's persistent packed parameter storage `packed` = (W [Dp,F], bw/a1/a2 [Dp],
     b1/b2 [H]; the per-head parameters are views of it) and the 6H per-head parameters themselves (*params, in the
@@ -78,6 +94,9 @@ class GATLayerFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, bias, graph, geom, mask, fuse, packed, *params):
+        # mask: None | [E', H] keep-multiplier tensor (parity tests) | (p, seed int64[2] device tensor): in-kernel Philox
+        drop = mask if isinstance(mask, tuple) else None
+        mask = None if drop is not None else mask
         w, bw, a1, a2, b1, b2 = packed
         f_in, c, h, concat = geom
         act_in, act_out, x_amax, logit = fuse
@@ -114,10 +133,11 @@ class GATLayerFunction(torch.autograd.Function):
             _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
             ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
                                   bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
-                                  rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr())
+                                  rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr(), _abi.dropout_struct(drop))
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
         ctx.graph, ctx.geom, ctx.mask, ctx.act, ctx.logit = graph, geom, mask, (bool(act_in), bool(act_out)), logit
+        ctx.drop = drop
         # the kernels read the packed storage through raw pointers and the per-head Parameters alias it through `.data =`,
         # which does not share version counters: remember the Parameters' versions so that an in-place update between this
         # forward and its backward (optimizer.step, load_state_dict, ...) is an error, as it is in the reference
@@ -163,6 +183,9 @@ class GATLayerFunction(torch.autograd.Function):
             # gT goes straight into the tensor-core operand format when the projection backward runs there
             gs_bytes = int(lib.b200gat_edge_bwd_split_bytes(ctypes.byref(layer), n))
             g_split = _workspace(gs_bytes, dev) if gs_bytes else None
+            # the across-heads softmax logits couple the heads of an edge in the backward: the one variant with a per-edge
+            # scratch buffer ([E', H] floats, include/b200gat.h)
+            scratch = (_workspace(graph.num_edges * h * 4, dev) if ctx.logit[0] == _abi.LOGIT_HEAD_SOFTMAX else None)
             ea = _abi.EdgeBwdArgs(layer, graph.c_struct(), gout.data_ptr(), d_out,
                                   None if heads_mode else fwd_out.data_ptr(), d_out,
                                   fwd_out.data_ptr() if heads_mode else None, bias.data_ptr(),
@@ -170,7 +193,8 @@ class GATLayerFunction(torch.autograd.Function):
                                   rowsum.data_ptr(), _ptr(mask), a1.data_ptr(), a2.data_ptr(),
                                   g_t.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(), g_a2.data_ptr(),
                                   g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes,
-                                  _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g_split), gs_bytes)
+                                  _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g_split), gs_bytes,
+                                  _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
             ws2 = _workspace(ws2_bytes, dev)
@@ -290,16 +314,19 @@ class GraphAttentionLayer(torch.nn.Module):
         return w.reshape(h * (c + pad), -1), bw.reshape(-1), a1.reshape(-1), a2.reshape(-1), b1, b2
 
     def _dropout_mask(self, num_edges, device):
-        """GAT.py:61: F.dropout on the [E', H] coefficients (original edge order), scaled 1/(1-p), not renormalised."""
+        """GAT.py:61: F.dropout on the [E', H] coefficients (original edge order), scaled 1/(1-p), not renormalised.
+        -> None (eval / p == 0), the hook's [E', H] tensor (parity tests: the reference's own masks), or (p, seed): the
+        kernels generate the mask themselves (Philox keyed on (seed, edge, head), include/b200gat.h b200gat_dropout) —
+        forward and backward regenerate the same bits and no [E', H] tensor is ever allocated.  The two seed words are drawn
+        on the device from torch's CUDA generator (torch.manual_seed applies; capturable in a CUDA graph)."""
         if self.mask_hook is not None:
             return self.mask_hook((num_edges, self.num_heads)).to(device=device, dtype=torch.float32).contiguous()
         p = float(self.dropout_val)
         if not self.training or p <= 0.0:
             return None
-        if p >= 1.0:
-            return torch.zeros((num_edges, self.num_heads), dtype=torch.float32, device=device)
-        keep = torch.rand((num_edges, self.num_heads), device=device) >= p
-        return keep.to(torch.float32).mul_(1.0 / (1.0 - p))
+        seed = torch.randint(-2 ** 63, 2 ** 63 - 1, (2,), dtype=torch.int64, device=device)
+        self._last_dropout_seed = seed
+        return (min(p, 1.0), seed)
 
     def forward(self, x, edge_index, graph=None):
         """GAT.py:37 — forward(x, edge_index) -> [N, H*C] (concat) or [N, C]."""
@@ -345,11 +372,14 @@ def _logit_code(fn):
     if isinstance(fn, torch.nn.Tanh):
         return _abi.LOGIT_TANH, NEGATIVE_SLOPE
     if isinstance(fn, torch.nn.Softmax):
-        raise NotImplementedError(
-            "nn.Softmax() on the [E', H] logits normalises ACROSS THE HEADS of one edge (implicit dim=1; with one head "
-            "it degenerates to uniform attention): it couples the heads and is not offered by the fused kernels")
+        # run_act_func_experiment.py:111 passes nn.Softmax() (dim=None): on the 2-D [E', H] logit tensor torch's implicit
+        # choice is dim=1, i.e. a softmax ACROSS THE HEADS of one edge (uniform attention with one head)
+        if fn.dim not in (None, 1, -1):
+            raise NotImplementedError("nn.Softmax(dim=0) on the [E', H] logits would normalise over ALL edges of the graph; "
+                                      "only the across-heads form the reference's experiment runs (dim None / 1 / -1) is offered")
+        return _abi.LOGIT_HEAD_SOFTMAX, NEGATIVE_SLOPE
     raise NotImplementedError(f"logit activation {type(fn).__name__} is not offered by the fused kernels "
-                              "(LeakyReLU, LogSigmoid, Tanh are)")
+                              "(LeakyReLU, LogSigmoid, Tanh, Softmax are)")
 
 
 class GraphAttentionLayerActivationTest(GraphAttentionLayer):

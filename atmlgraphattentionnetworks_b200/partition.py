@@ -20,12 +20,12 @@ import torch
 import torch.distributed as dist
 
 from . import _abi
-from .gat import _call, _layer_struct, _ptr, _timed, _workspace
+from .gat import _call, _layer_struct, _ptr, _split_mask, _timed, _workspace
 
 
 # ------------------------------------------------------------------------------------------------ graph partition
 class RowPartition:
-    __slots__ = ("num_nodes", "world", "rank", "block", "lo", "hi", "rowptr", "col", "eid", "colptr", "crow", "ceid",
+    __slots__ = ("num_nodes", "num_input_edges", "world", "rank", "block", "lo", "hi", "rowptr", "col", "eid", "colptr", "crow", "ceid",
                  "hub_rows", "hub_cols", "rowend", "colend", "max_in_degree", "max_out_degree", "_struct")
 
     @property
@@ -74,7 +74,7 @@ def build_row_partition(edge_index, num_nodes, world, rank):
     colptr, crow, ceid = build(s_src - lo, s_dst, s_pos)
 
     p = RowPartition()
-    p.num_nodes, p.world, p.rank, p.block, p.lo, p.hi = n, world, rank, b, lo, hi
+    p.num_nodes, p.num_input_edges, p.world, p.rank, p.block, p.lo, p.hi = n, e, world, rank, b, lo, hi
     p.rowptr, p.col, p.eid, p.colptr, p.crow, p.ceid = rowptr, col, eid, colptr, crow, ceid
     p._struct = None
     # scheduling by degree (include/b200gat.h: b200gat_graph.hub_rows): own rows / columns longer than HUB_DEGREE
@@ -175,9 +175,10 @@ def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask):
     rowsum = torch.empty((n, h), **f32)
     o_heads = torch.empty((n, dp), **f32) if heads_mode else None
     stream = torch.cuda.current_stream(dev).cuda_stream
+    mask, drop = _split_mask(mask)      # [E', H] tensor in ORIGINAL (global) edge order, or (p, seed): in-kernel Philox
     ea = _abi.EdgeFwdArgs(layer, part.c_struct(), wh_full.data_ptr(), s_src_full.data_ptr(), s_dst_own.data_ptr(),
                           bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(), rowsum.data_ptr(),
-                          _ptr(o_heads))
+                          _ptr(o_heads), None, _abi.dropout_struct(drop))
     _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
     return out, rowmax, rowsum, o_heads
 
@@ -233,12 +234,13 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
     g_s_src = torch.empty((n, h), **f32)
     g_s_dst_full = torch.zeros((part.padded_rows, h), **f32)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    mask, drop = _split_mask(mask)
     ca = _abi.EdgeBwdCscArgs(layer, n, part.colptr.data_ptr(), part.crow.data_ptr(), part.ceid.data_ptr(),
                              wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
                              g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
                              part.num_nodes, part.hub_cols.data_ptr() if part.hub_cols.numel() else None,
                              int(part.hub_cols.numel()), part.colend.data_ptr() if part.hub_cols.numel() else None,
-                             part.max_out_degree)
+                             part.max_out_degree, _abi.dropout_struct(drop))
     _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
     return g_wh, g_s_src, g_s_dst_full
 
@@ -348,13 +350,23 @@ class PartitionedGATFunction(torch.autograd.Function):
 
 
 def partitioned_layer_forward(layer, x_own, part, group=None):
-    """Run a GraphAttentionLayer module on the own block of a row-partitioned graph (dropout masks: not yet
-    supported in partitioned mode — the reference trains the large configs with dropout disabled in the bench)."""
-    if layer.training and float(layer.dropout_val) > 0.0:
-        raise NotImplementedError("attention dropout in row-partitioned mode")
+    """Run a GraphAttentionLayer module on the own block of a row-partitioned graph.  Attention dropout (GAT.py:61) is
+    generated inside the kernels from (seed, ORIGINAL edge position, head): every rank uses rank 0's two seed words (one
+    16-byte broadcast), so an edge gets the same multiplier in the forward of the rank owning its destination and in the
+    backward of the rank owning its source — as on one GPU with the same seed."""
+    mask = None
+    if layer.mask_hook is not None:
+        mask = layer.mask_hook((part.num_nodes + part.num_input_edges, layer.num_heads)).to(device=x_own.device,
+                                                                                          dtype=torch.float32).contiguous()
+    elif layer.training and float(layer.dropout_val) > 0.0:
+        seed = torch.randint(-2 ** 63, 2 ** 63 - 1, (2,), dtype=torch.int64, device=x_own.device)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(seed, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        layer._last_dropout_seed = seed
+        mask = (min(float(layer.dropout_val), 1.0), seed)
     w, bw, a1, a2, b1, b2 = layer._packed()
     geom = (layer.input_channels, layer.output_channels, layer.num_heads, bool(layer.concat))
-    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, None, group,
+    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group,
                                         _peer_buffer(layer, geom, part, x_own, group))
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 10
+#define B200GAT_ABI_VERSION 11
 
 enum {
   B200GAT_OK = 0,
@@ -95,9 +95,22 @@ typedef struct {
 } b200gat_layer;
 
 /* Logit activations.  GAT.py:30 fixes LeakyReLU(0.2); run_act_func_experiment.py:15,111 runs the same layer with
- * LogSigmoid and Tanh (its third variant, nn.Softmax() over the head axis, couples the heads of an edge and is not
- * offered by the fused kernels). */
-enum { B200GAT_LOGIT_LEAKY_RELU = 0, B200GAT_LOGIT_LOGSIGMOID = 1, B200GAT_LOGIT_TANH = 2 };
+ * LogSigmoid, Tanh and nn.Softmax().  The last one is applied to the [E', H] logit tensor with no `dim`, i.e. ACROSS THE
+ * HEADS of one edge (B200GAT_LOGIT_HEAD_SOFTMAX; uniform attention with one head): every (row, head) work item computes
+ * all H logits of its edges in the forward; its backward couples the heads of an edge, so b200gat_edge_bwd runs it in two
+ * passes through a per-edge scratch buffer (b200gat_edge_bwd_args.edge_scratch) — the only variant that has one. */
+enum { B200GAT_LOGIT_LEAKY_RELU = 0, B200GAT_LOGIT_LOGSIGMOID = 1, B200GAT_LOGIT_TANH = 2, B200GAT_LOGIT_HEAD_SOFTMAX = 3 };
+
+/* Attention dropout (GAT.py:61: F.dropout on the [E', H] coefficients, scaled 1/(1-p), NOT renormalised).  The keep-
+ * multiplier of coefficient (edge e, head h) — e = position in the ORIGINAL [edges ; loops] order — has two sources:
+ *   the `mask` tensor of the args structs, if given (parity tests: the reference's own masks), else
+ *   p > 0: generated INSIDE the kernels — Philox4x32-10, key = seed[0], counter = (e, h / 4, seed[1]), word h % 4, keep
+ *   iff word >= p * 2^32, multiplier 1/(1-p).  Forward (CSR order) and backward (CSC order) regenerate the identical value
+ *   from (seed, e, h); no [E', H] tensor exists.  `seed` is a DEVICE pointer to two uint64 words read by the kernels, so a
+ *   captured CUDA graph draws a fresh mask on every replay once the caller's RNG kernel (inside the graph) rewrites them.
+ * b200gat_dropout_mask() writes the same multipliers as a tensor (tests: Philox mode == tensor mode, statistics). */
+typedef struct { float p; float reserved; const uint64_t* seed; } b200gat_dropout;
+int b200gat_dropout_mask(const b200gat_dropout* d, int64_t num_edges, int64_t heads, float* mask /* out [E', H] */, void* stream);
 
 int b200gat_abi_version(void);
 /* number of kernels this library has launched in the process so far (its own kernels; CUB sort passes excluded) */
@@ -165,6 +178,7 @@ typedef struct {
   float* rowmax; float* rowsum;   /* out [N, H]: softmax statistics kept for the recomputing backward */
   float* o_heads;                 /* out [N, Dp]; required iff !concat && H > 1 (per-head aggregate) */
   uint32_t* out_amax;             /* optional out: device word <- bit pattern of max|out| (for the next layer's x_amax) */
+  b200gat_dropout dropout;        /* in-kernel attention dropout, used when mask == NULL and dropout.p > 0 */
 } b200gat_edge_fwd_args;
 int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream);
 
@@ -190,6 +204,9 @@ typedef struct {
   void* g_t_split; size_t g_t_split_bytes;   /* optional out: gT as the tensor-core operand split consumed by
                                          b200gat_proj_bwd (b200gat_edge_bwd_split_bytes() bytes, 256-byte aligned).
                                          When given, g_t is scratch (it holds the un-finished gWh on return) */
+  b200gat_dropout dropout;            /* as in the forward (same p and seed words => the same mask) */
+  float* edge_scratch; size_t edge_scratch_bytes;   /* B200GAT_LOGIT_HEAD_SOFTMAX only: E' * H * 4 bytes (d loss / d e per
+                                         CSC entry and head, consumed by the second pass); NULL otherwise */
 } b200gat_edge_bwd_args;
 size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of a g_t_split buffer; 0 when the projection backward of this geometry runs on the CUDA-core path */
@@ -232,6 +249,7 @@ typedef struct {
   const int32_t* hub_cols; int64_t num_hub_cols;   /* own source rows with out-degree > B200GAT_HUB_DEGREE (or NULL / 0) */
   const int32_t* colend;              /* [rows] as b200gat_graph.colend (required when num_hub_cols > 0) */
   int64_t max_out_degree;             /* as b200gat_graph.max_out_degree for the own source rows */
+  b200gat_dropout dropout;            /* as in the forward; ceid required (global original edge positions) */
 } b200gat_edge_bwd_csc_args;
 int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
 

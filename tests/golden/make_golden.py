@@ -60,8 +60,14 @@ ACT_CASES = [
     ("logsigmoid_h1c7_mean", 80, 400, 64, 7, 1, False, 0.0, "log_sigmoid"),
     ("tanh_h4c16_mean", 90, 600, 20, 16, 4, False, 0.0, "tanh"),
     ("tanh_h2c64_cat", 100, 900, 40, 64, 2, True, 0.0, "tanh"),
+    # the experiment's third variant, nn.Softmax() on the [E', H] logits: implicit dim = 1, i.e. ACROSS THE HEADS of an edge
+    ("softmax_h8c8_cat_drop", 120, 700, 33, 8, 8, True, 0.6, "softmax"),
+    ("softmax_h4c16_mean", 90, 600, 20, 16, 4, False, 0.0, "softmax"),
+    ("softmax_h2c64_cat", 100, 900, 40, 64, 2, True, 0.0, "softmax"),
+    ("softmax_h1c7_mean", 80, 400, 64, 7, 1, False, 0.0, "softmax"),      # one head: every logit becomes 1 (uniform attention)
+    ("softmax_hub_h3c8_cat", 400, 6000, 12, 8, 3, True, 0.0, "softmax"),  # hub destination / source (> 512 edges)
 ]
-ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh}
+ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh, "softmax": torch.nn.Softmax}
 
 
 def make_graph(name, n, e, special, gen):
@@ -192,22 +198,26 @@ def run_net(ref_net, dataset, f, n, e, graphs, seed, classes=7):
 
 def main():
     ref_gat, ref_net = ref_loader.load()
-    for case in HUBREF_CASES:
+    for case in ([] if "--only-act-softmax" in sys.argv else HUBREF_CASES):
         rec = run_layer(ref_gat, case)
         np.savez_compressed(os.path.join(HERE, f"hubref_{case[0]}.npz"), **rec)
         print("hubref", case[0], {k: v.shape for k, v in rec.items() if k in ("x", "edge_index", "out_f32")})
     if "--only-hubref" in sys.argv:
         return
-    for case in LAYER_CASES:
+    for case in ([] if "--only-act-softmax" in sys.argv else LAYER_CASES):
         rec = run_layer(ref_gat, case)
         np.savez_compressed(os.path.join(HERE, f"layer_{case[0]}.npz"), **rec)
         print("layer", case[0], {k: v.shape for k, v in rec.items() if k in ("x", "edge_index", "out_f32")})
     ref_act = ref_loader.load_act_experiment()
     for (name, n, e, f, c, h, concat, p, act) in ACT_CASES:
-        rec = run_layer(ref_act, (name, n, e, f, c, h, concat, p, ""), act=act)
+        if "--only-act-softmax" in sys.argv and act != "softmax":
+            continue
+        rec = run_layer(ref_act, (name, n, e, f, c, h, concat, p, "hubs" if "_hub_" in name else ""), act=act)
         rec["activation"] = np.array(act)
         np.savez_compressed(os.path.join(HERE, f"actlayer_{name}.npz"), **rec)
         print("actlayer", name, act)
+    if "--only-act-softmax" in sys.argv:
+        return
     np.savez_compressed(os.path.join(HERE, "net_cora.npz"), **run_net(ref_net, "Cora", 37, 150, 700, 0, 11))
     np.savez_compressed(os.path.join(HERE, "net_cifar_f3.npz"), **run_net(ref_net, "CIFAR10", 3, 160, 1280, 8, 12))
     np.savez_compressed(os.path.join(HERE, "net_pubmed.npz"), **run_net(ref_net, "Pubmed", 21, 130, 600, 0, 13, classes=3))

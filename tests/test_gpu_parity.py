@@ -432,13 +432,14 @@ def test_stack_with_fused_activation_matches_cpu_oracle(case):
 
 
 # ------------------------------------------ logit-activation variants (run_act_func_experiment.py:13-74,111) vs the oracle
-@pytest.mark.parametrize("act_name", ["log_sigmoid", "tanh", "leaky_0.05"])
+@pytest.mark.parametrize("act_name", ["log_sigmoid", "tanh", "leaky_0.05", "head_softmax"])
 @pytest.mark.parametrize("geom", [(1500, 20000, 40, 8, 8, True, 0.6), (2000, 30000, 50, 256, 2, True, 0.0),
                                   (1200, 9000, 64, 7, 1, False, 0.0)], ids=["8x8_drop", "2x256", "1x7_mean"])
 def test_activation_experiment_layer_matches_cpu_oracle(act_name, geom):
     from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest
     from oracle.gat_port import PortGraphAttentionLayer
-    make = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh, "leaky_0.05": lambda: torch.nn.LeakyReLU(0.05)}[act_name]
+    make = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh, "leaky_0.05": lambda: torch.nn.LeakyReLU(0.05),
+            "head_softmax": lambda: torch.nn.Softmax(dim=1)}[act_name]
     n, e, f, c, h, concat, p = geom
     gen = torch.Generator().manual_seed(n + e)
     torch.manual_seed(2)
@@ -477,7 +478,110 @@ def test_activation_experiment_layer_matches_cpu_oracle(act_name, geom):
         assert nerr(got[k], want[k]) <= max(FP32_TOL, 4.0 * floor), (k, nerr(got[k], want[k]), floor)
 
 
-def test_activation_experiment_rejects_head_softmax():
+def test_activation_experiment_rejects_softmax_over_all_edges():
     from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest
     with pytest.raises(NotImplementedError):
-        GraphAttentionLayerActivationTest(8, 8, num_heads=2, activation_function=torch.nn.Softmax())
+        GraphAttentionLayerActivationTest(8, 8, num_heads=2, activation_function=torch.nn.Softmax(dim=0))
+    GraphAttentionLayerActivationTest(8, 8, num_heads=2, activation_function=torch.nn.Softmax())      # the reference's form
+
+
+# ------------------------------------------ in-kernel attention dropout (GAT.py:61): Philox keyed on (seed, edge, head)
+PHILOX_CASES = [
+    # name, N, E, F, C, H, concat, hub, force_stream, activation
+    ("cora_l1_8x8", 2708, 10556, 143, 8, 8, True, False, False, None),
+    ("cora_l2_1x7_mean", 2708, 10556, 64, 7, 1, False, False, False, None),
+    ("pubmed_l2_8x3_mean", 1500, 9000, 64, 3, 8, False, False, False, None),
+    ("wide_4x256", 1500, 20000, 50, 256, 4, True, False, False, None),
+    ("hub_giant_2x64", 2000, 30000, 50, 64, 2, True, True, False, None),
+    ("stream_row_wide_4x32_hub", 2000, 30000, 40, 32, 4, True, True, True, None),
+    ("stream_mean_h6c100_hub", 1500, 30000, 40, 100, 6, False, True, True, None),
+    ("tanh_8x8", 1500, 20000, 40, 8, 8, True, False, False, "tanh"),
+]
+
+
+@pytest.mark.parametrize("case", PHILOX_CASES, ids=lambda c: c[0])
+def test_in_kernel_dropout_equals_the_same_mask_supplied_as_a_tensor(case):
+    """Training mode draws NO [E', H] tensor: the kernels regenerate the keep-multipliers from (seed, original edge
+    position, head) in the forward (CSR order) and in the backward (CSC order).  Materialising the same multipliers with
+    b200gat_dropout_mask and feeding them through the mask-tensor path — the one pinned against the reference's own masks —
+    must give the same outputs and gradients in every kernel variant."""
+    import GAT
+    from atmlgraphattentionnetworks_b200.gat import GraphAttentionLayerActivationTest, dropout_mask_tensor
+    from atmlgraphattentionnetworks_b200.graph import GraphCache
+    name, n, e, f, c, h, concat, hub, force_stream, act = case
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    torch.manual_seed(5)
+    if act:
+        layer = GraphAttentionLayerActivationTest(f, c, num_heads=h, concat=concat, dropout=0.6,
+                                                  activation_function=ACTIVATIONS[act]())
+    else:
+        layer = GAT.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=0.6)
+    layer = layer.to(DEV).train()
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    if hub:
+        ei[1, : e // 4] = 11
+        ei[0, e // 4: e // 2] = 13
+        ei[1, e // 2: e // 2 + 900] = 17
+        ei[0, e // 2 + 900: e // 2 + 1800] = 19
+    eig = ei.to(DEV)
+    x = torch.randn(n, f, generator=gen).to(DEV)
+    gout = torch.randn(n, h * c if concat else c, generator=gen).to(DEV)
+    layer.graph_cache = GraphCache()
+    if force_stream:
+        layer.graph_cache.get(eig, n).c_struct().span = 1 << 40
+
+    def run():
+        layer.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        out = layer(xg, eig)
+        out.backward(gout)
+        res = packed_grads(layer, xg.grad)
+        res["out"] = out.detach().cpu().numpy()
+        return res
+    assert isinstance(layer._dropout_mask(e + n, torch.device(DEV)), tuple)       # (p, seed): no [E', H] tensor
+    got = run()
+    seed = layer._last_dropout_seed
+    mask = dropout_mask_tensor(0.6, seed, e + n, h)
+    keep = float((mask != 0).float().mean())
+    assert abs(keep - 0.4) < 4 * (0.24 / mask.numel()) ** 0.5 + 1e-3, keep
+    layer.mask_hook = lambda shape: mask
+    want = run()
+    # same multipliers => same arithmetic; only the order of the float atomics (g_s_dst, and the segment sums of giant
+    # rows) differs from run to run
+    tol = 2e-5 if hub else 2e-6
+    for k in ("out",) + GRAD_KEYS:
+        assert nerr(got[k], want[k]) <= tol, (k, nerr(got[k], want[k]))
+    layer.mask_hook = None
+    again = run()                                              # a new forward draws new seed words
+    assert not torch.equal(layer._last_dropout_seed, seed) and nerr(again["out"], got["out"]) > 1e-3
+
+
+def test_in_kernel_dropout_statistics():
+    """keep-rate 1 - p within 4 sigma overall and per head, multiplier exactly 1 / (1 - p), independent of the seed's
+    neighbours, p = 1 drops everything, and the same (seed, edge, head) always gives the same value."""
+    from atmlgraphattentionnetworks_b200.gat import dropout_mask_tensor
+    ep, h = 200_000, 8
+    seeds = torch.tensor([[123456789, 987654321], [123456790, 987654321], [-5, 2 ** 62]], dtype=torch.int64, device=DEV)
+    masks = []
+    for p in (0.6, 0.1, 0.9):
+        m = dropout_mask_tensor(p, seeds[0], ep, h)
+        vals = torch.unique(m)
+        assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) * (1.0 - p) - 1.0) < 1e-6
+        sigma = (p * (1 - p) / (ep * h)) ** 0.5
+        assert abs(float((m != 0).float().mean()) - (1 - p)) < 4 * sigma
+        per_head = (m != 0).float().mean(0)
+        assert float((per_head - (1 - p)).abs().max()) < 5 * (p * (1 - p) / ep) ** 0.5
+        assert abs(float(m.mean()) - 1.0) < 4 * sigma / (1 - p)        # E[multiplier] = 1: not renormalised (GAT.py:61)
+    for s in seeds:
+        masks.append(dropout_mask_tensor(0.6, s, ep, h) != 0)
+    assert torch.equal(masks[0], dropout_mask_tensor(0.6, seeds[0].clone(), ep, h) != 0)
+    for a in range(3):
+        for b in range(a + 1, 3):
+            agree = float((masks[a] == masks[b]).float().mean())      # independent masks agree with prob 0.4^2 + 0.6^2 = 0.52
+            assert abs(agree - 0.52) < 0.01, (a, b, agree)
+    # neighbouring edges / heads are uncorrelated
+    k = masks[0].float()
+    assert abs(float((k[1:] * k[:-1]).mean()) - 0.16) < 0.005 and abs(float((k[:, 1:] * k[:, :-1]).mean()) - 0.16) < 0.005
+    assert float(dropout_mask_tensor(1.0, seeds[0], 1000, h).abs().max()) == 0.0
+    # a prefix of a longer mask equals the shorter mask: the value depends on (seed, edge, head) only
+    assert torch.equal(dropout_mask_tensor(0.6, seeds[0], 1000, h), dropout_mask_tensor(0.6, seeds[0], ep, h)[:1000])

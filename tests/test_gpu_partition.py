@@ -31,13 +31,23 @@ def _single_gpu(layer, x, ei, gout):
     return out.detach(), xg.grad, grads
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.6], ids=["nodrop", "philox"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_c%d_h%d_%s_p%d" % (c[0], c[3], c[4], "cat" if c[5] else "mean", c[6]))
-def test_partitioned_stages_match_single_gpu(case):
+def test_partitioned_stages_match_single_gpu(case, dropout):
     import GAT
     from atmlgraphattentionnetworks_b200 import partition as pt
+    from atmlgraphattentionnetworks_b200.gat import dropout_mask_tensor
     n, e, f, c, h, concat, world = case
     torch.manual_seed(n + c)
     layer = GAT.GraphAttentionLayer(f, c, num_heads=h, concat=concat, dropout=0.0).to(DEV)
+    drop = None
+    if dropout:
+        # in-kernel dropout in partitioned mode: every rank's stages get the same (p, seed); the single-GPU layer is fed the
+        # materialised mask of that seed (global ORIGINAL edge positions key the multipliers on every rank)
+        seed = torch.tensor([n * 7919 + c, e], dtype=torch.int64, device=DEV)
+        drop = (dropout, seed)
+        full_mask = dropout_mask_tensor(dropout, seed, e + n, h)
+        layer.mask_hook = lambda shape: full_mask
     with torch.no_grad():
         layer.bias.uniform_(-0.5, 0.5)
     x = torch.randn(n, f, device=DEV)
@@ -58,14 +68,14 @@ def test_partitioned_stages_match_single_gpu(case):
         proj = [pt.stage_proj(geom, (w, bw, a1, a2, b1, b2), xs[r], blk) for r in range(world)]
         wh_full = torch.cat([p[0] for p in proj])                       # == all_gather_into_tensor
         s_src_full = torch.cat([p[1] for p in proj])
-        fwd = [pt.stage_edge_fwd(geom, parts[r], wh_full, s_src_full, proj[r][2], bias, None) for r in range(world)]
+        fwd = [pt.stage_edge_fwd(geom, parts[r], wh_full, s_src_full, proj[r][2], bias, drop) for r in range(world)]
         out = torch.cat([f_[0] for f_ in fwd])
         assert nerr(out.cpu().numpy(), out_ref.cpu().numpy()) <= 1e-5
         prep = [pt.stage_prep(geom, gout[p.lo:p.hi].contiguous(), fwd[r][3] if heads_mode else fwd[r][0], bias, proj[r][2],
                               fwd[r][1], fwd[r][2], blk) for r, p in enumerate(parts)]
         rowrec_full = torch.cat([p[0] for p in prep])
         g_full = torch.cat([p[1] for p in prep])
-        csc = [pt.stage_csc(geom, parts[r], proj[r][0][:parts[r].n_own], proj[r][1][:parts[r].n_own], rowrec_full, g_full, None)
+        csc = [pt.stage_csc(geom, parts[r], proj[r][0][:parts[r].n_own], proj[r][1][:parts[r].n_own], rowrec_full, g_full, drop)
                for r in range(world)]
         g_s_dst = sum(c_[2] for c_ in csc)                              # == reduce_scatter (sum) + own slice below
         fin = [pt.stage_finish(geom, proj[r][0][:parts[r].n_own], a1, a2, csc[r][1],

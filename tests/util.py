@@ -11,7 +11,7 @@ NET_FILES = sorted(glob.glob(os.path.join(GOLDEN, "net_*.npz")))
 ACT_FILES = sorted(glob.glob(os.path.join(GOLDEN, "actlayer_*.npz")))   # run_act_func_experiment.py layer, other logit activations
 # graphs with hub (> 512) and giant (> 4096) degrees, from the unmodified reference: they pin the ORACLE on those shapes
 HUBREF_FILES = sorted(glob.glob(os.path.join(GOLDEN, "hubref_*.npz")))
-ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh}
+ACTIVATIONS = {"log_sigmoid": torch.nn.LogSigmoid, "tanh": torch.nn.Tanh, "softmax": torch.nn.Softmax}
 GRAD_KEYS = ("g_x", "g_W", "g_bw", "g_a1", "g_b1", "g_a2", "g_b2", "g_bias")
 FP32_TOL = 1e-5   # north-star: fp32 outputs within 1e-5 relative (max|a-b| <= tol * max|b|)
 
