@@ -15,18 +15,35 @@ class GraphCSR:
     """int32 device arrays of [edge_index ; self loops] (see include/b200gat.h: b200gat_graph)."""
 
     __slots__ = ("num_nodes", "num_input_edges", "num_edges", "rowptr", "col", "eid", "colptr", "crow", "ceid",
-                 "device", "span", "hub_rows", "hub_cols", "rowend", "colend", "_struct", "__weakref__")
+                 "device", "span", "hub_rows", "hub_cols", "rowend", "colend", "status", "_struct", "__weakref__")
 
     def c_struct(self):
         return self._struct
+
+    def check(self):
+        """Lazy validation of a graph built with sync=False: ONE device->host read of the build's status word.  Raises
+        IndexError for out-of-range indices exactly as the synchronous build does (the arrays of such a graph are still
+        well formed — indices clamped — so kernels that already ran on it did not fault)."""
+        bad = int(self.status[0])
+        if bad:
+            raise IndexError(f"edge_index has {bad} entries outside [0, {self.num_nodes})")
+        return self
 
     def arrays(self):
         return {k: getattr(self, k) for k in ("rowptr", "col", "eid", "colptr", "crow", "ceid")}
 
 
-def build_csr(edge_index, num_nodes, validate=True):
+def build_csr(edge_index, num_nodes, validate=True, sync=True):
     """edge_index: int64 [2, E] CUDA tensor (row 0 = source, row 1 = target, GAT.py:37).  One device sync when
-    `validate` (the reference would raise from index_select on an out-of-range index; so do we)."""
+    `validate` (the reference would raise from index_select on an out-of-range index; so do we).
+
+    sync=False: no host synchronisation at all — nothing is read back, so the build can run inside a captured CUDA graph
+    for a NEW edge_index every replay (run_gnn_benchmark.py:60-63) and never stalls a training loop.  The degree classes
+    (b200gat_graph.hub_rows) are then not used: every row runs on the lane-group-per-row schedule, which is the right one
+    for batches of small graphs and still CORRECT (only slow) for a power-law graph; the index check is deferred to
+    GraphCSR.check()."""
+    if not sync:
+        validate = False
     if not edge_index.is_cuda:
         raise _abi.B200GatError("edge_index must be a CUDA tensor: the GAT hot path has no CPU fallback")
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -61,6 +78,7 @@ def build_csr(edge_index, num_nodes, validate=True):
         _abi.check(rc, "b200gat_csr_build")
         _abi.launches += 5 if ep else 0
         g.span = -1
+        g.status = status
         g.hub_rows = g.hub_cols = g.rowend = g.colend = None
         n_hub, max_deg = [0, 0], [0, 0]
         if validate:
@@ -131,6 +149,15 @@ class GraphCache:
         if len(self._entries) > self.capacity:
             self._entries.pop(0)
         return g
+
+    def put(self, edge_index, num_nodes, graph):
+        """Register a CSR built by the caller (capture.CapturedStep builds it sync-free inside the captured graph) so the
+        layers find it under this edge_index tensor."""
+        self._entries = [ent for ent in self._entries if ent[0]() is not None and ent[0]() is not edge_index]
+        self._entries.append((weakref.ref(edge_index), self._version(edge_index), num_nodes, graph))
+        if len(self._entries) > self.capacity:
+            self._entries.pop(0)
+        return graph
 
     def clear(self):
         self._entries = []

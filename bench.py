@@ -395,6 +395,60 @@ class Runner:
     def resident_step(self):
         return self.train_step(self.x_d, self.ei_d, self.y_d)
 
+    def captured_step(self):
+        """The train step through the product's whole-step capture (atmlgraphattentionnetworks_b200.capture.CapturedStep):
+        static input buffers, the CSR / CSC build of the current edge_index INSIDE the graph, one graph launch per step."""
+        from atmlgraphattentionnetworks_b200.capture import CapturedStep
+        assert self.env.world == 1 and not self.partitioned
+
+        def fn(x, edge_index, y):
+            return self.train_step(x, edge_index, y).detach()
+        return CapturedStep(fn, dict(x=self.x_d, edge_index=self.ei_d, y=self.y_d), num_nodes=self.n)
+
+    def time_captured(self, steps, warmup):
+        """-> record: resident replay (static buffers already hold the batch; the graph still re-ingests edge_index) and
+        end to end (pinned host -> static buffers, replay, loss -> pinned host, every step)."""
+        from atmlgraphattentionnetworks_b200 import _abi
+        l0 = _abi.launch_count()
+        cap = self.captured_step()
+        for _ in range(warmup):
+            cap()
+        torch.cuda.synchronize()
+        launches_total = _abi.launch_count() - l0                 # warm-up runs + ONE capture
+        ms = self.timed(cap, steps)
+        loss_h = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+        def e2e_run(nsteps):
+            pending, losses = None, []
+            for k in range(nsteps):
+                out = cap(x=self.x_h, edge_index=self.ei_h, y=self.y_h)       # H2D into the static buffers + replay
+                loss_h[k % 2].copy_(out, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    losses.append(float(pending[1]))
+                pending = (ev, loss_h[k % 2])
+            pending[0].synchronize()
+            losses.append(float(pending[1]))
+            assert all(v == v for v in losses)
+        e2e_run(3)
+        flush, self.flush_buf = self.flush_buf, None
+        try:
+            ms_e2e = statistics.median(self.timed(lambda: e2e_run(steps), 1) / steps for _ in range(3))
+        finally:
+            self.flush_buf = flush
+        cap.check()
+        h2d = self.x_h.numel() * 4 + self.ei_h.numel() * 8 + self.y_h.numel() * self.y_h.element_size()
+        per_run = launches_total // (3 + 1)                       # CapturedStep: 3 warm-up runs + the capture
+        return {"api": "atmlgraphattentionnetworks_b200.capture.CapturedStep (train step + in-graph CSR/CSC build of the batch's edge_index)",
+                "ms_per_step": ms, "value": self.total_edges() / (ms / 1e3), "unit": UNIT,
+                "gpu_launches_per_replay": per_run,
+                "e2e": {"ms_per_step": ms_e2e, "value": self.total_edges() / (ms_e2e / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "includes": "every step: pinned host -> static device buffers (x, edge_index, y), ONE graph launch (CSR/CSC "
+                                    "build + train step), loss D2H into pinned memory read one step behind"}}
+
     def total_edges(self):
         """edges all ranks process per step (sum over layers)"""
         per_rank = len(self.spec) * self.ep
@@ -649,11 +703,11 @@ class Runner:
 
 
 def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp="weak", e2e=True, cpu=True, breakdown=True,
-                 cuda_graph=False, traffic_name=None):
+                 cuda_graph=False, traffic_name=None, captured=False):
     """-> the record of one workload (all ranks take part; only rank 0's record is complete)."""
     from atmlgraphattentionnetworks_b200 import _abi
     t_wall = time.perf_counter()
-    run = Runner(name, env, heads=heads, num_graphs=num_graphs, dp=dp, capturable=cuda_graph)
+    run = Runner(name, env, heads=heads, num_graphs=num_graphs, dp=dp, capturable=cuda_graph or captured)
     rec = {"config": run.config, "n_gpus": env.world, "steps": steps, "warmup": warmup,
            "scaling": "strong" if (run.partitioned or run.dp == "strong") else "weak"}
     if env.world > 1:
@@ -663,22 +717,13 @@ def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp=
     resident = run.resident_step
     launches_per_replay = None
     if cuda_graph:
-        # whole-step capture: zero_grad + forward + loss + backward + fused Adam of the resident
-        # batch become ONE graph launch; the CSR is cached (no host sync inside), every buffer comes from the graph's pool
+        # whole-step capture through the product API: zero_grad + forward + loss + backward + fused
+        # Adam — and the CSR / CSC build of the batch's edge_index — become ONE graph launch
         assert env.world == 1, "--cuda-graph is a single-GPU mode"
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                run.resident_step()
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        run.opt.zero_grad(set_to_none=True)
         l0 = _abi.launch_count()
-        with torch.cuda.graph(graph):
-            run.resident_step()
-        launches_per_replay = _abi.launch_count() - l0
-        resident = graph.replay
+        cap = run.captured_step()
+        launches_per_replay = (_abi.launch_count() - l0) // 4      # 3 warm-up runs + the capture
+        resident = cap
         for _ in range(3):
             resident()
     launches0 = _abi.launch_count()
@@ -702,6 +747,8 @@ def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp=
                                    "one step behind" if not run.partitioned else
                                    "every step: H2D of the own rows of x / y from pinned host, train step, loss D2H (the partitioned "
                                    "graph is static and resident)")}
+    if captured and env.world == 1:
+        rec["captured"] = run.time_captured(steps, warmup)
     if breakdown:
         kernels, roofline, edge_phase, coll = run.per_op(5, traffic_name or name)
         rec.update({"roofline": roofline, "edge_phase": edge_phase, "kernels": kernels})
@@ -712,6 +759,8 @@ def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp=
         ksum = sum(r["ms"] for r in kernels)
         rec["abi_ops_ms_sum"] = ksum
         rec["step_over_abi_ops"] = ms_step / ksum if ksum else None
+        if "captured" in rec:
+            rec["captured"]["step_over_abi_ops"] = rec["captured"]["ms_per_step"] / ksum if ksum else None
     spec_n = (len(run.spec), run.ep)
     run.close()
     if cpu and env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
@@ -800,9 +849,12 @@ def main():
     def heads_sweep():
         points = []
         for h in HEAD_POINTS:
-            r = run_workload("heads", env, args.steps, warmup, args, heads=h, e2e=False, traffic_name=f"heads{h}")
+            r = run_workload("heads", env, args.steps, warmup, args, heads=h, e2e=False, traffic_name=f"heads{h}", captured=True)
+            cp = r.get("captured") or {}
             pt = {"heads": h, "ms_per_step": r["ms_per_step"], "value": r["value"], "abi_ops_ms_sum": r.get("abi_ops_ms_sum"),
                   "step_over_abi_ops": r.get("step_over_abi_ops"), "gpu_launches": r["gpu_launches"],
+                  "captured_ms_per_step": cp.get("ms_per_step"), "captured_value": cp.get("value"),
+                  "captured_step_over_abi_ops": cp.get("step_over_abi_ops"),
                   "edge_phase_frac_of_measured_hbm": (r.get("edge_phase") or {}).get("frac_of_measured_hbm"),
                   "kernels": [{k: v for k, v in kr.items() if k in ("op", "ms", "GBps", "frac_hbm", "TFLOPs")} for kr in r.get("kernels", [])],
                   "cpu_baseline": r.get("cpu_baseline")}
@@ -816,16 +868,16 @@ def main():
                      head["points"][-1]["gpu_launches"], "n_gpus": world, "steps": args.steps, "warmup": warmup, "scaling": "weak"})
     else:
         head = run_workload(head_name, env, args.steps, warmup, args, heads=args.heads or 8, num_graphs=args.graphs, dp=args.dp,
-                            cuda_graph=args.cuda_graph)
+                            cuda_graph=args.cuda_graph, captured=(world == 1 and head_name != "large"))
     subs = {}
     if everything:
         sub_steps = min(args.steps, 10)
         subs["large"] = run_workload("large", env, sub_steps, 3, args)
         if world == 1:
-            subs["cifar"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=128)
+            subs["cifar"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, captured=True)
             subs["cifar"]["batch512"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=512, cpu=False,
-                                                     traffic_name="cifar512")
-            subs["cora"] = run_workload("cora", env, args.steps, warmup, args)
+                                                     traffic_name="cifar512", captured=True)
+            subs["cora"] = run_workload("cora", env, args.steps, warmup, args, captured=True)
             subs["heads"] = heads_sweep()
         else:
             subs["cifar"] = {"dp_strong": run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, dp="strong"),
@@ -840,7 +892,7 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head.get("scaling", "weak"),
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "git_sha": git_sha()}
     for k in ("config", "e2e", "gpu_launches", "roofline", "edge_phase", "kernels", "abi_ops_ms_sum", "step_over_abi_ops",
-              "collectives_ms_per_step", "collectives_note", "check", "cpu_baseline", "clocks", "cuda_graph", "points"):
+              "collectives_ms_per_step", "collectives_note", "check", "cpu_baseline", "clocks", "cuda_graph", "points", "captured"):
         if k in head:
             line[k] = head[k]
     line.update(subs)
