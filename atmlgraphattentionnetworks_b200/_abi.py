@@ -117,6 +117,26 @@ class ProjBwdArgs(C.Structure):
                 ("x_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
 
 
+class ReadoutGeom(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_graphs", C.c_int64), ("in_channels", C.c_int64), ("hidden", C.c_int64),
+                ("classes", C.c_int64)]
+
+
+class ReadoutFwdArgs(C.Structure):
+    _fields_ = [("geom", ReadoutGeom), ("x", C.c_void_p), ("ldx", C.c_int64), ("batch", C.c_void_p),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("pooled", C.c_void_p), ("counts", C.c_void_p), ("hidden_out", C.c_void_p), ("logp", C.c_void_p),
+                ("status", C.c_void_p), ("x_activation", C.c_int32)]
+
+
+class ReadoutBwdArgs(C.Structure):
+    _fields_ = [("geom", ReadoutGeom), ("batch", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p),
+                ("pooled", C.c_void_p), ("counts", C.c_void_p), ("hidden_out", C.c_void_p), ("logp", C.c_void_p),
+                ("g_logp", C.c_void_p), ("g_x", C.c_void_p), ("ldgx", C.c_int64),
+                ("g_w1", C.c_void_p), ("g_b1", C.c_void_p), ("g_w2", C.c_void_p), ("g_b2", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 ACT_NONE, ACT_ELU = 0, 1
 LOGIT_LEAKY_RELU, LOGIT_LOGSIGMOID, LOGIT_TANH, LOGIT_HEAD_SOFTMAX = 0, 1, 2, 3
 
@@ -141,6 +161,8 @@ _SIGNATURES = {
     "b200gat_edge_bwd_finish": (C.c_int, [C.POINTER(EdgeBwdFinishArgs), C.c_void_p]),
     "b200gat_proj_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_bwd": (C.c_int, [C.POINTER(ProjBwdArgs), C.c_void_p]),
+    "b200gat_readout_fwd": (C.c_int, [C.POINTER(ReadoutFwdArgs), C.c_void_p]),
+    "b200gat_readout_bwd": (C.c_int, [C.POINTER(ReadoutBwdArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libb200gat.so")
 OBJ = os.path.join(CSRC, "build")
-SOURCES = ["abi.cu", "csr_build.cu", "proj.cu", "proj_tc.cu", "edge_fwd.cu", "edge_bwd.cu"]
+SOURCES = ["abi.cu", "csr_build.cu", "proj.cu", "proj_tc.cu", "edge_fwd.cu", "edge_bwd.cu", "readout.cu"]
 # never --use_fast_math: expf / division must stay IEEE-accurate for the 1e-5 parity bar
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3", "-Xptxas", "-v"]

@@ -193,6 +193,63 @@ __global__ void __launch_bounds__(256, 2) bwd_prep_rows_kernel(const PrepRowsPar
   }
 }
 
+// ---- the same for NARROW concat-like layers (D_out <= 128: the 8 x 8 layers of GATNet, the heads sweep's 1 x 64 / 2 x 64):
+// one lane group of G = pow2ceil(D / 4) lanes per destination row, 32 / G rows per warp, one float4 slot per lane.
+template <bool ACT, int G>
+__global__ void __launch_bounds__(256) bwd_prep_rows_narrow_kernel(const PrepRowsParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = p.C >> 2, DQ = p.D >> 2;                  // Q is a power of two <= G
+  const bool live = gl < DQ;
+  const float4 bv = live ? ldg4(p.bias + 4 * gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t base = warp * RPW; base < p.N; base += nwarps * RPW) {
+    const int64_t i = base + gi;
+    const bool valid = live && i < p.N;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), ov = gv;
+    if (valid) {
+      gv = ldg4(p.gout + i * p.ldgo + 4 * gl);
+      ov = ldg4(p.out + i * p.ldo + 4 * gl);
+      if (ACT) {
+        gv.x *= elu_grad(ov.x); gv.y *= elu_grad(ov.y); gv.z *= elu_grad(ov.z); gv.w *= elu_grad(ov.w);
+        *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * gl) = gv;
+      }
+    }
+    cs.x += gv.x; cs.y += gv.y; cs.z += gv.z; cs.w += gv.w;
+    float d = gv.x * (ov.x - bv.x) + gv.y * (ov.y - bv.y) + gv.z * (ov.z - bv.z) + gv.w * (ov.w - bv.w);
+    for (int o2 = Q >> 1; o2 > 0; o2 >>= 1) d += __shfl_xor_sync(FULL, d, o2);
+    if (valid && (gl & (Q - 1)) == 0) {
+      const int64_t item = i * p.H + gl / Q;
+      p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
+    }
+  }
+  // column sums: the RPW groups of a warp, then the 8 warps of the CTA, then one atomic per column per CTA
+#pragma unroll
+  for (int o2 = G; o2 < 32; o2 <<= 1) {
+    cs.x += __shfl_xor_sync(FULL, cs.x, o2); cs.y += __shfl_xor_sync(FULL, cs.y, o2);
+    cs.z += __shfl_xor_sync(FULL, cs.z, o2); cs.w += __shfl_xor_sync(FULL, cs.w, o2);
+  }
+  __shared__ float4 red[8][G];
+  if (lane < G) red[threadIdx.x >> 5][lane] = cs;
+  __syncthreads();
+  if (threadIdx.x < G && threadIdx.x < DQ) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += red[w][threadIdx.x].x; t.y += red[w][threadIdx.x].y; t.z += red[w][threadIdx.x].z; t.w += red[w][threadIdx.x].w; }
+    atomicAdd(p.g_bias + 4 * threadIdx.x + 0, t.x); atomicAdd(p.g_bias + 4 * threadIdx.x + 1, t.y);
+    atomicAdd(p.g_bias + 4 * threadIdx.x + 2, t.z); atomicAdd(p.g_bias + 4 * threadIdx.x + 3, t.w);
+  }
+}
+
+template <int G>
+static void launch_prep_narrow(const PrepRowsParams& pr, bool act, int blocks, cudaStream_t stream) {
+  if (act) bwd_prep_rows_narrow_kernel<true, G><<<blocks, 256, 0, stream>>>(pr);
+  else bwd_prep_rows_narrow_kernel<false, G><<<blocks, 256, 0, stream>>>(pr);
+}
+
 // ---- fast prep for mean-over-heads layers (!concat, H > 1): one warp per destination row.  The row of the upstream
 // gradient (C values, shared by all heads, scaled 1/H) is loaded once, written to the gatherable copy gp [N, Cp] and
 // dotted with each head's aggregate O[i,h,:]; the g_bias column sums ride along. --------------------------------------
@@ -923,14 +980,22 @@ gt_amax_kernel(const float* __restrict__ gwh, int64_t n_nd, const float* __restr
   }
 }
 
-// one thread per FOUR adjacent columns (same head: c_pad % 4 == 0), a strip of rows per blockIdx.y
-template <bool PLANES>
+// one thread per FOUR adjacent columns (same head: c_pad % 4 == 0); the 256 threads of a CTA form TX column groups x
+// RY = 256 / TX row lanes (TX = min(256, pow2ceil(Dp / 4)): narrow layers — the 8 x 8 layers of GATNet have Dp = 64 — would
+// otherwise leave 240 of 256 threads idle: 49 us for 15 k rows, measured), a strip of row batches per blockIdx.y
+template <bool PLANES, int TXS>
 __global__ void __launch_bounds__(256, 4) bwd_finish_kernel(const FinishParams p) {
-  const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (c >= p.Dp) return;
-  const int h = c / p.Cp;
-  const bool head_lead = (c - h * p.Cp) == 0;
-  const float4 a1c = ldg4(p.a1 + c), a2c = ldg4(p.a2 + c);
+  constexpr int TX = 1 << TXS, RY = 256 >> TXS;
+  const int tx = threadIdx.x & (TX - 1), ry = threadIdx.x >> TXS;
+  const int c = 4 * (blockIdx.x * TX + tx);
+  const bool active = c < p.Dp;
+  if constexpr (RY == 1) {
+    if (!active) return;                                  // (no CTA-wide barrier below in this form)
+  }
+  const int cc = (RY == 1 || active) ? c : 0;
+  const int h = cc / p.Cp;
+  const bool head_lead = (cc - h * p.Cp) == 0;
+  const float4 a1c = ldg4(p.a1 + cc), a2c = ldg4(p.a2 + cc);
   float scale = 1.f;
   if (PLANES) {
     const float bound = __uint_as_float(p.amax[0]) + __uint_as_float(p.amax[1]) * __uint_as_float(p.amax[3]) +
@@ -944,13 +1009,13 @@ __global__ void __launch_bounds__(256, 4) bwd_finish_kernel(const FinishParams p
   float4 sbw = make_float4(0.f, 0.f, 0.f, 0.f), sa1 = sbw, sa2 = sbw;
   float sb1 = 0.f, sb2 = 0.f;
   // Row batches are INTERLEAVED over the CTAs (batch b goes to CTA b mod gridDim.y), so at any time the grid streams one
-  // window of ~gridDim.y * RB consecutive rows of each array — DRAM pages are walked in address order, as a plain copy
+  // window of ~gridDim.y * RY * RB consecutive rows of each array — DRAM pages are walked in address order, as a plain copy
   // does — instead of gridDim.y separate strips (thousands of concurrently open pages).
   // rows in batches of RB: ALL loads of a batch are issued before its first store — the stores (g_t / planes) may alias
   // the loads as far as the compiler can tell, so a plain unrolled loop kept one row in flight per thread (3.9 TB/s)
   constexpr int RB = 4;
-  const int64_t r1 = p.N;
-  for (int64_t rb = int64_t(blockIdx.y) * RB; rb < r1; rb += int64_t(gridDim.y) * RB) {
+  const int64_t r1 = (RY == 1 || active) ? p.N : 0;
+  for (int64_t rb = (int64_t(blockIdx.y) * RY + ry) * RB; rb < r1; rb += int64_t(gridDim.y) * RY * RB) {
     float gs[RB], gd[RB];
     float4 w[RB], t[RB];
 #pragma unroll
@@ -988,16 +1053,44 @@ __global__ void __launch_bounds__(256, 4) bwd_finish_kernel(const FinishParams p
       sb2 += gd[u];
     }
   }
-  const float bw4[4] = {sbw.x, sbw.y, sbw.z, sbw.w}, a14[4] = {sa1.x, sa1.y, sa1.z, sa1.w}, a24[4] = {sa2.x, sa2.y, sa2.z, sa2.w};
+  if constexpr (RY == 1) {
+    const float bw4[4] = {sbw.x, sbw.y, sbw.z, sbw.w}, a14[4] = {sa1.x, sa1.y, sa1.z, sa1.w}, a24[4] = {sa2.x, sa2.y, sa2.z, sa2.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      atomicAdd(p.g_bw + c + u, bw4[u]);
+      atomicAdd(p.g_a1 + c + u, a14[u]);
+      atomicAdd(p.g_a2 + c + u, a24[u]);
+    }
+    if (head_lead) {
+      atomicAdd(p.g_b1 + h, sb1);
+      atomicAdd(p.g_b2 + h, sb2);
+    }
+    return;
+  }
+  float v[14] = {sbw.x, sbw.y, sbw.z, sbw.w, sa1.x, sa1.y, sa1.z, sa1.w, sa2.x, sa2.y, sa2.z, sa2.w, sb1, sb2};
+  if constexpr (RY > 1) {                                 // combine the row lanes before the atomics
+    __shared__ float red[14][256 + 1];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) red[k][threadIdx.x] = v[k];
+    __syncthreads();
+    if (ry != 0) return;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      float acc = v[k];
+      for (int y = 1; y < RY; ++y) acc += red[k][y * TX + tx];
+      v[k] = acc;
+    }
+  }
+  if (!active) return;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    atomicAdd(p.g_bw + c + u, bw4[u]);
-    atomicAdd(p.g_a1 + c + u, a14[u]);
-    atomicAdd(p.g_a2 + c + u, a24[u]);
+    atomicAdd(p.g_bw + c + u, v[u]);
+    atomicAdd(p.g_a1 + c + u, v[4 + u]);
+    atomicAdd(p.g_a2 + c + u, v[8 + u]);
   }
   if (head_lead) {
-    atomicAdd(p.g_b1 + h, sb1);
-    atomicAdd(p.g_b2 + h, sb2);
+    atomicAdd(p.g_b1 + h, v[12]);
+    atomicAdd(p.g_b2 + h, v[13]);
   }
 }
 
@@ -1106,6 +1199,17 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
     const int64_t want = ceil_div(rows, 8);
     const int64_t cap_rows = int64_t(sm_count()) * 4;       // few, fat CTAs: one g_bias atomic per column per CTA
     const int blocks = static_cast<int>(want < cap_rows ? want : cap_rows);
+    const int DQ = static_cast<int>(g.d_out / 4);
+    if (DQ <= 32 && (Q & (Q - 1)) == 0) {                   // narrow rows: a lane group per row instead of a warp
+      const int64_t rows_per_cta = DQ <= 4 ? 64 : (DQ <= 8 ? 32 : (DQ <= 16 ? 16 : 8));
+      const int64_t want_n = ceil_div(rows, rows_per_cta * 4);
+      const int blocks_n = static_cast<int>(want_n < cap_rows ? (want_n > 0 ? want_n : 1) : cap_rows);
+      if (DQ <= 4) launch_prep_narrow<4>(pr, act != 0, blocks_n, stream);
+      else if (DQ <= 8) launch_prep_narrow<8>(pr, act != 0, blocks_n, stream);
+      else if (DQ <= 16) launch_prep_narrow<16>(pr, act != 0, blocks_n, stream);
+      else launch_prep_narrow<32>(pr, act != 0, blocks_n, stream);
+      return check_launch("bwd_prep_rows_narrow_kernel");
+    }
     if (act) bwd_prep_rows_kernel<true><<<blocks, 256, 0, stream>>>(pr);
     else bwd_prep_rows_kernel<false><<<blocks, 256, 0, stream>>>(pr);
     return check_launch("bwd_prep_rows_kernel");
@@ -1228,14 +1332,23 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
       if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
     }
   }
-  const int xblocks = static_cast<int>(ceil_div(g.Dp, 4 * 256));
+  const int tx_shift = g.Dp <= 64 ? 4 : (g.Dp <= 256 ? 6 : 8);   // TX = 16 / 64 / 256 column groups per CTA
+  const int TX = 1 << tx_shift, RY = 256 >> tx_shift;
+  const int xblocks = static_cast<int>(ceil_div(g.Dp, 4 * TX));
   int64_t ysplit = ceil_div(cap, xblocks);
-  const int64_t max_y = ceil_div(rows, 16);
+  const int64_t max_y = ceil_div(rows, int64_t(16) * RY);      // at least 4 batches of 4 rows per thread
   if (ysplit > max_y) ysplit = max_y;
   if (ysplit < 1) ysplit = 1;
   dim3 grid(xblocks, static_cast<unsigned>(ysplit));
-  if (gsplit) bwd_finish_kernel<true><<<grid, 256, 0, stream>>>(f);
-  else bwd_finish_kernel<false><<<grid, 256, 0, stream>>>(f);
+  if (gsplit) {
+    if (tx_shift == 4) bwd_finish_kernel<true, 4><<<grid, 256, 0, stream>>>(f);
+    else if (tx_shift == 6) bwd_finish_kernel<true, 6><<<grid, 256, 0, stream>>>(f);
+    else bwd_finish_kernel<true, 8><<<grid, 256, 0, stream>>>(f);
+  } else {
+    if (tx_shift == 4) bwd_finish_kernel<false, 4><<<grid, 256, 0, stream>>>(f);
+    else if (tx_shift == 6) bwd_finish_kernel<false, 6><<<grid, 256, 0, stream>>>(f);
+    else bwd_finish_kernel<false, 8><<<grid, 256, 0, stream>>>(f);
+  }
   return check_launch("bwd_finish_kernel");
 }
 

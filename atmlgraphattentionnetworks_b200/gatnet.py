@@ -8,12 +8,14 @@ per-graph mean readout, lin1/lin2, log_softmax) are PyTorch CUDA ops.
 The GCN branch (GATNet.py:38-58) is a third-party comparison baseline (torch_geometric.nn.GCNConv) and is only
 available when torch_geometric is installed.
 """
+import ctypes
 import os
 
 import torch
 import torch.nn.functional as F
 
-from .gat import GraphAttentionLayer
+from . import _abi
+from .gat import GraphAttentionLayer, _call, _workspace
 
 # dataset -> (conv2 out_channels, conv2 heads, conv2 concat, dropout)           GATNet.py:17-37
 _GAT_TABLE = {
@@ -38,6 +40,62 @@ def segment_mean(x, batch, num_graphs=None):
     count = torch.zeros(groups, dtype=x.dtype, device=x.device).index_add_(
         0, batch, torch.ones(batch.numel(), dtype=x.dtype, device=x.device)).clamp_(min=1)
     return total / count.unsqueeze(1)
+
+
+class ReadoutHeadFunction(torch.autograd.Function):
+    """GATNet.py:72-75 fused (b200gat_readout_fwd / _bwd): log_softmax(lin2(relu(lin1(scatter_mean(act(x), batch))))).
+    x [N, F] CUDA float32; act_in: x is the PRE-activation output of the last GAT layer (produced with act_out) and ELU is
+    applied while it is loaded — the gradient returned for x is then the one w.r.t. ELU(x), as that layer expects."""
+
+    @staticmethod
+    def forward(ctx, x, batch, w1, b1, w2, b2, num_graphs, act_in):
+        lib = _abi.lib()
+        dev = x.device
+        x, batch = x.contiguous(), batch.contiguous()
+        w1, b1, w2, b2 = (t.contiguous() for t in (w1, b1, w2, b2))
+        n, f = x.shape
+        g, hd, k = int(num_graphs), w1.shape[0], w2.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        pooled, counts = torch.empty((g, f), **f32), torch.empty(g, **f32)
+        hid, logp = torch.empty((g, hd), **f32), torch.empty((g, k), **f32)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        geom = _abi.ReadoutGeom(n, g, f, hd, k)
+        with torch.cuda.device(dev):
+            a = _abi.ReadoutFwdArgs(geom, x.data_ptr(), x.stride(0) if n else f, batch.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                                    w2.data_ptr(), b2.data_ptr(), pooled.data_ptr(), counts.data_ptr(), hid.data_ptr(),
+                                    logp.data_ptr(), status.data_ptr(), _abi.ACT_ELU if act_in else _abi.ACT_NONE)
+            _call("b200gat_readout_fwd", lib.b200gat_readout_fwd, a, torch.cuda.current_stream(dev).cuda_stream, (f, hd, k))
+        ctx.save_for_backward(batch, w1, w2, pooled, counts, hid, logp)
+        ctx.dims = (n, g, f, hd, k)
+        ctx.status = status            # nodes whose graph id is outside [0, num_graphs): readable lazily (status.item())
+        return logp
+
+    @staticmethod
+    def backward(ctx, g_logp):
+        batch, w1, w2, pooled, counts, hid, logp = ctx.saved_tensors
+        n, g, f, hd, k = ctx.dims
+        lib = _abi.lib()
+        dev = g_logp.device
+        g_logp = g_logp.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_x = torch.empty((n, f), **f32) if ctx.needs_input_grad[0] else None
+        g_w1, g_b1, g_w2, g_b2 = torch.empty((hd, f), **f32), torch.empty(hd, **f32), torch.empty((k, hd), **f32), torch.empty(k, **f32)
+        ws_bytes = g * (k + hd + f) * 4
+        ws = _workspace(ws_bytes, dev)
+        with torch.cuda.device(dev):
+            a = _abi.ReadoutBwdArgs(_abi.ReadoutGeom(n, g, f, hd, k), batch.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                    pooled.data_ptr(), counts.data_ptr(), hid.data_ptr(), logp.data_ptr(), g_logp.data_ptr(),
+                                    g_x.data_ptr() if g_x is not None else None, f, g_w1.data_ptr(), g_b1.data_ptr(),
+                                    g_w2.data_ptr(), g_b2.data_ptr(), ws.data_ptr(), ws_bytes)
+            _call("b200gat_readout_bwd", lib.b200gat_readout_bwd, a, torch.cuda.current_stream(dev).cuda_stream, (f, hd, k))
+        return g_x, None, g_w1, g_b1, g_w2, g_b2, None, None
+
+
+def readout_head(x, batch, lin1, lin2, num_graphs=None, act_in=False):
+    """GATNet.py:72-75 on the fused kernels.  num_graphs (PyG batches carry it as data.num_graphs) avoids the host
+    synchronisation of batch.max().item()."""
+    groups = int(num_graphs) if num_graphs is not None else (int(batch.max().item()) + 1 if batch.numel() else 0)
+    return ReadoutHeadFunction.apply(x, batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias, groups, bool(act_in))
 
 
 class GATNet(torch.nn.Module):
@@ -74,9 +132,12 @@ class GATNet(torch.nn.Module):
         x, edge_index = data.x, data.edge_index
         act = F.relu if self.model_name == "GCN" else F.elu
         if self.dataset_name == "CIFAR10":                     # GATNet.py:62-76
-            if self.model_name == "GAT":                       # elu(conv1) fused into the conv1 -> conv2 boundary
+            if self.model_name == "GAT":
+                # elu(conv1) is fused into the conv1 -> conv2 boundary, elu(conv2) into the readout's load of x, and
+                # scatter_mean -> lin1 -> relu -> lin2 -> log_softmax (GATNet.py:73-75) run as ONE fused op
                 x, amax = self.conv1.forward_fused(x, edge_index, act_out=True)
-                x = act(self.conv2.forward_fused(x, edge_index, act_in=True, x_amax=amax)[0])
+                x = self.conv2.forward_fused(x, edge_index, act_in=True, act_out=True, x_amax=amax)[0]
+                return readout_head(x, data.batch.long(), self.lin1, self.lin2, getattr(data, "num_graphs", None), act_in=True)
             else:
                 x = act(self.conv1(x, edge_index))
                 x = act(self.conv2(x, edge_index))

@@ -282,6 +282,43 @@ typedef struct {
 size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);
 
+/* ---- graph-level readout head of GATNet (GATNet.py:72-75), fused ----------------------------------------------------
+ *   pooled = scatter_mean(act(x), batch, dim=0)   hid = relu(lin1(pooled))   logp = log_softmax(lin2(hid), dim=1)
+ * act = ELU when x_activation is set: x is then the PRE-activation output of the last GAT layer (layer-boundary fusion as
+ * above) and the gradient handed back is the one w.r.t. act(x).  `batch` need not be sorted; graph ids outside
+ * [0, num_graphs) are skipped and counted in *status (device int32, read lazily by the caller).  Empty graphs pool to 0. */
+typedef struct {
+  int64_t num_nodes, num_graphs;
+  int64_t in_channels, hidden, classes;   /* lin1: [hidden, in_channels], lin2: [classes, hidden] */
+} b200gat_readout_geom;
+
+typedef struct {
+  b200gat_readout_geom geom;
+  const float* x; int64_t ldx;            /* [N, in_channels] */
+  const int64_t* batch;                   /* [N] graph id of every node */
+  const float* w1; const float* b1;       /* lin1.weight [hidden, in_channels], lin1.bias [hidden] */
+  const float* w2; const float* b2;       /* lin2.weight [classes, hidden], lin2.bias [classes] */
+  float* pooled;                          /* out [G, in_channels] per-graph means   (kept for the backward) */
+  float* counts;                          /* out [G] nodes per graph                (kept for the backward) */
+  float* hidden_out;                      /* out [G, hidden] relu(lin1(pooled))      (kept for the backward) */
+  float* logp;                            /* out [G, classes] */
+  int32_t* status;                        /* out: device word, number of nodes with a graph id outside [0, G) */
+  int32_t x_activation;                   /* B200GAT_ACT_* */
+} b200gat_readout_fwd_args;
+int b200gat_readout_fwd(const b200gat_readout_fwd_args* a, void* stream);
+
+typedef struct {
+  b200gat_readout_geom geom;
+  const int64_t* batch;
+  const float* w1; const float* w2;
+  const float* pooled; const float* counts; const float* hidden_out; const float* logp;   /* from the forward */
+  const float* g_logp;                    /* [G, classes] upstream gradient */
+  float* g_x; int64_t ldgx;               /* out [N, in_channels] gradient w.r.t. act(x), or NULL */
+  float* g_w1; float* g_b1; float* g_w2; float* g_b2;   /* out, overwritten */
+  void* workspace; size_t workspace_bytes;   /* G * (classes + hidden + in_channels) * 4 bytes */
+} b200gat_readout_bwd_args;
+int b200gat_readout_bwd(const b200gat_readout_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,7 +58,9 @@ def test_struct_layouts_match_header(tmp_path):
     structs = {"b200gat_graph": _abi.Graph, "b200gat_layer": _abi.Layer, "b200gat_proj_fwd_args": _abi.ProjFwdArgs,
                "b200gat_edge_fwd_args": _abi.EdgeFwdArgs, "b200gat_edge_bwd_args": _abi.EdgeBwdArgs,
                "b200gat_proj_bwd_args": _abi.ProjBwdArgs, "b200gat_edge_bwd_prep_args": _abi.EdgeBwdPrepArgs,
-               "b200gat_edge_bwd_csc_args": _abi.EdgeBwdCscArgs, "b200gat_edge_bwd_finish_args": _abi.EdgeBwdFinishArgs}
+               "b200gat_edge_bwd_csc_args": _abi.EdgeBwdCscArgs, "b200gat_edge_bwd_finish_args": _abi.EdgeBwdFinishArgs,
+               "b200gat_dropout": _abi.Dropout, "b200gat_readout_geom": _abi.ReadoutGeom,
+               "b200gat_readout_fwd_args": _abi.ReadoutFwdArgs, "b200gat_readout_bwd_args": _abi.ReadoutBwdArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200gat.h"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -135,3 +135,42 @@ def test_captured_training_draws_a_fresh_dropout_mask_every_replay():
     step = capture_train_step(net, opt, lambda out, y: F.nll_loss(out, y), d)
     losses = [float(step()) for _ in range(4)]
     assert len(set(losses)) == 4, losses
+
+
+# ------------------------------------------------------------------ fused readout head (GATNet.py:72-75) vs torch ops
+@pytest.mark.parametrize("shape", [(15052, 128, 64, 64, 10), (1000, 7, 33, 20, 3), (50, 60, 64, 64, 10)],
+                         ids=["cifar128", "odd", "empty_graphs"])
+@pytest.mark.parametrize("act_in", [False, True], ids=["plain", "elu_on_load"])
+def test_readout_head_matches_torch_ops(shape, act_in):
+    """scatter_mean -> lin1 -> relu -> lin2 -> log_softmax as one fused op, forward and all five gradients, against the
+    same composition in float64 torch ops (unsorted batch vector, empty graphs, ELU applied on load)."""
+    from atmlgraphattentionnetworks_b200.gatnet import readout_head
+    n, g, f, hd, k = shape
+    gen = torch.Generator().manual_seed(n + g)
+    x = torch.randn(n, f, generator=gen)
+    batch = torch.randint(0, g if g < n else n // 2, (n,), generator=gen)          # unsorted; some graphs stay empty
+    lin1, lin2 = torch.nn.Linear(f, hd), torch.nn.Linear(hd, k)
+    gl = torch.randn(g, k, generator=gen)
+
+    def ref(dt):
+        xr = x.to(dt).requires_grad_(True)
+        l1, l2 = torch.nn.Linear(f, hd).to(dt), torch.nn.Linear(hd, k).to(dt)
+        l1.load_state_dict({a: b.to(dt) for a, b in lin1.state_dict().items()})
+        l2.load_state_dict({a: b.to(dt) for a, b in lin2.state_dict().items()})
+        xa = F.elu(xr) if act_in else xr
+        tot = torch.zeros(g, f, dtype=dt).index_add(0, batch, xa)
+        cnt = torch.zeros(g, dtype=dt).index_add(0, batch, torch.ones(n, dtype=dt)).clamp(min=1)
+        xa.retain_grad()
+        out = F.log_softmax(l2(F.relu(l1(tot / cnt.unsqueeze(1)))), dim=1)
+        out.backward(gl.to(dt))
+        # the fused op returns the gradient w.r.t. act(x) when act_in (the producing layer applies act')
+        gx = xa.grad if act_in else xr.grad
+        return [out.detach(), gx, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad]
+    want = ref(torch.float64)
+    xg = x.to(DEV).requires_grad_(True)
+    l1, l2 = lin1.to(DEV), lin2.to(DEV)
+    out = readout_head(xg, batch.to(DEV), l1, l2, num_graphs=g, act_in=act_in)
+    out.backward(gl.to(DEV))
+    got = [out.detach(), xg.grad, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad]
+    for name, a, b in zip(("logp", "g_x", "g_w1", "g_b1", "g_w2", "g_b2"), got, want):
+        assert nerr(a.cpu().numpy(), b.numpy()) <= 1e-5, name
