@@ -299,26 +299,39 @@ class PartitionedGATFunction(torch.autograd.Function):
     partial sums: all-reduce (SUM) them over ranks (parallel.GradBucket.all_reduce_mean(weight=1.0))."""
 
     @staticmethod
-    def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group, peer=None):
+    def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group, peer=None, x_full=None):
+        # x_full: the layer's input for ALL nodes, replicated on every rank (the static input features of layer 1).  The
+        # rank then projects all N rows itself and NOTHING is exchanged in this layer's forward: for the 2.4 M-node graph
+        # a 100 -> 512 projection of every node costs 2.5 ms, its all-gather (4.3 GB received per rank) 6-7 ms.
         if x_own.shape[0] != part.n_own:
             raise ValueError(f"x_own has {x_own.shape[0]} rows, the partition's own block [{part.lo}, {part.hi}) has "
                              f"{part.n_own} (blocks are ceil(N / P) rows: partition.block_size)")
         x_own = x_own.contiguous()
         w, bw, a1, a2, b1, b2, bias = (t.contiguous() for t in (w, bw, a1, a2, b1, b2, bias))
         with torch.cuda.device(x_own.device):
-            if peer is not None:          # nobody may still be reading this buffer (an earlier forward's edge kernel) when
-                with _timed("peer_barrier", geom):   # the first remote tile lands: one more signal-pad barrier, ~10 us
+            if peer is not None and x_full is None:   # nobody may still be reading this buffer (an earlier forward's edge
+                with _timed("peer_barrier", geom):   # kernel) when the first remote tile lands: one more signal-pad barrier
                     peer.barrier()
-            wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer)
-            if peer is not None:          # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
+            if x_full is not None:
+                n_all = x_full.shape[0]
+                wh_full, s_src_full, s_dst_full = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_full.contiguous(), n_all, None)
+                wh_pad, s_src_pad = wh_full[part.lo:], s_src_full[part.lo:]        # own rows first (only [:n_own] is used)
+                s_dst = s_dst_full[part.lo:part.hi]
+                peer = None
+            else:
+                wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer)
+            if x_full is not None:
+                pass
+            elif peer is not None:        # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
                 with _timed("peer_barrier", geom):
                     peer.barrier()
                 wh_full = peer.tensor
             else:
                 with _timed("all_gather_wh", geom):
                     wh_full = all_gather_rows(wh_pad, group)
-            with _timed("all_gather_s_src", geom):
-                s_src_full = all_gather_rows(s_src_pad, group)
+            if x_full is None:
+                with _timed("all_gather_s_src", geom):
+                    s_src_full = all_gather_rows(s_src_pad, group)
             out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask)
         n = part.n_own
         ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
@@ -346,10 +359,10 @@ class PartitionedGATFunction(torch.autograd.Function):
                 g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
             g_bw, g_a1, g_a2, g_b1, g_b2 = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh)
             g_x, g_w = stage_proj_bwd(geom, g_wh, x_own, w, ctx.needs_input_grad[0])
-        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None, None
+        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None, None, None
 
 
-def partitioned_layer_forward(layer, x_own, part, group=None):
+def partitioned_layer_forward(layer, x_own, part, group=None, x_full=None):
     """Run a GraphAttentionLayer module on the own block of a row-partitioned graph.  Attention dropout (GAT.py:61) is
     generated inside the kernels from (seed, ORIGINAL edge position, head): every rank uses rank 0's two seed words (one
     16-byte broadcast), so an edge gets the same multiplier in the forward of the rank owning its destination and in the
@@ -366,8 +379,8 @@ def partitioned_layer_forward(layer, x_own, part, group=None):
         mask = (min(float(layer.dropout_val), 1.0), seed)
     w, bw, a1, a2, b1, b2 = layer._packed()
     geom = (layer.input_channels, layer.output_channels, layer.num_heads, bool(layer.concat))
-    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group,
-                                        _peer_buffer(layer, geom, part, x_own, group))
+    peer = None if x_full is not None else _peer_buffer(layer, geom, part, x_own, group)
+    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group, peer, x_full)
 
 
 def _peer_buffer(layer, geom, part, x_own, group):
@@ -405,10 +418,12 @@ class PartitionedGATStack(torch.nn.Module):
         super().__init__()
         self.stack = stack
 
-    def forward(self, x_own, part, group=None):
+    def forward(self, x_own, part, group=None, x_full=None):
+        """x_full: the input features of ALL nodes when every rank holds them (a static graph's features are loaded once):
+        layer 1 then exchanges nothing in its forward (PartitionedGATFunction)."""
         convs = self.stack.convs
         for k, conv in enumerate(convs):
-            x_own = partitioned_layer_forward(conv, x_own, part, group)
+            x_own = partitioned_layer_forward(conv, x_own, part, group, x_full if k == 0 else None)
             if k + 1 < len(convs):
                 x_own = torch.nn.functional.elu(x_own)
         return x_own

@@ -327,7 +327,7 @@ class Runner:
         seed = rank if self.dp == "weak" else 0
         data, spec, loss_fn, desc = make_workload(name, seed=seed, heads=heads, num_graphs=num_graphs)
         self.global_data = data
-        mode = (f"row{world} (destination-row partition, all-gather of Wh / gout per layer, reduce-scatter of g_s_dst, grad all-reduce)"
+        mode = (f"row{world} (destination-row partition; input features replicated, so layer 1 exchanges nothing forward; all-gather of Wh (layers 2, 3) / gradient rows (all layers), reduce-scatter of g_s_dst, grad all-reduce)"
                 if self.partitioned else
                 f"dp{world} {self.dp} (independent graphs per rank, one-group NCCL all-reduce of the packed gradient buffers)")
         self.config, self.flush = describe_config(name, desc, data, spec, world, mode)
@@ -360,6 +360,9 @@ class Runner:
             self.x_h = data.x[self.part.lo:self.part.hi].contiguous().pin_memory()
             self.y_h = data.y[self.part.lo:self.part.hi].contiguous().pin_memory()
             self.ei_h = torch.zeros((2, 0), dtype=torch.int64).pin_memory()    # the partitioned graph is static and resident
+            # the static input features are replicated (loaded once, like the graph): layer 1 projects every node on every
+            # rank and exchanges nothing in its forward (partition.PartitionedGATFunction, x_full)
+            self.x_full_d = data.x.to(dev) if os.environ.get("B200GAT_REPLICATE_X", "1") == "1" else None
             torch.cuda.empty_cache()
         else:
             self.x_h, self.ei_h, self.y_h = data.x.pin_memory(), data.edge_index.pin_memory(), data.y.pin_memory()
@@ -375,7 +378,7 @@ class Runner:
         else:
             self.opt.zero_grad(set_to_none=True)
         if self.partitioned:
-            out = self.pmodel(x, self.part)
+            out = self.pmodel(x, self.part, x_full=self.x_full_d)
             # global mean loss = sum over ranks of (own sum / N); parameter gradients are then SUMMED over ranks
             loss = torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(out, dim=1), y, reduction="sum") / self.n
             loss.backward()

@@ -101,7 +101,7 @@ def test_partitioned_stages_match_single_gpu(case, dropout):
             assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 1e-5, k
 
 
-def _nccl_worker(rank, world, port, results, second_forward=False):
+def _nccl_worker(rank, world, port, results, second_forward=False, replicated_input=False):
     import torch.distributed as dist
     import GAT
     from atmlgraphattentionnetworks_b200 import partition as pt
@@ -121,7 +121,8 @@ def _nccl_worker(rank, world, port, results, second_forward=False):
     gout = torch.randn(n, h * c, generator=gen).to(dev)
     part = pt.build_row_partition(ei, n, world, rank)
     xo = x[part.lo:part.hi].clone().requires_grad_(True)
-    out = pt.partitioned_layer_forward(layer, xo, part)
+    # replicated_input: every rank holds the layer's input for all nodes and projects it itself (no forward exchange)
+    out = pt.partitioned_layer_forward(layer, xo, part, x_full=x if replicated_input else None)
     if second_forward:
         # a SECOND forward through the same layer before the first one's backward (an eval forward, a second micro-batch,
         # activation checkpointing): it overwrites the layer's persistent symmetric Wh buffer, which the first forward's
@@ -172,4 +173,20 @@ def test_partitioned_layer_peer_push_second_forward_before_backward():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, port, results, True), nprocs=2, join=True)
+    assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_partitioned_layer_nccl_replicated_input():
+    """layer 1 of a static graph: the input features are replicated, every rank projects all rows, nothing is exchanged
+    in the forward; results equal the single-GPU layer"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, results, False, True), nprocs=2, join=True)
     assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
