@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -87,7 +87,7 @@ class EdgeBwdPrepArgs(C.Structure):
                 ("gout", C.c_void_p), ("ldgo", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64),
                 ("o_heads", C.c_void_p), ("bias", C.c_void_p),
                 ("s_dst", C.c_void_p), ("rowmax", C.c_void_p), ("rowsum", C.c_void_p),
-                ("rowrec", C.c_void_p), ("g_pad", C.c_void_p), ("g_bias", C.c_void_p)]
+                ("rowrec", C.c_void_p), ("g_pad", C.c_void_p), ("g_bias", C.c_void_p), ("out_activation", C.c_int32)]
 
 
 class EdgeBwdCscArgs(C.Structure):
@@ -105,7 +105,7 @@ class EdgeBwdFinishArgs(C.Structure):
                 ("wh", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
                 ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("g_t", C.c_void_p),
                 ("g_bw", C.c_void_p), ("g_a1", C.c_void_p), ("g_a2", C.c_void_p),
-                ("g_b1", C.c_void_p), ("g_b2", C.c_void_p)]
+                ("g_b1", C.c_void_p), ("g_b2", C.c_void_p), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
 
 
 class ProjBwdArgs(C.Structure):

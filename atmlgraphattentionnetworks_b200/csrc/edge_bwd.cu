@@ -1457,8 +1457,10 @@ extern "C" int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* 
                   "edge_bwd_prep: forward output (out / o_heads) missing");
   B200GAT_REQUIRE(a->ldgo >= g.d_out && (!g.concat_like || a->ldo >= g.d_out), B200GAT_E_SHAPE, "edge_bwd_prep: leading dimension < D_out");
   B200GAT_REQUIRE(aligned16(a->rowrec), B200GAT_E_ALIGN, "edge_bwd_prep: rowrec must be 16-byte aligned");
+  B200GAT_REQUIRE(a->out_activation == ACT_NONE || a->out_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
+                  "edge_bwd_prep: unknown out_activation %d", a->out_activation);
   return run_prep(a->layer, a->num_rows, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum,
-                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, ACT_NONE, stream);
+                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, a->out_activation, stream);
 }
 
 extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream_) {
@@ -1491,6 +1493,17 @@ extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, vo
                   "edge_bwd_finish: NULL pointer");
   B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_t) && aligned16(a->a1) && aligned16(a->a2), B200GAT_E_ALIGN,
                   "edge_bwd_finish: wh / g_t / a1 / a2 must be 16-byte aligned");
+  uint32_t* amax = nullptr;
+  if (a->g_t_split && a->num_rows > 0) {
+    const Geom g = geom_of(a->layer);
+    const size_t need = blob_bytes(a->num_rows, g.Dp);
+    B200GAT_REQUIRE(a->g_t_split_bytes >= need, B200GAT_E_WORKSPACE, "edge_bwd_finish: g_t_split %zu < %zu bytes", a->g_t_split_bytes, need);
+    B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a->g_t_split) & 255u) == 0, B200GAT_E_ALIGN, "edge_bwd_finish: g_t_split must be 256-byte aligned");
+    // the five max-magnitude slots of the scale bound live in the spare words of the blob header
+    amax = reinterpret_cast<uint32_t*>(static_cast<char*>(a->g_t_split) + 16);
+    cudaError_t ce = cudaMemsetAsync(amax, 0, 5 * sizeof(uint32_t), stream);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd_finish: memset: %s", cudaGetErrorString(ce));
+  }
   return run_finish(a->layer, a->num_rows, a->wh, a->a1, a->a2, a->g_s_src, a->g_s_dst, a->g_t, a->g_bw, a->g_a1, a->g_a2,
-                    a->g_b1, a->g_b2, nullptr, nullptr, false, stream);
+                    a->g_b1, a->g_b2, a->num_rows > 0 ? a->g_t_split : nullptr, amax, false, stream);
 }

@@ -137,10 +137,12 @@ def peer_push_enabled(world):
     return env == "1" if env is not None else world == 2
 
 
-def stage_proj(geom, params, x_own, block, peer=None):
-    """-> wh [block, Dp] (rows >= n_own zero), s_src [block, H], s_dst [n_own, H]   (GAT.py:42-52 on own rows).
+def stage_proj(geom, params, x_own, block, peer=None, act_in=False, x_amax=None, keep_split=False):
+    """-> wh [block, Dp] (rows >= n_own zero), s_src [block, H], s_dst [n_own, H]   (GAT.py:42-52 on own rows)
+    [, x_split when keep_split: the tensor-core operand split of x kept for stage_proj_bwd, or None on the CUDA-core path].
     peer: a PeerBuffer — wh is then the own row block INSIDE the gathered buffer and the kernel also stores it into every
-    other rank's copy (rows >= n_own of the block are left untouched: no node id points at them)."""
+    other rank's copy (rows >= n_own of the block are left untouched: no node id points at them).
+    act_in / x_amax: the layer-boundary fusion of b200gat_proj_fwd (x is a pre-activation tensor, ELU applied on load)."""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     w, bw, a1, a2, b1, b2 = params
@@ -152,20 +154,26 @@ def stage_proj(geom, params, x_own, block, peer=None):
     stream = torch.cuda.current_stream(dev).cuda_stream
     ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
     ws = _workspace(ws_bytes, dev)
+    split_bytes = int(lib.b200gat_proj_split_bytes(ctypes.byref(layer), n)) if keep_split else 0
+    x_split = _workspace(split_bytes, dev) if split_bytes else None
     pa = _abi.ProjFwdArgs(layer, n, x_own.data_ptr(), x_own.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
                           a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(), s_src.data_ptr(),
-                          s_dst.data_ptr(), ws.data_ptr(), ws_bytes)
+                          s_dst.data_ptr(), ws.data_ptr(), ws_bytes, _ptr(x_split), split_bytes,
+                          _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(x_amax))
     if peer is not None:
         ptrs = peer.peer_ptrs()
         for k, ptr in enumerate(ptrs):
             pa.wh_peers[k] = ptr
         pa.num_peers = len(ptrs)
     _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
+    if keep_split:
+        return wh, s_src, s_dst, x_split
     return wh, s_src, s_dst
 
 
-def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask):
-    """-> out [n_own, D_out], rowmax, rowsum [n_own, H], o_heads or None   (GAT.py:53-67 for the own destination rows)"""
+def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask, out_amax=None):
+    """-> out [n_own, D_out], rowmax, rowsum [n_own, H], o_heads or None   (GAT.py:53-67 for the own destination rows)
+    out_amax: optional int32[1] device word <- bit pattern of max|out| over the OWN rows (the next layer's x_amax)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = wh_full.device, part.n_own
@@ -178,29 +186,31 @@ def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask):
     mask, drop = _split_mask(mask)      # [E', H] tensor in ORIGINAL (global) edge order, or (p, seed): in-kernel Philox
     ea = _abi.EdgeFwdArgs(layer, part.c_struct(), wh_full.data_ptr(), s_src_full.data_ptr(), s_dst_own.data_ptr(),
                           bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(), rowsum.data_ptr(),
-                          _ptr(o_heads), None, _abi.dropout_struct(drop))
+                          _ptr(o_heads), _ptr(out_amax), _abi.dropout_struct(drop))
     _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
     return out, rowmax, rowsum, o_heads
 
 
-def gather_layout(geom):
-    """Which rows the backward all-gathers: (direct, width, ldg, head_stride).  direct: gout itself is gatherable."""
+def gather_layout(geom, act_out=False):
+    """Which rows the backward all-gathers: (direct, width, ldg, head_stride).  direct: gout itself is gatherable (never
+    with a deferred output activation: the gathered rows are then gout * ELU'(out), written by the prep stage)."""
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     concat_like = concat or h == 1
-    if concat_like and c % 4 == 0:
+    if concat_like and c % 4 == 0 and not act_out:
         return True, d_out, d_out, c
     if concat_like:
         return False, dp, dp, cp
     return False, cp, cp, 0
 
 
-def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, block):
-    """-> rowrec [block, H, 4], g_rows [block, width] (zero padded), g_bias partial [D_out]"""
+def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, block, act_out=False):
+    """-> rowrec [block, H, 4], g_rows [block, width] (zero padded), g_bias partial [D_out]
+    act_out: gout is d/d ELU(out) of a layer whose activation was deferred to its consumer (concat-like layers)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = gout_own.device, gout_own.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
-    direct, width, _, _ = gather_layout(geom)
+    direct, width, _, _ = gather_layout(geom, act_out)
     rowrec = torch.zeros((block, h, 4), **f32)
     g_bias = torch.empty(d_out, **f32)
     if direct:
@@ -218,18 +228,18 @@ def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, blo
                               None if heads_mode else fwd_out_own.data_ptr(), d_out,
                               fwd_out_own.data_ptr() if heads_mode else None, bias.data_ptr(),
                               s_dst_own.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), rowrec.data_ptr(),
-                              _ptr(g_pad), g_bias.data_ptr())
+                              _ptr(g_pad), g_bias.data_ptr(), _abi.ACT_ELU if act_out else _abi.ACT_NONE)
     _call("b200gat_edge_bwd_prep", lib.b200gat_edge_bwd_prep, pa, stream, geom)
     return rowrec, g_rows, g_bias
 
 
-def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
+def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out=False):
     """-> g_wh [n_own, Dp], g_s_src [n_own, H], g_s_dst_full [P*block, H] (this rank's partial sums for ALL nodes)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = wh_own.device, part.n_own
     f32 = dict(dtype=torch.float32, device=dev)
-    _, _, ldg, hs = gather_layout(geom)
+    _, _, ldg, hs = gather_layout(geom, act_out)
     g_wh = torch.empty((n, dp), **f32)
     g_s_src = torch.empty((n, h), **f32)
     g_s_dst_full = torch.zeros((part.padded_rows, h), **f32)
@@ -245,8 +255,10 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask):
     return g_wh, g_s_src, g_s_dst_full
 
 
-def stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh):
-    """g_wh -> gT in place; -> (g_bw, g_a1, g_a2 [Dp], g_b1, g_b2 [H]) partial sums of the own block"""
+def stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh, want_split=False):
+    """g_wh -> gT in place; -> (g_bw, g_a1, g_a2 [Dp], g_b1, g_b2 [H]) partial sums of the own block [, g_split].
+    want_split: gT is written directly as the tensor-core operand split stage_proj_bwd consumes (no fp32 gT, no split
+    pass); g_split is None when the geometry's projection backward runs on the CUDA cores (g_wh then holds fp32 gT)."""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = wh_own.device, g_wh.shape[0]
@@ -254,14 +266,19 @@ def stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh):
     g_bw, g_a1, g_a2 = (torch.empty(dp, **f32) for _ in range(3))
     g_b1, g_b2 = (torch.empty(h, **f32) for _ in range(2))
     stream = torch.cuda.current_stream(dev).cuda_stream
+    gs_bytes = int(lib.b200gat_edge_bwd_split_bytes(ctypes.byref(layer), n)) if want_split else 0
+    g_split = _workspace(gs_bytes, dev) if gs_bytes else None
     fa = _abi.EdgeBwdFinishArgs(layer, n, wh_own.data_ptr(), a1.data_ptr(), a2.data_ptr(), g_s_src.data_ptr(),
                                 g_s_dst_own.data_ptr(), g_wh.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(),
-                                g_a2.data_ptr(), g_b1.data_ptr(), g_b2.data_ptr())
+                                g_a2.data_ptr(), g_b1.data_ptr(), g_b2.data_ptr(), _ptr(g_split), gs_bytes)
     _call("b200gat_edge_bwd_finish", lib.b200gat_edge_bwd_finish, fa, stream, geom)
+    if want_split:
+        return g_bw, g_a1, g_a2, g_b1, g_b2, g_split
     return g_bw, g_a1, g_a2, g_b1, g_b2
 
 
-def stage_proj_bwd(geom, g_t, x_own, w, need_gx):
+def stage_proj_bwd(geom, g_t, x_own, w, need_gx, x_split=None, g_split=None, act_in=False):
+    """x_split / g_split: the operand splits kept by stage_proj / written by stage_finish (skip the split passes)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = x_own.device, x_own.shape[0]
@@ -272,7 +289,10 @@ def stage_proj_bwd(geom, g_t, x_own, w, need_gx):
     ws_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
     ws = _workspace(ws_bytes, dev)
     pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x_own.data_ptr(), x_own.stride(0) if n else f_in, w.data_ptr(),
-                          _ptr(g_x), f_in, g_w.data_ptr(), ws.data_ptr(), ws_bytes)
+                          _ptr(g_x), f_in, g_w.data_ptr(), ws.data_ptr(), ws_bytes,
+                          _ptr(x_split), x_split.numel() if x_split is not None else 0,
+                          _abi.ACT_ELU if act_in else _abi.ACT_NONE,
+                          _ptr(g_split), g_split.numel() if g_split is not None else 0)
     _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, geom)
     return g_x, g_w
 
@@ -299,7 +319,12 @@ class PartitionedGATFunction(torch.autograd.Function):
     partial sums: all-reduce (SUM) them over ranks (parallel.GradBucket.all_reduce_mean(weight=1.0))."""
 
     @staticmethod
-    def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group, peer=None, x_full=None):
+    def forward(ctx, x_own, w, bw, a1, a2, b1, b2, bias, part, geom, mask, group, peer=None, x_full=None,
+                fuse=(False, False, None)):
+        # fuse = (act_in, act_out, x_amax): the layer-boundary fusions of gat.GATLayerFunction — the ELU between two layers
+        # is applied by the CONSUMER while it loads its operand, the producer's backward multiplies by ELU'(out).
+        # -> (out, out_amax): out_amax (int32[1]) bounds max|out| of the OWN rows for the next layer's operand scale
+        act_in, act_out, x_amax = fuse
         # x_full: the layer's input for ALL nodes, replicated on every rank (the static input features of layer 1).  The
         # rank then projects all N rows itself and NOTHING is exchanged in this layer's forward: for the 2.4 M-node graph
         # a 100 -> 512 projection of every node costs 2.5 ms, its all-gather (4.3 GB received per rank) 6-7 ms.
@@ -317,9 +342,10 @@ class PartitionedGATFunction(torch.autograd.Function):
                 wh_full, s_src_full, s_dst_full = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_full.contiguous(), n_all, None)
                 wh_pad, s_src_pad = wh_full[part.lo:], s_src_full[part.lo:]        # own rows first (only [:n_own] is used)
                 s_dst = s_dst_full[part.lo:part.hi]
-                peer = None
+                peer, x_split = None, None
             else:
-                wh_pad, s_src_pad, s_dst = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer)
+                wh_pad, s_src_pad, s_dst, x_split = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer,
+                                                               act_in=act_in, x_amax=x_amax, keep_split=True)
             if x_full is not None:
                 pass
             elif peer is not None:        # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
@@ -332,37 +358,43 @@ class PartitionedGATFunction(torch.autograd.Function):
             if x_full is None:
                 with _timed("all_gather_s_src", geom):
                     s_src_full = all_gather_rows(s_src_pad, group)
-            out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask)
+            out_amax = torch.zeros(1, dtype=torch.int32, device=x_own.device)
+            out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask, out_amax)
         n = part.n_own
         ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
+        ctx.act = (bool(act_in), bool(act_out))
         # peer mode: wh_pad is a view of the layer's persistent symmetric buffer, which the NEXT forward through this layer
         # overwrites through raw pointers (no autograd version bump) — an eval forward, a second micro-batch or activation
         # checkpointing between this forward and its backward would silently corrupt the saved Wh.  Keep a private copy.
         wh_saved = wh_pad[:n].clone() if peer is not None else wh_pad[:n]
         ctx.save_for_backward(x_own, w, a1, a2, bias, wh_saved, s_src_pad[:n], s_dst, rowmax, rowsum,
-                              out if o_heads is None else o_heads)
-        return out
+                              out if o_heads is None else o_heads, x_split)
+        ctx.mark_non_differentiable(out_amax)
+        return out, out_amax
 
     @staticmethod
-    def backward(ctx, gout):
-        x_own, w, a1, a2, bias, wh_own, s_src_own, s_dst, rowmax, rowsum, fwd_out = ctx.saved_tensors
+    def backward(ctx, gout, _g_amax):
+        x_own, w, a1, a2, bias, wh_own, s_src_own, s_dst, rowmax, rowsum, fwd_out, x_split = ctx.saved_tensors
         part, geom, mask, group = ctx.part, ctx.geom, ctx.mask, ctx.group
+        act_in, act_out = ctx.act
         gout = gout.contiguous()
         with torch.cuda.device(gout.device):
-            rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block)
+            rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block, act_out)
             with _timed("all_gather_g", geom):
                 g_full = all_gather_rows(g_rows, group)
             with _timed("all_gather_rowrec", geom):
                 rowrec_full = all_gather_rows(rowrec, group)
-            g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask)
+            g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out)
             with _timed("reduce_scatter_g_s_dst", geom):
                 g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
-            g_bw, g_a1, g_a2, g_b1, g_b2 = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh)
-            g_x, g_w = stage_proj_bwd(geom, g_wh, x_own, w, ctx.needs_input_grad[0])
-        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None, None, None
+            g_bw, g_a1, g_a2, g_b1, g_b2, g_split = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh,
+                                                                 want_split=True)
+            g_x, g_w = stage_proj_bwd(geom, g_wh, x_own, w, ctx.needs_input_grad[0], x_split, g_split, act_in)
+        return g_x, g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias, None, None, None, None, None, None, None
 
 
-def partitioned_layer_forward(layer, x_own, part, group=None, x_full=None):
+def partitioned_layer_forward(layer, x_own, part, group=None, x_full=None, act_in=False, act_out=False, x_amax=None,
+                              return_amax=False):
     """Run a GraphAttentionLayer module on the own block of a row-partitioned graph.  Attention dropout (GAT.py:61) is
     generated inside the kernels from (seed, ORIGINAL edge position, head): every rank uses rank 0's two seed words (one
     16-byte broadcast), so an edge gets the same multiplier in the forward of the rank owning its destination and in the
@@ -379,8 +411,12 @@ def partitioned_layer_forward(layer, x_own, part, group=None, x_full=None):
         mask = (min(float(layer.dropout_val), 1.0), seed)
     w, bw, a1, a2, b1, b2 = layer._packed()
     geom = (layer.input_channels, layer.output_channels, layer.num_heads, bool(layer.concat))
+    if act_out and not layer.can_fuse_activation_out():
+        raise ValueError("act_out needs a concat-like layer")
     peer = None if x_full is not None else _peer_buffer(layer, geom, part, x_own, group)
-    return PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group, peer, x_full)
+    out, amax = PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group, peer, x_full,
+                                             (bool(act_in), bool(act_out), x_amax))
+    return (out, amax) if return_amax else out
 
 
 def _peer_buffer(layer, geom, part, x_own, group):
@@ -422,8 +458,14 @@ class PartitionedGATStack(torch.nn.Module):
         """x_full: the input features of ALL nodes when every rank holds them (a static graph's features are loaded once):
         layer 1 then exchanges nothing in its forward (PartitionedGATFunction)."""
         convs = self.stack.convs
+        pending, amax = False, None          # pending: x_own is a pre-activation tensor whose ELU the next layer applies
+        last = len(convs) - 1
         for k, conv in enumerate(convs):
-            x_own = partitioned_layer_forward(conv, x_own, part, group, x_full if k == 0 else None)
-            if k + 1 < len(convs):
+            fuse_out = k < last and conv.can_fuse_activation_out()
+            # (x_amax bounds the OWN rows only — each rank projects its own rows, so that is all the operand scale needs)
+            x_own, amax = partitioned_layer_forward(conv, x_own, part, group, x_full if k == 0 else None, act_in=pending,
+                                                    act_out=fuse_out, x_amax=amax if pending else None, return_amax=True)
+            pending = fuse_out
+            if k < last and not fuse_out:
                 x_own = torch.nn.functional.elu(x_own)
         return x_own

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 11
+#define B200GAT_ABI_VERSION 12
 
 enum {
   B200GAT_OK = 0,
@@ -229,6 +229,7 @@ typedef struct {
   float* g_pad;                       /* out: padded / 1/H-scaled copy of G ([rows, Dp] if concat || H == 1 else
                                          [rows, c_pad]); NULL iff gout is directly gatherable (concat-like, C % 4 == 0) */
   float* g_bias;                      /* out [D_out] (this block's partial column sums) */
+  int32_t out_activation;             /* as in b200gat_edge_bwd_args: gout is d/d act(out); needs g_pad (G = gout * act'(out)) */
 } b200gat_edge_bwd_prep_args;
 int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* stream);
 
@@ -262,6 +263,8 @@ typedef struct {
   float* g_t;                         /* in: g_wh, out: gT  [rows, Dp] */
   float* g_bw; float* g_a1; float* g_a2;   /* out [Dp] (partial sums of this block) */
   float* g_b1; float* g_b2;           /* out [H] */
+  void* g_t_split; size_t g_t_split_bytes;   /* optional out, as in b200gat_edge_bwd_args: gT as the tensor-core operand split
+                                         consumed by b200gat_proj_bwd (g_t then keeps the un-finished gWh) */
 } b200gat_edge_bwd_finish_args;
 int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream);
 

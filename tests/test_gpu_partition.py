@@ -190,3 +190,60 @@ def test_partitioned_layer_nccl_replicated_input():
     results = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, port, results, False, True), nprocs=2, join=True)
     assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
+
+
+def _nccl_stack_worker(rank, world, port, results):
+    """3-layer stack row-partitioned over 2 GPUs (fused ELU boundaries, kept operand splits, replicated input for layer 1,
+    in-kernel dropout with rank 0's seed) against the single-GPU GATStack on rank 0 fed the SAME dropout masks."""
+    import torch.distributed as dist
+    from atmlgraphattentionnetworks_b200 import partition as pt
+    from atmlgraphattentionnetworks_b200.gat import dropout_mask_tensor
+    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n, e, f = 3001, 40000, 64
+    spec = [(f, 64, 4, True), (256, 32, 4, True), (128, 7, 2, False)]
+    torch.manual_seed(0)
+    model = GATStack(spec, dropout=0.5).to(dev).train()
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(n, f, generator=gen).to(dev)
+    ei = torch.randint(0, n, (2, e), generator=gen).to(dev)
+    gout = torch.randn(n, 7, generator=gen).to(dev)
+    part = pt.build_row_partition(ei, n, world, rank)
+    pmodel = pt.PartitionedGATStack(model)
+    xo = x[part.lo:part.hi].clone().requires_grad_(True)
+    out = pmodel(xo, part, x_full=x)
+    seeds = [c._last_dropout_seed.clone() for c in model.convs]
+    out.backward(gout[part.lo:part.hi])
+    flat = torch.cat([p.grad.flatten() for p in model.parameters()])
+    dist.all_reduce(flat)
+    if rank == 0:
+        model.zero_grad()
+        for c, s in zip(model.convs, seeds):
+            m = dropout_mask_tensor(0.5, s, e + n, c.num_heads)
+            c.mask_hook = (lambda mm: (lambda shape: mm))(m)
+        xr = x.clone().requires_grad_(True)
+        ref = model(xr, ei)
+        ref.backward(gout)
+        flat_ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+        results["out"] = nerr(out.detach().cpu().numpy(), ref[part.lo:part.hi].detach().cpu().numpy())
+        results["gp"] = float((flat - flat_ref).abs().max() / flat_ref.abs().max())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_partitioned_stack_nccl_fused_boundaries_and_dropout():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_nccl_stack_worker, args=(2, port, results), nprocs=2, join=True)
+    assert results["out"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
