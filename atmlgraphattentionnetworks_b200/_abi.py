@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -114,7 +114,8 @@ class ProjBwdArgs(C.Structure):
                 ("g_x", C.c_void_p), ("ldgx", C.c_int64), ("g_w", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
-                ("x_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t)]
+                ("x_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t),
+                ("parts", C.c_int32)]
 
 
 class ReadoutGeom(C.Structure):
@@ -138,6 +139,7 @@ class ReadoutBwdArgs(C.Structure):
 
 
 ACT_NONE, ACT_ELU = 0, 1
+PROJ_BWD_GX, PROJ_BWD_GW = 1, 2
 LOGIT_LEAKY_RELU, LOGIT_LOGSIGMOID, LOGIT_TANH, LOGIT_HEAD_SOFTMAX = 0, 1, 2, 3
 
 _SIGNATURES = {

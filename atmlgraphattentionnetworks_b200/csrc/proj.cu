@@ -117,8 +117,10 @@ extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
   const b200gat_layer& L = a->layer;
   const int64_t N = a->num_nodes, F = L.in_channels, Dp = L.heads * L.c_pad;
   B200GAT_REQUIRE(N >= 0, B200GAT_E_SHAPE, "proj_bwd: negative num_nodes");
-  B200GAT_REQUIRE(a->g_w && a->w, B200GAT_E_NULL, "proj_bwd: NULL pointer");
+  B200GAT_REQUIRE(a->parts >= 0 && a->parts <= B200GAT_PROJ_BWD_GW, B200GAT_E_SHAPE, "proj_bwd: unknown parts %d", a->parts);
+  B200GAT_REQUIRE((a->g_w || a->parts == B200GAT_PROJ_BWD_GX) && a->w, B200GAT_E_NULL, "proj_bwd: NULL pointer");
   if (N == 0) {
+    if (a->parts == B200GAT_PROJ_BWD_GX) return 0;
     cudaError_t e = cudaMemsetAsync(a->g_w, 0, size_t(Dp) * F * sizeof(float), stream);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "proj_bwd: memset: %s", cudaGetErrorString(e));
     return 0;
@@ -129,10 +131,11 @@ extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->ldx >= F && (!a->g_x || a->ldgx >= F), B200GAT_E_SHAPE, "proj_bwd: leading dimension < in_channels");
   if (proj_tc_bwd_supported(L, N)) return proj_tc_bwd(*a, stream);
   B200GAT_REQUIRE(a->g_t && a->x, B200GAT_E_NULL, "proj_bwd: the CUDA-core path needs fp32 g_t and x");
-  if (a->g_x) {
+  if (a->g_x && a->parts != B200GAT_PROJ_BWD_GW) {
     rc = gemm_simt<true, false>(a->g_t, Dp, a->w, F, a->g_x, a->ldgx, nullptr, N, F, Dp, 1, stream);
     if (rc) return rc;
   }
+  if (a->parts == B200GAT_PROJ_BWD_GX) return 0;
   // gW[Dp,F] = sum_n gT[n,:]^T X[n,:] — reduction over nodes, split so that the grid covers the machine
   const int64_t tiles = ceil_div(Dp, GM) * ceil_div(F, GN);
   int64_t splits = ceil_div(int64_t(sm_count()) * 4, tiles);

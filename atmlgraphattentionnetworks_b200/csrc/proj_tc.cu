@@ -859,13 +859,15 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   const Blob X = make_blob(have_x ? const_cast<void*>(a.x_split) : static_cast<void*>(base + wb + (have_g ? 0 : gb)), N, F);
   if (!have_g && (rc = launch_split(a.g_t, Dp, G, stream))) return rc;
   if (!have_x && (rc = launch_split(a.x, a.ldx, X, stream, a.x_activation))) return rc;
-  if (a.g_x) {
+  const bool want_gx = a.g_x && a.parts != B200GAT_PROJ_BWD_GW, want_gw = a.parts != B200GAT_PROJ_BWD_GX;
+  if (want_gx) {
     // gX[N,F] = gT[N,Dp] · W[Dp,F] : K = Dp; B = the W planes read MN-major (F contiguous)
     if ((rc = launch_split(a.w, F, W, stream))) return rc;
     TcGemmParams p{};
     p.C = a.g_x; p.ldc = a.ldgx;
     if ((rc = gemm_blobs<false, true, EPI_STORE>(G, W, N, F, Dp, p, 1, stream))) return rc;
   }
+  if (!want_gw) return 0;
   // gW[Dp,F] = gT^T · X : K = nodes; both operands MN-major straight from the row-major planes; split-K across CTAs
   // with a red.global.add epilogue
   cudaError_t ce = cudaMemsetAsync(a.g_w, 0, size_t(Dp) * F * sizeof(float), stream);

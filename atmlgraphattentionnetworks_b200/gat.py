@@ -58,6 +58,38 @@ class _timed:
         return False
 
 
+# OPT-IN (B200GAT_OVERLAP_GW=1).  Measured on one B200: PPI-shaped step 5.30 -> 5.20 ms (the gW GEMM of layer k + 1 overlaps
+# layer k's edge backward), but the 2.4 M-node graph's step went 177 -> 234 ms — the GB-sized buffers that now live across two
+# streams defeat the caching allocator's reuse.  Off by default.
+_OVERLAP_GW = __import__("os").environ.get("B200GAT_OVERLAP_GW", "0") == "1"
+_side_streams = {}
+_join_pending = set()
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
+def _queue_join(dev, main, side):
+    """main waits for side once, when the running backward pass ends (autograd engine final callback — what DDP uses to
+    finalise its buckets); outside a backward pass (a direct .backward of the Function in tests) join immediately."""
+    key = (dev.type, dev.index)
+    if key in _join_pending:
+        return
+
+    def join():
+        _join_pending.discard(key)
+        main.wait_stream(side)
+    try:
+        _join_pending.add(key)
+        torch.autograd.Variable._execution_engine.queue_callback(join)
+    except RuntimeError:
+        join()
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -197,12 +229,37 @@ class GATLayerFunction(torch.autograd.Function):
                                   _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
-            ws2 = _workspace(ws2_bytes, dev)
-            pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
-                                  _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes,
-                                  _ptr(x_split), x_split.numel() if x_split is not None else 0,
-                                  _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes)
-            _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, stream, ctx.geom)
+
+            def proj_bwd(parts, strm):
+                ws2 = _workspace(ws2_bytes, dev)
+                pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
+                                      _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes,
+                                      _ptr(x_split), x_split.numel() if x_split is not None else 0,
+                                      _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes, parts)
+                _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, strm, ctx.geom)
+                return ws2
+            # gX feeds the previous layer's backward; gW feeds nobody until the optimizer.  When this layer has a
+            # predecessor waiting (need_gx) and the tensor-core path runs (gs_bytes), gW is issued on a side stream so that
+            # it overlaps the predecessor's edge backward (memory-bound, while the GEMM is tensor-bound); the streams are
+            # joined by an autograd-engine callback at the end of the backward pass.  Not when a parameter already holds a
+            # gradient: AccumulateGrad would then add into it on the main stream before the side stream has finished.
+            overlap = (need_gx and gs_bytes and _abi.timing is None and _OVERLAP_GW
+                       and all(p.grad is None for p in ctx.params))
+            if overlap:
+                main = torch.cuda.current_stream(dev)
+                side = _side_stream(dev)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                proj_bwd(_abi.PROJ_BWD_GX, stream)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    ws_side = proj_bwd(_abi.PROJ_BWD_GW, side.cuda_stream)
+                for t in (g_w, g_t, g_split, x_split, x, ws_side):
+                    if t is not None:
+                        t.record_stream(side)
+                _queue_join(dev, main, side)
+            else:
+                proj_bwd(0, stream)
             _abi.launches += 2
         # per-head gradients are views of the packed buffers, in the order of _head_parameters (autograd takes them as
         # the parameters' .grad without a copy when no gradient is accumulated yet)

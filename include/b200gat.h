@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 12
+#define B200GAT_ABI_VERSION 13
 
 enum {
   B200GAT_OK = 0,
@@ -281,7 +281,12 @@ typedef struct {
   const void* x_split; size_t x_split_bytes;   /* optional in: the split of x written by b200gat_proj_fwd */
   int32_t x_activation;               /* as in the forward (used when x_split is absent) */
   const void* g_t_split; size_t g_t_split_bytes;   /* optional in: gT as written by b200gat_edge_bwd (g_t may be NULL) */
+  int32_t parts;                      /* 0 = both products; B200GAT_PROJ_BWD_GX / _GW = only that one.  The two GEMMs are
+                                         independent: a caller may issue gW on a second stream so that it overlaps the
+                                         previous layer's edge backward, which only waits for gX (each call needs its own
+                                         workspace) */
 } b200gat_proj_bwd_args;
+enum { B200GAT_PROJ_BWD_GX = 1, B200GAT_PROJ_BWD_GW = 2 };
 size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);
 
