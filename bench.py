@@ -685,6 +685,21 @@ class Runner:
                 roofline["regime"] = "cached: gathered rows are L2-resident, the kernel is bound by L2->SM gather traffic (DESIGN.md §5)"
             elif roofline["bound"] == "hbm":
                 roofline["regime"] = "streaming: every gathered row comes from HBM"
+        # SURVEY.md §8d caveat 2: whatever the HBM count says, every edge pulls its gathered row through L2 -> SM:
+        # 4 (D + H) bytes in the forward, 4 (D_out + 4 H) in the backward.  The "gather service rate" is that traffic over the
+        # edge-kernel time; the bare 128-bit gather loop of tools/microbench/gather_bench.cu reaches 18 TB/s on the L2-resident
+        # PPI-shaped batch and 6.0-6.7 TB/s from HBM on the power-law graph — the bound of the cached regime
+        for rec in kernels:
+            li = rec["layer"]
+            f, c, h, concat = self.spec[li]
+            d = h * c
+            d_out = d if concat else c
+            if rec["op"] == "b200gat_edge_fwd":
+                rec["gather_bytes"] = 4 * ep_loc * (d + h)
+            elif rec["op"] == "b200gat_edge_bwd":
+                rec["gather_bytes"] = 4 * ep_loc * (d_out + 4 * h)
+            if "gather_bytes" in rec:
+                rec["gather_TBps"] = rec["gather_bytes"] / rec["ms"] / 1e9
         edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
         edge_bytes = sum(r["alg_bytes"] for r in kernels if r["op"].startswith("b200gat_edge"))
         edge_phase = {"per_rank": self.partitioned, "ms": edge_ms, "alg_bytes": edge_bytes,
@@ -692,6 +707,15 @@ class Runner:
                       "frac_of_measured_hbm": edge_bytes / edge_ms / 1e6 / peaks["hbm"] if edge_ms else None,
                       "frac_of_nominal_8TBps": edge_bytes / edge_ms / 1e6 / 8000.0 if edge_ms else None,
                       "edges_per_s": len(self.spec) * ep_loc / (edge_ms / 1e3) if edge_ms else None}
+        gbytes = sum(r.get("gather_bytes", 0) for r in kernels)
+        if edge_ms and gbytes:
+            ref_rate = 18.0 if cached else 6.5      # TB/s: the bare gather loop on this regime (gather_bench.cu, round 1)
+            edge_phase.update({"gather_bytes_through_l2": gbytes, "gather_service_TBps": gbytes / edge_ms / 1e9,
+                               "bare_gather_loop_TBps": ref_rate,
+                               "frac_of_bare_gather_loop": gbytes / edge_ms / 1e9 / ref_rate,
+                               "gather_note": ("cached regime: rows come from L2; the whole op (prep / finish streaming passes "
+                                               "included) is compared with a loop that does nothing but the gathers"
+                                               if cached else "streaming regime: rows come from HBM")})
         return kernels, roofline, edge_phase, (coll or None)
 
     def close(self):

@@ -3,7 +3,7 @@
 The kernels of a step run in the order  [proj_fwd, edge_fwd] x layers, then [edge_bwd, proj_bwd] x layers reversed;
 consecutive launches of one class form one op.  bench.py reads the JSON to fill `roofline.traffic` (measured
 dram__bytes_read.sum + dram__bytes_write.sum, summed over the op's kernels) next to the algorithmic bytes."""
-import csv, io, json, subprocess, sys
+import csv, io, json, os, subprocess, sys
 
 # checked in this order ("gt_amax_kernel" must win over "amax_kernel")
 CLASSES = {"EB": ("bwd_prep", "colsum_kernel", "edge_bwd_", "gt_amax_kernel", "bwd_finish_kernel"),
@@ -44,7 +44,8 @@ def main(rep, out_path):
             layer, op = layers - 1 - j // 2, ("b200gat_edge_bwd" if cls == "EB" else "b200gat_proj_bwd")
         ops[f"{op}:{layer}"] = {"dram_bytes": sum(r[1] for r in recs), "us_under_ncu": sum(r[2] for r in recs),
                                 "kernels": [r[0].replace("b200gat::", "").replace("void ", "") for r in recs]}
-    json.dump({"source": rep, "ops": ops}, open(out_path, "w"), indent=1)
+    sha = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or os.environ.get("B200GAT_GIT_SHA")
+    json.dump({"source": rep, "git_sha": sha, "ops": ops}, open(out_path, "w"), indent=1)
     for k, v in ops.items():
         print(f"{k:24s} {v['dram_bytes'] / 1e6:9.1f} MB  {v['us_under_ncu']:8.1f} us  {len(v['kernels'])} kernels")
 
