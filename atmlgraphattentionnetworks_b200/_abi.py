@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -55,7 +55,7 @@ class ProjFwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
                 ("x_activation", C.c_int32), ("x_amax", C.c_void_p),
-                ("wh_peers", C.c_void_p * 7), ("num_peers", C.c_int32)]
+                ("wh_peers", C.c_void_p * 7), ("num_peers", C.c_int32), ("wh_bf16", C.c_void_p)]
 
 
 class EdgeFwdArgs(C.Structure):
@@ -64,7 +64,7 @@ class EdgeFwdArgs(C.Structure):
                 ("mask", C.c_void_p),
                 ("out", C.c_void_p), ("ldo", C.c_int64),
                 ("rowmax", C.c_void_p), ("rowsum", C.c_void_p), ("o_heads", C.c_void_p), ("out_amax", C.c_void_p),
-                ("dropout", Dropout)]
+                ("dropout", Dropout), ("wh_bf16", C.c_void_p)]
 
 
 class EdgeBwdArgs(C.Structure):
@@ -79,7 +79,8 @@ class EdgeBwdArgs(C.Structure):
                 ("g_b1", C.c_void_p), ("g_b2", C.c_void_p), ("g_bias", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("out_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t),
-                ("dropout", Dropout), ("edge_scratch", C.c_void_p), ("edge_scratch_bytes", C.c_size_t)]
+                ("dropout", Dropout), ("edge_scratch", C.c_void_p), ("edge_scratch_bytes", C.c_size_t),
+                ("gather_bf16", C.c_int32)]
 
 
 class EdgeBwdPrepArgs(C.Structure):
@@ -87,7 +88,8 @@ class EdgeBwdPrepArgs(C.Structure):
                 ("gout", C.c_void_p), ("ldgo", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64),
                 ("o_heads", C.c_void_p), ("bias", C.c_void_p),
                 ("s_dst", C.c_void_p), ("rowmax", C.c_void_p), ("rowsum", C.c_void_p),
-                ("rowrec", C.c_void_p), ("g_pad", C.c_void_p), ("g_bias", C.c_void_p), ("out_activation", C.c_int32)]
+                ("rowrec", C.c_void_p), ("g_pad", C.c_void_p), ("g_bias", C.c_void_p), ("out_activation", C.c_int32),
+                ("g_pad_bf16", C.c_void_p)]
 
 
 class EdgeBwdCscArgs(C.Structure):
@@ -97,7 +99,7 @@ class EdgeBwdCscArgs(C.Structure):
                 ("g", C.c_void_p), ("ldg", C.c_int64), ("g_head_stride", C.c_int64),
                 ("g_wh", C.c_void_p), ("g_s_src", C.c_void_p), ("g_s_dst", C.c_void_p), ("span", C.c_int64),
                 ("hub_cols", C.c_void_p), ("num_hub_cols", C.c_int64), ("colend", C.c_void_p),
-                ("max_out_degree", C.c_int64), ("dropout", Dropout)]
+                ("max_out_degree", C.c_int64), ("dropout", Dropout), ("g_bf16", C.c_void_p)]
 
 
 class EdgeBwdFinishArgs(C.Structure):

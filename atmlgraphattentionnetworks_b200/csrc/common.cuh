@@ -58,6 +58,30 @@ __device__ __forceinline__ float4 ldg4_row(const char* base, int row, uint32_t r
   return __ldg(reinterpret_cast<const float4*>(base + static_cast<uint64_t>(static_cast<uint32_t>(row)) * row_bytes));
 }
 
+// ---- optional bf16 storage of the GATHERED rows (Wh in the forward, the gradient rows G in the backward): halves the bytes
+// every edge pulls through L2 / HBM (and over NVLink in the row-partitioned mode) at a separately stated tolerance
+// (DESIGN.md §4.11); all arithmetic stays fp32.  ROW16 = false is the default fp32 path, untouched.
+template <bool ROW16>
+__device__ __forceinline__ const char* row_base(const float* rows32, const void* rows16, int64_t elem) {
+  return ROW16 ? static_cast<const char*>(rows16) + elem * 2 : reinterpret_cast<const char*>(rows32 + elem);
+}
+template <bool ROW16>
+__device__ __forceinline__ float4 gather4(const char* base, int row, uint32_t row_bytes) {
+  if (!ROW16) return ldg4_row(base, row, row_bytes);
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(base + static_cast<uint64_t>(static_cast<uint32_t>(row)) * row_bytes));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+// four fp32 values -> four bf16 (round to nearest even), packed in 8 bytes
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  auto rn = [](float f) -> uint32_t {
+    const uint32_t u = __float_as_uint(f);
+    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;                       // inf / nan: truncate
+    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+  };
+  return make_uint2(rn(a) | (rn(b) << 16), rn(c) | (rn(d) << 16));
+}
+
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
 
 // logit activation e = f(z) and f'(z) (include/b200gat.h B200GAT_LOGIT_*).  GENERIC = false is the LeakyReLU of GAT.py:30

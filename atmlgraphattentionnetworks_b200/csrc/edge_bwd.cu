@@ -35,6 +35,7 @@ struct PrepParams {
   float gscale;                       // 1 or 1/H
   int act;                            // 1: gout is d/d ELU(out) (concat_like only): G = gout * ELU'(out), needs gp
   float* gp; int64_t ldgp;            // optional padded copy: concat_like ? [N, H*Cp] : [N, Cp]
+  int gp16;                           // the copy is stored as bf16 (same element layout, 2-byte elements)
   float4* rowrec;                     // [N, H] {s_dst, rowmax, 1/(rowsum + 1e-16), Drow}
 };
 
@@ -74,7 +75,11 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepParams p) {
           }
           d = fmaf(gv, o, d);
         }
-        if (p.gp && (p.concat_like || h == 0)) p.gp[i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c] = gv;
+        if (p.gp && (p.concat_like || h == 0)) {
+          const int64_t e = i * p.ldgp + (p.concat_like ? h * p.Cp : 0) + c;
+          if (p.gp16) reinterpret_cast<uint16_t*>(p.gp)[e] = static_cast<uint16_t>(pack_bf16x4(gv, 0.f, 0.f, 0.f).x & 0xffffu);
+          else p.gp[e] = gv;
+        }
       }
     }
     d = group_sum<32>(d);
@@ -94,7 +99,8 @@ struct PrepRowsParams {
   const float* out; int64_t ldo;      // forward output BEFORE the activation (O = out - bias)
   const float* bias;
   const float* s_dst; const float* rowmax; const float* rowsum;
-  float* gp;                          // [N, D] (ACT only)
+  float* gp;                          // [N, D] (ACT, or gp16: then ALWAYS written, as bf16)
+  int gp16;
   float4* rowrec;
   float* g_bias;                      // [D], zero-initialised, accumulated atomically
 };
@@ -137,8 +143,9 @@ __global__ void __launch_bounds__(256, 2) bwd_prep_rows_kernel(const PrepRowsPar
           if (ACT) {
             gv[u].x *= elu_grad(ov[u].x); gv[u].y *= elu_grad(ov[u].y);
             gv[u].z *= elu_grad(ov[u].z); gv[u].w *= elu_grad(ov[u].w);
-            *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * q) = gv[u];
           }
+          if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + i * int64_t(p.D) + 4 * q) = pack_bf16x4(gv[u].x, gv[u].y, gv[u].z, gv[u].w);
+          else if (ACT) *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * q) = gv[u];
           cs[t].x += gv[u].x; cs[t].y += gv[u].y; cs[t].z += gv[u].z; cs[t].w += gv[u].w;
           pd[t] = gv[u].x * (ov[u].x - bv.x) + gv[u].y * (ov[u].y - bv.y) + gv[u].z * (ov[u].z - bv.z) + gv[u].w * (ov[u].w - bv.w);
         }
@@ -215,8 +222,9 @@ __global__ void __launch_bounds__(256) bwd_prep_rows_narrow_kernel(const PrepRow
       ov = ldg4(p.out + i * p.ldo + 4 * gl);
       if (ACT) {
         gv.x *= elu_grad(ov.x); gv.y *= elu_grad(ov.y); gv.z *= elu_grad(ov.z); gv.w *= elu_grad(ov.w);
-        *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * gl) = gv;
       }
+      if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + i * int64_t(p.D) + 4 * gl) = pack_bf16x4(gv.x, gv.y, gv.z, gv.w);
+      else if (ACT) *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * gl) = gv;
     }
     cs.x += gv.x; cs.y += gv.y; cs.z += gv.z; cs.w += gv.w;
     float d = gv.x * (ov.x - bv.x) + gv.y * (ov.y - bv.y) + gv.z * (ov.z - bv.z) + gv.w * (ov.w - bv.w);
@@ -260,6 +268,7 @@ struct PrepMeanParams {
   const float* o_heads;               // [N, H, Cp], 16-byte aligned
   const float* s_dst; const float* rowmax; const float* rowsum;
   float* gp;                          // [N, Cp]
+  int gp16;
   float4* rowrec;
   float* g_bias;                      // [C], zero-initialised, accumulated atomically
 };
@@ -288,7 +297,8 @@ __global__ void __launch_bounds__(256) bwd_prep_mean_rows_kernel(const PrepMeanP
         if (c + 3 < p.C) gv[t].w = __ldg(g + c + 3);
         cs[t].x += gv[t].x; cs[t].y += gv[t].y; cs[t].z += gv[t].z; cs[t].w += gv[t].w;
         gv[t].x *= gscale; gv[t].y *= gscale; gv[t].z *= gscale; gv[t].w *= gscale;
-        *reinterpret_cast<float4*>(p.gp + i * int64_t(p.Cp) + c) = gv[t];
+        if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + i * int64_t(p.Cp) + c) = pack_bf16x4(gv[t].x, gv[t].y, gv[t].z, gv[t].w);
+        else *reinterpret_cast<float4*>(p.gp + i * int64_t(p.Cp) + c) = gv[t];
       }
     }
     const float* o = p.o_heads + i * int64_t(p.H) * p.Cp;
@@ -358,6 +368,7 @@ struct EdgeBwdParams {
   const float* wh; const float* s_src; const float4* rowrec;
   DropoutSpec drop;                        // attention dropout: mask tensor or in-kernel Philox (common.cuh)
   const float* g; int64_t ldg; int hs;     // G[i,h,c] = g[i*ldg + h*hs + c]   (hs = 0: shared by all heads)
+  const void* g16;                         // the same rows stored as bf16 (ROW16 instantiations gather these instead)
   float* gwh;                              // [N, Dp]
   float* g_s_src; float* g_s_dst;          // [N, H]; g_s_dst is zero-initialised and accumulated atomically
   // scheduling by degree (b200gat_graph.hub_cols): colend[j] = colptr[j + 1] except for hub source rows, which look
@@ -430,7 +441,7 @@ __device__ __forceinline__ float reduce_deliver(float (&d)[U], int lane, int rel
   return got;
 }
 
-template <int G, int NV, bool HAS_MASK, bool GENERIC, bool HUB>
+template <int G, int NV, bool HAS_MASK, bool GENERIC, bool HUB, bool ROW16 = false>
 __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -446,7 +457,7 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
-  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored; their Wh slice is zero
@@ -482,7 +493,7 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
     float gsrc = 0.f;
     const char* gb[NV];                                   // this lane's column slices of row 0 of G[:, h, :]
 #pragma unroll
-    for (int v = 0; v < NV; ++v) gb[v] = reinterpret_cast<const char*>(p.g + h * p.hs + off[v]);
+    for (int v = 0; v < NV; ++v) gb[v] = row_base<ROW16>(p.g, p.g16, h * p.hs + off[v]);
 
     for (int k0 = 0; k0 < maxdeg; k0 += G) {
       const int k = beg + k0 + gl;
@@ -521,9 +532,9 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdParams& p) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6): dz needs no dot product, skip the gather
-              g4[u][v] = a_t[u] != 0.f ? ldg4_row(gb[v], it[u], g_row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+              g4[u][v] = a_t[u] != 0.f ? gather4<ROW16>(gb[v], it[u], g_row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-              g4[u][v] = ldg4_row(gb[v], it[u], g_row_bytes);
+              g4[u][v] = gather4<ROW16>(gb[v], it[u], g_row_bytes);
             }
           }
         }
@@ -579,6 +590,11 @@ template <int G, int NV, bool HAS_MASK, bool HUB>
 __global__ void __launch_bounds__(256, (NV <= 2 && !HAS_MASK) ? 4 : 2) edge_bwd_kernel(const EdgeBwdParams p) {
   edge_bwd_body<G, NV, HAS_MASK, false, HUB>(p);
 }
+// bf16-stored gradient rows (no mask, LeakyReLU)
+template <int G, int NV, bool HUB>
+__global__ void __launch_bounds__(256, NV <= 2 ? 4 : 2) edge_bwd16_kernel(const EdgeBwdParams p) {
+  edge_bwd_body<G, NV, false, false, HUB, true>(p);
+}
 // other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
 template <int G, int NV>
 __global__ void __launch_bounds__(256) edge_bwd_act_kernel(const EdgeBwdParams p) { edge_bwd_body<G, NV, true, true, true>(p); }
@@ -612,7 +628,7 @@ __device__ __forceinline__ float transpose_reduce(float (&d)[V], int gl) {
 
 __host__ __device__ constexpr int pow2ceil_c(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int G, int HH, bool HAS_MASK>
+template <int G, int HH, bool HAS_MASK, bool ROW16 = false>
 __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -626,11 +642,11 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
-  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   const bool live = gl < Q;                               // dead lanes gather a clamped (valid) column; their Wh slice is zero
   const int off = 4 * (live ? gl : Q - 1);
-  const char* gb = reinterpret_cast<const char*>(p.g + off);
+  const char* gb = row_base<ROW16>(p.g, p.g16, off);
 
   const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
   float amax_w = 0.f, amax_s = 0.f;
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_mean_kernel(const EdgeBwdPara
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int it = __shfl_sync(FULL, i, t + u, G);
-          g4[u] = ldg4_row(gb, it, g_row_bytes);
+          g4[u] = gather4<ROW16>(gb, it, g_row_bytes);
         }
         float d[V];
 #pragma unroll
@@ -752,7 +768,8 @@ static int launch_edge_bwd_mean(const EdgeBwdParams& p, cudaStream_t stream) {
   const int64_t want = ceil_div(ceil_div(p.N, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  if (p.drop.active()) edge_bwd_mean_kernel<G, HH, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.g16) edge_bwd_mean_kernel<G, HH, false, true><<<blocks, threads, 0, stream>>>(p);
+  else if (p.drop.active()) edge_bwd_mean_kernel<G, HH, true><<<blocks, threads, 0, stream>>>(p);
   else edge_bwd_mean_kernel<G, HH, false><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_bwd_mean_kernel");
 }
@@ -776,7 +793,7 @@ static bool edge_bwd_mean_supported(int H, int Q, int hs, int act) {
 // ---- hub source rows (out-degree > B200GAT_HUB_DEGREE): one CTA per (source row, head); the 8 warps walk interleaved
 // 32-edge chunks of the column (same arithmetic as edge_bwd_body with a full-warp group) and merge their gWh / g_s_src
 // partial sums through shared memory.  Handles every logit activation and the optional mask at run time.
-template <int NV>
+template <int NV, bool ROW16 = false>
 __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
@@ -785,7 +802,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
-  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * 4u;
+  const uint32_t g_row_bytes = static_cast<uint32_t>(p.ldg) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   const int act = p.act;
   int off[NV];
@@ -818,7 +835,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
     float gsrc = 0.f;
     const char* gb[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) gb[v] = reinterpret_cast<const char*>(p.g + h * p.hs + off[v]);
+    for (int v = 0; v < NV; ++v) gb[v] = row_base<ROW16>(p.g, p.g16, h * p.hs + off[v]);
     for (int k0 = beg + w * 32; k0 < end; k0 += 256) {
       const int k = k0 + lane;
       const bool ok = k < end;
@@ -853,7 +870,7 @@ __global__ void __launch_bounds__(256) edge_bwd_hub_kernel(const EdgeBwdParams p
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) g4[u][v] = ldg4_row(gb[v], it[u], g_row_bytes);
+          for (int v = 0; v < NV; ++v) g4[u][v] = gather4<ROW16>(gb[v], it[u], g_row_bytes);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -926,7 +943,12 @@ static int launch_edge_bwd_hub(const EdgeBwdParams& p, cudaStream_t stream) {
   B200GAT_REQUIRE(nseg <= 65535, B200GAT_E_UNSUPPORTED, "edge_bwd: a source row of %d edges is not supported", p.max_deg);
   const dim3 blocks(static_cast<unsigned>(want < cap ? want : cap), static_cast<unsigned>(nseg));
   const int Q = p.Cp / 4;
-  if (Q <= 32) edge_bwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
+  if (p.g16) {
+    if (Q <= 32) edge_bwd_hub_kernel<1, true><<<blocks, 256, 0, stream>>>(p);
+    else if (Q <= 64) edge_bwd_hub_kernel<2, true><<<blocks, 256, 0, stream>>>(p);
+    else edge_bwd_hub_kernel<4, true><<<blocks, 256, 0, stream>>>(p);
+  }
+  else if (Q <= 32) edge_bwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
   else if (Q <= 64) edge_bwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
   else edge_bwd_hub_kernel<4><<<blocks, 256, 0, stream>>>(p);
   return check_launch("edge_bwd_hub_kernel");
@@ -1140,7 +1162,11 @@ static int launch_edge_bwd(const EdgeBwdParams& p, bool streaming, cudaStream_t 
   // 48.3 vs 42.6 ms): the per-batch dot-product reduce chain wants warps, not loads in flight
   (void)streaming;
   const bool hub = p.nhub > 0;
-  if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_bwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
+  if (p.g16) {
+    if (hub) edge_bwd16_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
+    else edge_bwd16_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
+  }
+  else if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_bwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
   else if (p.drop.active() && hub) edge_bwd_kernel<G, NV, true, true><<<blocks, threads, 0, stream>>>(p);
   else if (p.drop.active()) edge_bwd_kernel<G, NV, true, false><<<blocks, threads, 0, stream>>>(p);
   else if (hub) edge_bwd_kernel<G, NV, false, true><<<blocks, threads, 0, stream>>>(p);
@@ -1180,8 +1206,10 @@ static bool gout_direct(const Geom& g, const float* gout, int64_t ldgo) {
 // stage 1: row records + Drow (+ padded / activation-scaled G copy when gp != nullptr) + g_bias column sums
 static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int64_t ldgo, const float* out, int64_t ldo,
                     const float* o_heads, const float* bias, const float* s_dst, const float* rowmax, const float* rowsum,
-                    float4* rowrec, float* gp, float* g_bias, int act, cudaStream_t stream) {
+                    float4* rowrec, float* gp, float* g_bias, int act, cudaStream_t stream, bool gp16 = false) {
+  // gp16: the gatherable copy `gp` is written as bf16 (same element layout, half the bytes) — always, activation or not
   const Geom g = geom_of(L);
+  B200GAT_REQUIRE(!gp16 || gp, B200GAT_E_NULL, "edge_bwd: the bf16 gradient rows need the copy buffer");
   const int64_t cap = int64_t(sm_count()) * 8;
   B200GAT_REQUIRE(!act || (g.concat_like && gp), B200GAT_E_UNSUPPORTED,
                   "edge_bwd: out_activation needs a concat-like layer (concat or one head) and the G copy buffer");
@@ -1190,12 +1218,12 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
   const bool vec = ldo % 4 == 0 && aligned16(out) && aligned16(bias);
   const int Q = g.C / 4;
   const bool fast = g.concat_like && g.C % 4 == 0 && vec && gout_direct(g, gout, ldgo) && g.d_out <= 1024 &&
-                    ((Q <= 32 && (Q & (Q - 1)) == 0) || Q % 32 == 0) && (act || gp == nullptr);
+                    ((Q <= 32 && (Q & (Q - 1)) == 0) || Q % 32 == 0) && (act || gp == nullptr || gp16);
   if (fast) {
     PrepRowsParams pr;
     pr.N = rows; pr.H = g.H; pr.C = g.C; pr.D = static_cast<int>(g.d_out);
     pr.gout = gout; pr.ldgo = ldgo; pr.out = out; pr.ldo = ldo; pr.bias = bias;
-    pr.s_dst = s_dst; pr.rowmax = rowmax; pr.rowsum = rowsum; pr.gp = gp; pr.rowrec = rowrec; pr.g_bias = g_bias;
+    pr.s_dst = s_dst; pr.rowmax = rowmax; pr.rowsum = rowsum; pr.gp = gp; pr.gp16 = gp16 ? 1 : 0; pr.rowrec = rowrec; pr.g_bias = g_bias;
     const int64_t want = ceil_div(rows, 8);
     const int64_t cap_rows = int64_t(sm_count()) * 4;       // few, fat CTAs: one g_bias atomic per column per CTA
     const int blocks = static_cast<int>(want < cap_rows ? want : cap_rows);
@@ -1218,7 +1246,7 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
     PrepMeanParams pm;
     pm.N = rows; pm.H = g.H; pm.C = g.C; pm.Cp = g.Cp;
     pm.gout = gout; pm.ldgo = ldgo; pm.o_heads = o_heads; pm.s_dst = s_dst; pm.rowmax = rowmax; pm.rowsum = rowsum;
-    pm.gp = gp; pm.rowrec = rowrec; pm.g_bias = g_bias;
+    pm.gp = gp; pm.gp16 = gp16 ? 1 : 0; pm.rowrec = rowrec; pm.g_bias = g_bias;
     const int64_t want = ceil_div(rows, 8);
     const int64_t cap_rows = int64_t(sm_count()) * 8;
     bwd_prep_mean_rows_kernel<<<static_cast<int>(want < cap_rows ? want : cap_rows), 256, 0, stream>>>(pm);
@@ -1234,6 +1262,7 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
   dp.gscale = g.concat_like ? 1.f : 1.f / static_cast<float>(g.H);
   dp.act = act;
   dp.gp = gp;
+  dp.gp16 = gp16 ? 1 : 0;
   dp.ldgp = g.concat_like ? g.Dp : g.Cp;
   dp.rowrec = rowrec;
   const int64_t want = ceil_div(rows * g.H, 8);
@@ -1242,6 +1271,8 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
   if (rc) return rc;
   const int64_t ysplit = ceil_div(rows, 8) < 64 ? ceil_div(rows, 8) : 64;
   dim3 grid(static_cast<unsigned>(ceil_div(g.d_out, 32)), static_cast<unsigned>(ysplit));
+  B200GAT_REQUIRE(!(act && gp16), B200GAT_E_UNSUPPORTED,
+                  "edge_bwd: bf16 gradient rows with a deferred activation need a head width that is a multiple of 4");
   if (act) colsum_kernel<<<grid, 256, 0, stream>>>(gp, dp.ldgp, rows, static_cast<int>(g.d_out), g.C, g.Cp, g_bias);
   else colsum_kernel<<<grid, 256, 0, stream>>>(gout, ldgo, rows, static_cast<int>(g.d_out), 1, 1, g_bias);
   return check_launch("colsum_kernel");
@@ -1253,13 +1284,16 @@ static int run_csc(const b200gat_layer& L, int64_t rows, const int32_t* colptr, 
                    const float* wh, const float* s_src, const float4* rowrec, const DropoutSpec& drop, const float* gsrc_rows,
                    int64_t ldg, int hs, float* gwh, float* g_s_src, float* g_s_dst, int64_t span, const int32_t* colend,
                    const int32_t* hub, int64_t nhub, int64_t max_deg, uint32_t* amax, cudaStream_t stream,
-                   float* de = nullptr, int64_t num_entries = 0) {
+                   float* de = nullptr, int64_t num_entries = 0, bool rows16 = false) {
   const Geom g = geom_of(L);
   EdgeBwdParams p;
   p.N = rows; p.items = rows * g.H; p.H = g.H; p.Cp = g.Cp; p.Dp = static_cast<int>(g.Dp); p.slope = L.negative_slope; p.act = L.logit_activation;
   p.colptr = colptr; p.crow = crow; p.ceid = ceid;
   p.wh = wh; p.s_src = s_src; p.rowrec = rowrec; p.drop = drop;
   p.g = gsrc_rows; p.ldg = ldg; p.hs = hs;
+  p.g16 = rows16 ? static_cast<const void*>(gsrc_rows) : nullptr;      // bf16 rows: same element layout
+  B200GAT_REQUIRE(!rows16 || (!drop.active() && p.act == B200GAT_LOGIT_LEAKY_RELU), B200GAT_E_UNSUPPORTED,
+                  "edge_bwd: bf16 gradient rows are offered without dropout and with LeakyReLU logits only");
   p.gwh = gwh; p.g_s_src = g_s_src; p.g_s_dst = g_s_dst;
   B200GAT_REQUIRE(nhub >= 0 && (nhub == 0 || (hub && colend)), B200GAT_E_NULL, "edge_bwd: hub_cols / colend missing");
   p.hub = hub; p.nhub = nhub; p.colend = nhub > 0 ? colend : colptr + 1;
@@ -1419,17 +1453,18 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
     B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(gsplit) & 255u) == 0, B200GAT_E_ALIGN, "edge_bwd: g_t_split must be 256-byte aligned");
   }
   // with an output activation the gathered rows are gout * ELU'(out): always the copy
-  const bool direct = !act && gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
+  const bool rows16 = a->gather_bf16 != 0;
+  const bool direct = !act && !rows16 && gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
                       aligned16(a->bias);
   if ((rc = run_prep(L, N, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum, rowrec,
-                     direct ? nullptr : gp, a->g_bias, act, stream)))
+                     direct ? nullptr : gp, a->g_bias, act, stream, rows16)))
     return rc;
   const float* grows = direct ? a->gout : gp;
   const int64_t ldg = direct ? a->ldgo : (g.concat_like ? g.Dp : g.Cp);
   const int hs = direct ? g.C : (g.concat_like ? g.Cp : 0);
   if ((rc = run_csc(L, N, a->graph.colptr, a->graph.crow, a->graph.ceid, a->wh, a->s_src, rowrec, drop, grows, ldg, hs,
                     a->g_t, g_s_src, g_s_dst, a->graph.span, a->graph.colend, a->graph.hub_cols, a->graph.num_hub_cols,
-                    a->graph.max_out_degree, gsplit ? amax : nullptr, stream, a->edge_scratch, a->graph.num_edges)))
+                    a->graph.max_out_degree, gsplit ? amax : nullptr, stream, a->edge_scratch, a->graph.num_edges, rows16)))
     return rc;
   // giant source rows are accumulated from per-segment partial sums: their maxima are not the maxima of the sums
   // (and with the across-heads softmax g_s_src is only complete after the second pass)
@@ -1459,8 +1494,10 @@ extern "C" int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* 
   B200GAT_REQUIRE(aligned16(a->rowrec), B200GAT_E_ALIGN, "edge_bwd_prep: rowrec must be 16-byte aligned");
   B200GAT_REQUIRE(a->out_activation == ACT_NONE || a->out_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
                   "edge_bwd_prep: unknown out_activation %d", a->out_activation);
+  B200GAT_REQUIRE(!(a->g_pad && a->g_pad_bf16), B200GAT_E_SHAPE, "edge_bwd_prep: give g_pad OR g_pad_bf16");
   return run_prep(a->layer, a->num_rows, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum,
-                  reinterpret_cast<float4*>(a->rowrec), a->g_pad, a->g_bias, a->out_activation, stream);
+                  reinterpret_cast<float4*>(a->rowrec), a->g_pad_bf16 ? static_cast<float*>(a->g_pad_bf16) : a->g_pad, a->g_bias,
+                  a->out_activation, stream, a->g_pad_bf16 != nullptr);
 }
 
 extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream_) {
@@ -1470,16 +1507,18 @@ extern "C" int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* st
   if (rc) return rc;
   B200GAT_REQUIRE(a->num_rows >= 0, B200GAT_E_SHAPE, "edge_bwd_csc: negative num_rows");
   if (a->num_rows == 0) return 0;
-  B200GAT_REQUIRE(a->colptr && a->crow && a->wh && a->s_src && a->rowrec && a->g && a->g_wh && a->g_s_src && a->g_s_dst,
+  const float* grows = a->g_bf16 ? static_cast<const float*>(a->g_bf16) : a->g;
+  B200GAT_REQUIRE(a->colptr && a->crow && a->wh && a->s_src && a->rowrec && grows && a->g_wh && a->g_s_src && a->g_s_dst,
                   B200GAT_E_NULL, "edge_bwd_csc: NULL pointer");
   DropoutSpec drop;
   if ((rc = make_dropout(a->mask, a->dropout, &drop))) return rc;
   B200GAT_REQUIRE(!drop.active() || a->ceid, B200GAT_E_NULL, "edge_bwd_csc: dropout needs ceid");
-  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_wh) && aligned16(a->g) && aligned16(a->rowrec) && a->ldg % 4 == 0 &&
+  B200GAT_REQUIRE(aligned16(a->wh) && aligned16(a->g_wh) && aligned16(grows) && aligned16(a->rowrec) && a->ldg % 4 == 0 &&
                   a->g_head_stride % 4 == 0, B200GAT_E_ALIGN, "edge_bwd_csc: wh / g / g_wh / rowrec must be 16-byte aligned");
   return run_csc(a->layer, a->num_rows, a->colptr, a->crow, a->ceid, a->wh, a->s_src,
-                 reinterpret_cast<const float4*>(a->rowrec), drop, a->g, a->ldg, static_cast<int>(a->g_head_stride),
-                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, nullptr, stream);
+                 reinterpret_cast<const float4*>(a->rowrec), drop, grows, a->ldg, static_cast<int>(a->g_head_stride),
+                 a->g_wh, a->g_s_src, a->g_s_dst, a->span, a->colend, a->hub_cols, a->num_hub_cols, a->max_out_degree, nullptr, stream,
+                 nullptr, 0, a->g_bf16 != nullptr);
 }
 
 extern "C" int b200gat_edge_bwd_finish(const b200gat_edge_bwd_finish_args* a, void* stream_) {

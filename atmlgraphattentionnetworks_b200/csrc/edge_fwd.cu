@@ -32,6 +32,7 @@ struct EdgeFwdParams {
   float slope; int act;
   const int32_t* rowptr; const int32_t* col; const int32_t* eid;
   const float* wh; const float* s_src; const float* s_dst; const float* bias;
+  const void* wh16;   // optional bf16 copy of wh [N, Dp]: the gathers read it instead (ROW16 instantiations)
   DropoutSpec drop;   // attention dropout (GAT.py:61): mask tensor or in-kernel Philox (common.cuh)
   float* out; int64_t ldo;
   float* rowmax; float* rowsum; float* o_heads;
@@ -49,7 +50,7 @@ struct EdgeFwdParams {
 // makes ptxas issue ALL U*NV gathers of a batch back to back (76 registers) — 3x the bytes in flight per warp at 3/4
 // of the occupancy.  Measured (tools/microbench/gather_bench.cu, power-law graph): 5.3 vs 3.7 TB/s gathered.  On the
 // L2-resident PPI-shaped batch the same build is 13 % SLOWER than the occupancy-first one, hence two instantiations.
-template <int G, int NV, bool HAS_MASK, bool STREAM, bool GENERIC = false>
+template <int G, int NV, bool HAS_MASK, bool STREAM, bool GENERIC = false, bool ROW16 = false>
 __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -58,7 +59,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
-  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   const int act = GENERIC ? p.act : 0;
   // lanes beyond the head width gather a clamped (valid) column and are never stored
@@ -89,7 +90,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
     float m = -INFINITY, l = 0.f;
     const char* wb[NV];                                   // this lane's column slices of row 0 of head h
 #pragma unroll
-    for (int v = 0; v < NV; ++v) wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + off[v]);
+    for (int v = 0; v < NV; ++v) wb[v] = row_base<ROW16>(p.wh, p.wh16, h * Cp + off[v]);
     // For 256-wide heads (NV = 2) the FIRST gather batch of a chunk is issued as soon as col[] is known — before the
     // dependent s_src gather, the exp and the softmax bookkeeping, none of which the Wh gathers need.  Tuned with
     // tools/microbench/gather_bench.cu (PPI-shaped batch, same loop): NV=2: weights-first U=4 0.279 ms, early U=4 0.317,
@@ -110,7 +111,7 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
             // slots past the chunk's edge count read a valid row (lane t+u's own j, or the destination itself), weight 0
             const int jt = __shfl_sync(FULL, j, t + u, G);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) w[u][v] = ldg4_row(wb[v], jt, row_bytes);
+            for (int v = 0; v < NV; ++v) w[u][v] = gather4<ROW16>(wb[v], jt, row_bytes);
           }
         };
         load_batch(0);
@@ -192,9 +193,9 @@ __device__ __forceinline__ void edge_fwd_body(const EdgeFwdParams& p) {
   #pragma unroll
             for (int v = 0; v < NV; ++v) {
               if (HAS_MASK) {   // dropped edges (60 % under the reference's p = 0.6) contribute nothing: skip the gather
-                w[u][v] = pt[u] != 0.f ? ldg4_row(wb[v], jt[u], row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u][v] = pt[u] != 0.f ? gather4<ROW16>(wb[v], jt[u], row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
               } else {          // no predicate, no branch: padded slots gather the row's own (valid) Wh and weigh it by 0
-                w[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
+                w[u][v] = gather4<ROW16>(wb[v], jt[u], row_bytes);
               }
             }
           }
@@ -257,6 +258,11 @@ template <int G, int NV, bool HAS_MASK>
 __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, HAS_MASK, false>(p); }
 template <int G, int NV>
 __global__ void __launch_bounds__(256, 3) edge_fwd_stream_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, false, true>(p); }
+// bf16-stored gathered rows (no mask, LeakyReLU): the same two schedules
+template <int G, int NV>
+__global__ void __launch_bounds__(256) edge_fwd16_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, false, false, false, true>(p); }
+template <int G, int NV>
+__global__ void __launch_bounds__(256, 3) edge_fwd16_stream_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, false, true, false, true>(p); }
 // other logit activations (run_act_func_experiment.py): one mask-capable instantiation per geometry (mask may be NULL)
 template <int G, int NV>
 __global__ void __launch_bounds__(256) edge_fwd_act_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, true, false, true>(p); }
@@ -287,7 +293,11 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
   const int64_t want = ceil_div(ceil_div(p.items, GPW), threads / 32);
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_fwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
+  if (p.wh16) {                                            // (the entry point only sets wh16 without mask / other activations)
+    if (streaming && G >= 16) edge_fwd16_stream_kernel<(G >= 16 ? G : 32), (G >= 16 ? NV : 1)><<<blocks, threads, 0, stream>>>(p);
+    else edge_fwd16_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
+  }
+  else if (p.act != B200GAT_LOGIT_LEAKY_RELU) edge_fwd_act_kernel<G, NV><<<blocks, threads, 0, stream>>>(p);
   else if (p.drop.active()) edge_fwd_kernel<G, NV, true><<<blocks, threads, 0, stream>>>(p);
   else if (streaming && G >= 16) edge_fwd_stream_kernel<(G >= 16 ? G : 32), (G >= 16 ? NV : 1)><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_kernel<G, NV, false><<<blocks, threads, 0, stream>>>(p);
@@ -298,7 +308,7 @@ static int launch_edge_fwd(const EdgeFwdParams& p, bool streaming, cudaStream_t 
 // chunks of the row with the same online softmax as above and merge their (max, sum, aggregate) partials through
 // shared memory.  A 40 k-edge row of the power-law graph costs 1257 dependent chunk walks in the row-per-group
 // kernels (~20 ms on one warp, longer than the rest of the grid needs for the other 2.4 M rows); here it is 157 per warp.
-template <int NV>
+template <int NV, bool ROW16 = false>
 __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
   const int64_t Dp = p.Dp;
-  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   const int act = p.act;
   int off[NV];
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + off[v]);
+      wb[v] = row_base<ROW16>(p.wh, p.wh16, h * Cp + off[v]);
     }
     float m = -INFINITY, l = 0.f;
     for (int k0 = beg + w * 32; k0 < end; k0 += 256) {
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(256) edge_fwd_hub_kernel(const EdgeFwdParams p
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) wv[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
+          for (int v = 0; v < NV; ++v) wv[u][v] = gather4<ROW16>(wb[v], jt[u], row_bytes);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -443,7 +453,12 @@ static int launch_edge_fwd_hub(const EdgeFwdParams& p, cudaStream_t stream) {
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? want : cap);
   const int Q = p.Cp / 4;
-  if (Q <= 32) edge_fwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
+  if (p.wh16) {
+    if (Q <= 32) edge_fwd_hub_kernel<1, true><<<blocks, 256, 0, stream>>>(p);
+    else if (Q <= 64) edge_fwd_hub_kernel<2, true><<<blocks, 256, 0, stream>>>(p);
+    else edge_fwd_hub_kernel<4, true><<<blocks, 256, 0, stream>>>(p);
+  }
+  else if (Q <= 32) edge_fwd_hub_kernel<1><<<blocks, 256, 0, stream>>>(p);
   else if (Q <= 64) edge_fwd_hub_kernel<2><<<blocks, 256, 0, stream>>>(p);
   else edge_fwd_hub_kernel<4><<<blocks, 256, 0, stream>>>(p);
   const int rc = check_launch("edge_fwd_hub_kernel");
@@ -497,7 +512,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_max_kernel(const EdgeFwdPa
   }
 }
 
-template <int NV>
+template <int NV, bool ROW16 = false>
 __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int U = NV >= 4 ? 2 : (NV == 1 ? 8 : 4);
@@ -507,7 +522,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdPa
   if (!giant_unit(p.hub, p.rowptr, p.H, i, h, kbeg, kend)) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int H = p.H, Cp = p.Cp, Q = p.Cp >> 2;
-  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * (ROW16 ? 2u : 4u);
   const float sd = __ldg(p.s_dst + i * H + h);
   const float M = p.rowmax[i * H + h];                    // final: written by edge_fwd_giant_max_kernel
   const DropoutKey dkey = dropout_key(p.drop);
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdPa
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wb[v] = reinterpret_cast<const char*>(p.wh + h * Cp + 4 * ((lane + v * 32 < Q) ? lane + v * 32 : Q - 1));
+    wb[v] = row_base<ROW16>(p.wh, p.wh16, h * Cp + 4 * ((lane + v * 32 < Q) ? lane + v * 32 : Q - 1));
   }
   float l = 0.f;
   for (int k0 = kbeg + w * 32; k0 < kend; k0 += 256) {
@@ -543,7 +558,7 @@ __global__ void __launch_bounds__(256) edge_fwd_giant_acc_kernel(const EdgeFwdPa
 #pragma unroll
       for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) wv[u][v] = ldg4_row(wb[v], jt[u], row_bytes);
+        for (int v = 0; v < NV; ++v) wv[u][v] = gather4<ROW16>(wb[v], jt[u], row_bytes);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -615,7 +630,12 @@ static int launch_edge_fwd_giant(const EdgeFwdParams& p, cudaStream_t stream) {
   int rc = check_launch("edge_fwd_giant_max_kernel");
   if (rc) return rc;
   const int Q = p.Cp / 4;
-  if (Q <= 32) edge_fwd_giant_acc_kernel<1><<<grid, 256, 0, stream>>>(p);
+  if (p.wh16) {
+    if (Q <= 32) edge_fwd_giant_acc_kernel<1, true><<<grid, 256, 0, stream>>>(p);
+    else if (Q <= 64) edge_fwd_giant_acc_kernel<2, true><<<grid, 256, 0, stream>>>(p);
+    else edge_fwd_giant_acc_kernel<4, true><<<grid, 256, 0, stream>>>(p);
+  }
+  else if (Q <= 32) edge_fwd_giant_acc_kernel<1><<<grid, 256, 0, stream>>>(p);
   else if (Q <= 64) edge_fwd_giant_acc_kernel<2><<<grid, 256, 0, stream>>>(p);
   else edge_fwd_giant_acc_kernel<4><<<grid, 256, 0, stream>>>(p);
   if ((rc = check_launch("edge_fwd_giant_acc_kernel"))) return rc;
@@ -630,7 +650,7 @@ static int launch_edge_fwd_giant(const EdgeFwdParams& p, cudaStream_t stream) {
 // computes the H softmax weights of each edge and parks them (and the edge's source id) in shared memory; in the
 // feature-parallel phase every lane reads the weight of ITS slot's head.  Used for streaming graphs (rows gathered
 // from HBM), where the longer contiguous reads and the 4x larger chunks pay.
-template <int G, int NV, int HH, bool HAS_MASK>
+template <int G, int NV, int HH, bool HAS_MASK, bool ROW16 = false>
 __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GPW = 32 / G;
@@ -647,7 +667,7 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int Q = p.Cp >> 2, S = HH * Q;
   const int64_t Dp = p.Dp;
-  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * 4u;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Dp) * (ROW16 ? 2u : 4u);
   const float slope = p.slope;
   int off[NV], hv[NV];
   bool live[NV];
@@ -659,7 +679,7 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
     const int sl = live[v] ? s : S - 1;                   // dead slots gather a clamped (valid) column and are never stored
     off[v] = 4 * sl;
     hv[v] = sl / Q;
-    wb[v] = reinterpret_cast<const char*>(p.wh + off[v]);
+    wb[v] = row_base<ROW16>(p.wh, p.wh16, off[v]);
   }
 
   const DropoutKey dkey = HAS_MASK ? dropout_key(p.drop) : DropoutKey{0u, 0u, 0u, 0u};
@@ -734,8 +754,8 @@ __device__ __forceinline__ void edge_fwd_row_body(const EdgeFwdParams& p) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             pt[u][v] = ps[(t + u) * HH + hv[v]];
-            if (HAS_MASK) w[u][v] = pt[u][v] != 0.f ? ldg4_row(wb[v], jt, row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
-            else w[u][v] = ldg4_row(wb[v], jt, row_bytes);
+            if (HAS_MASK) w[u][v] = pt[u][v] != 0.f ? gather4<ROW16>(wb[v], jt, row_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else w[u][v] = gather4<ROW16>(wb[v], jt, row_bytes);
           }
         }
 #pragma unroll
@@ -802,6 +822,8 @@ template <int G, int NV, int HH, bool HAS_MASK>
 __global__ void __launch_bounds__(256) edge_fwd_row_kernel(const EdgeFwdParams p) { edge_fwd_row_body<G, NV, HH, HAS_MASK>(p); }
 template <int G, int NV, int HH>
 __global__ void __launch_bounds__(256, 3) edge_fwd_row_stream_kernel(const EdgeFwdParams p) { edge_fwd_row_body<G, NV, HH, false>(p); }
+template <int G, int NV, int HH>
+__global__ void __launch_bounds__(256, 3) edge_fwd16_row_stream_kernel(const EdgeFwdParams p) { edge_fwd_row_body<G, NV, HH, false, true>(p); }
 
 template <int G, int NV, int HH>
 static int launch_edge_fwd_row(const EdgeFwdParams& p, bool streaming, cudaStream_t stream) {
@@ -811,7 +833,8 @@ static int launch_edge_fwd_row(const EdgeFwdParams& p, bool streaming, cudaStrea
   const int64_t cap = int64_t(sm_count()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   (void)streaming;                                        // only dispatched for streaming graphs (see b200gat_edge_fwd)
-  if (p.drop.active()) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
+  if (p.wh16) edge_fwd16_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
+  else if (p.drop.active()) edge_fwd_row_kernel<G, NV, HH, true><<<blocks, threads, 0, stream>>>(p);
   else edge_fwd_row_stream_kernel<G, NV, HH><<<blocks, threads, 0, stream>>>(p);
   return check_launch("edge_fwd_row_kernel");
 }
@@ -862,6 +885,11 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   p.slope = L.negative_slope; p.act = L.logit_activation;
   p.rowptr = a->graph.rowptr; p.col = a->graph.col; p.eid = a->graph.eid;
   p.wh = a->wh; p.s_src = a->s_src; p.s_dst = a->s_dst; p.bias = a->bias; p.drop = drop;
+  // bf16-stored gathered rows: only the plain configuration (LeakyReLU, no dropout) has ROW16 instantiations
+  B200GAT_REQUIRE(!a->wh_bf16 || (!drop.active() && L.logit_activation == B200GAT_LOGIT_LEAKY_RELU), B200GAT_E_UNSUPPORTED,
+                  "edge_fwd: wh_bf16 is offered without dropout and with LeakyReLU logits only");
+  B200GAT_REQUIRE(!a->wh_bf16 || aligned16(a->wh_bf16), B200GAT_E_ALIGN, "edge_fwd: wh_bf16 must be 16-byte aligned");
+  p.wh16 = a->wh_bf16;
   p.out = a->out; p.ldo = a->ldo; p.rowmax = a->rowmax; p.rowsum = a->rowsum; p.o_heads = a->o_heads;
   p.heads_mode = heads_mode ? 1 : 0;
   p.vec_out = (!heads_mode && C % 4 == 0 && a->ldo % 4 == 0 && aligned16(a->out) && aligned16(a->bias)) ? 1 : 0;

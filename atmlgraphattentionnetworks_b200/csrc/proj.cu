@@ -46,6 +46,14 @@ logits_kernel(const float* __restrict__ wh, const float* __restrict__ a1, const 
   }
 }
 
+// fp32 rows -> bf16 copy (the CUDA-core projection path of the bf16 gather mode; the tensor-core path writes it in its epilogue)
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = ldg4(src + 4 * t);
+    *reinterpret_cast<uint2*>(dst + 4 * t) = pack_bf16x4(v.x, v.y, v.z, v.w);
+  }
+}
+
 int launch_logits(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   const int64_t N = a.num_nodes;
   const int H = static_cast<int>(a.layer.heads), Cp = static_cast<int>(a.layer.c_pad), Q = Cp / 4;
@@ -101,6 +109,11 @@ extern "C" int b200gat_proj_fwd(const b200gat_proj_fwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->num_peers == 0, B200GAT_E_UNSUPPORTED, "proj_fwd: wh_peers needs the tensor-core path (shape too small)");
   rc = gemm_simt<true, true>(a->x, a->ldx, a->w, F, a->wh, Dp, a->bw, N, Dp, F, 1, stream, a->x_activation);
   if (rc) return rc;
+  if (a->wh_bf16) {
+    const int64_t n4 = N * Dp / 4, want = ceil_div(n4, 256), cap = int64_t(sm_count()) * 8;
+    to_bf16_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(a->wh, static_cast<uint16_t*>(a->wh_bf16), n4);
+    if ((rc = check_launch("to_bf16_kernel"))) return rc;
+  }
   return launch_logits(*a, stream);
 }
 

@@ -186,6 +186,7 @@ struct TcGemmParams {
   // projection fused with the all-gather of its output (b200gat_proj_fwd_args.wh_peers): every stored tile is also written
   // to the same (row, column) of n_peer peer-mapped copies of C
   float* peer_c[B200GAT_MAX_PEERS]; int n_peer;
+  uint16_t* c16;           // optional bf16 copy of C (same ldc): the gathered-row storage of the bf16 mode (wh_bf16)
 };
 
 enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2 };
@@ -508,6 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 float* d = p.C + rr * p.ldc + col;
                 if (col + 4 <= p.N) {
                   *reinterpret_cast<float4*>(d) = v;
+                  if (p.c16) *reinterpret_cast<uint2*>(p.c16 + rr * p.ldc + col) = pack_bf16x4(v.x, v.y, v.z, v.w);
                   for (int k = 0; k < p.n_peer; ++k)    // fused all-gather: the same 64-byte runs over NVLink
                     *reinterpret_cast<float4*>(p.peer_c[k] + rr * p.ldc + col) = v;
                 } else if (col < p.N) {                 // the (rare) ragged group of a column tail
@@ -817,6 +819,8 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   p.H = static_cast<int>(H); p.Cp = static_cast<int>(Cp);
   B200GAT_REQUIRE(a.num_peers >= 0 && a.num_peers <= B200GAT_MAX_PEERS, B200GAT_E_SHAPE, "proj_fwd: num_peers out of range");
   p.n_peer = a.num_peers;
+  B200GAT_REQUIRE(!a.wh_bf16 || (reinterpret_cast<uintptr_t>(a.wh_bf16) & 7u) == 0, B200GAT_E_ALIGN, "proj_fwd: wh_bf16 must be 8-byte aligned");
+  p.c16 = static_cast<uint16_t*>(a.wh_bf16);
   for (int k = 0; k < a.num_peers; ++k) {
     B200GAT_REQUIRE(a.wh_peers[k] && aligned16(a.wh_peers[k]), B200GAT_E_ALIGN, "proj_fwd: wh_peers[%d] NULL or not 16-byte aligned", k);
     p.peer_c[k] = a.wh_peers[k];

@@ -131,7 +131,10 @@ class GATLayerFunction(torch.autograd.Function):
         mask = None if drop is not None else mask
         w, bw, a1, a2, b1, b2 = packed
         f_in, c, h, concat = geom
-        act_in, act_out, x_amax, logit = fuse
+        act_in, act_out, x_amax, logit = fuse[:4]
+        # bf16 storage of the gathered rows (GraphAttentionLayer.gather_dtype): only the plain configuration has kernels for
+        # it (LeakyReLU logits, no dropout / mask); anything else keeps the fp32 rows — never less precise than asked
+        rows16 = bool(len(fuse) > 4 and fuse[4]) and drop is None and mask is None and logit[0] == _abi.LOGIT_LEAKY_RELU
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
@@ -151,6 +154,7 @@ class GATLayerFunction(torch.autograd.Function):
         rowsum = torch.empty((n, h), **f32)
         o_heads = torch.empty((n, dp), **f32) if heads_mode else None
         out_amax = torch.zeros(1, dtype=torch.int32, device=dev)
+        wh16 = torch.empty((n, dp), dtype=torch.bfloat16, device=dev) if rows16 else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
@@ -162,14 +166,16 @@ class GATLayerFunction(torch.autograd.Function):
                                   a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
                                   s_src.data_ptr(), s_dst.data_ptr(), ws.data_ptr(), ws_bytes,
                                   _ptr(x_split), split_bytes, _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(x_amax))
+            pa.wh_bf16 = _ptr(wh16)
             _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
             ea = _abi.EdgeFwdArgs(layer, graph.c_struct(), wh.data_ptr(), s_src.data_ptr(), s_dst.data_ptr(),
                                   bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(),
-                                  rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr(), _abi.dropout_struct(drop))
+                                  rowsum.data_ptr(), _ptr(o_heads), out_amax.data_ptr(), _abi.dropout_struct(drop), _ptr(wh16))
             _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
             _abi.launches += 2
         ctx.graph, ctx.geom, ctx.mask, ctx.act, ctx.logit = graph, geom, mask, (bool(act_in), bool(act_out)), logit
         ctx.drop = drop
+        ctx.rows16 = rows16
         # the kernels read the packed storage through raw pointers and the per-head Parameters alias it through `.data =`,
         # which does not share version counters: remember the Parameters' versions so that an in-place update between this
         # forward and its backward (optimizer.step, load_state_dict, ...) is an error, as it is in the reference
@@ -226,7 +232,8 @@ class GATLayerFunction(torch.autograd.Function):
                                   g_t.data_ptr(), g_bw.data_ptr(), g_a1.data_ptr(), g_a2.data_ptr(),
                                   g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes,
                                   _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g_split), gs_bytes,
-                                  _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0)
+                                  _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0,
+                                  1 if ctx.rows16 else 0)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
 
@@ -270,6 +277,19 @@ class GATLayerFunction(torch.autograd.Function):
         return (g_x, g_bias, None, None, None, None, None, *per_head)
 
 
+_DEFAULT_GATHER_DTYPE = torch.bfloat16 if __import__("os").environ.get("B200GAT_GATHER_DTYPE", "") in ("bf16", "bfloat16") else torch.float32
+
+
+def set_gather_dtype(module, dtype):
+    """Switch every GraphAttentionLayer under `module` to fp32 (default) or bf16 storage of the gathered rows."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("gather dtype must be torch.float32 or torch.bfloat16")
+    for m in module.modules():
+        if isinstance(m, GraphAttentionLayer):
+            m.gather_dtype = dtype
+    return module
+
+
 class GraphAttentionLayer(torch.nn.Module):
     """GAT.py:8 — GraphAttentionLayer(input_channels, output_channels, num_heads=1, concat=False, dropout=0.6)."""
 
@@ -302,6 +322,10 @@ class GraphAttentionLayer(torch.nn.Module):
         self._store = None      # persistent packed parameter storage (see _packed_storage)
         # the function applied to the edge logits before the softmax: (B200GAT_LOGIT_* code, negative slope); GAT.py:30
         self.logit_activation = (_abi.LOGIT_LEAKY_RELU, NEGATIVE_SLOPE)
+        # storage of the rows the edge kernels GATHER (Wh forward, the gradient rows backward): torch.float32 (default:
+        # the reference's arithmetic, 1e-5 parity) or torch.bfloat16 (half the gather / NVLink bytes, tolerance 1e-2 —
+        # DESIGN.md §4.11; set_gather_dtype(model, torch.bfloat16) switches every layer of a model)
+        self.gather_dtype = _DEFAULT_GATHER_DTYPE
 
     # ---- persistent packed storage: the kernels read ONE [Dp, F] / [Dp] / [H] set of arrays per layer (head-major, rows
     # padded to c_pad with zeros).  The per-head Linear parameters of GAT.py:19-25 (and the state_dict keys that come with
@@ -416,8 +440,8 @@ class GraphAttentionLayer(torch.nn.Module):
         packed = self._packed_storage()
         geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
         return GATLayerFunction.apply(x, self.bias, graph, geom, mask,
-                                      (bool(act_in), bool(act_out), x_amax, tuple(self.logit_activation)), packed,
-                                      *self._head_parameters())
+                                      (bool(act_in), bool(act_out), x_amax, tuple(self.logit_activation),
+                                       self.gather_dtype == torch.bfloat16), packed, *self._head_parameters())
 
 
 def _logit_code(fn):

@@ -113,20 +113,22 @@ def describe_config(name, desc, data, spec, world, mode):
 
 
 # ------------------------------------------------------------------------------------ algorithmic bytes
-def algorithmic_bytes(op, n, ep, f, c, h, concat, need_gx, cached):
+def algorithmic_bytes(op, n, ep, f, c, h, concat, need_gx, cached, row_b=4):
     """Bytes one ABI op must move (fp32 values, int32 indices); G = gather multiplicity: N when the gathered operand
     of the largest graph block fits half of L2 ("cached regime": the block-diagonal PPI-shaped batch, blocks <= 15 MB),
     E' otherwise ("streaming regime": the 2.4M-node graph, 4.9 GB of Wh) — SURVEY.md §8d."""
     d = h * c
     d_out = d if concat else c
     g = n if cached else ep
+    # row_b = bytes per element of the GATHERED rows: 4 (default) or 2 (bf16 gather mode: the bf16 copies are extra writes)
     if op == "b200gat_proj_fwd":
-        return 4 * (n * f + d * f + n * d + 2 * n * h), "tensor"
+        return 4 * (n * f + d * f + n * d + 2 * n * h) + (2 * n * d if row_b == 2 else 0), "tensor"
     if op == "b200gat_edge_fwd":
         extra = 4 * n * d if (not concat and h > 1) else 0
-        return 4 * ((n + 1) + ep + 2 * n * h + n * d_out) + 4 * g * (d + h) + extra, "hbm"
+        return 4 * ((n + 1) + ep + 2 * n * h + n * d_out) + g * (row_b * d + 4 * h) + extra, "hbm"
     if op == "b200gat_edge_bwd":
-        return 4 * ((n + 1) + ep + n * d_out + 3 * n * d + 4 * n * h) + 4 * g * (d_out + 4 * h), "hbm"
+        return (4 * ((n + 1) + ep + n * d_out + 3 * n * d + 4 * n * h) + g * (row_b * d_out + 16 * h) +
+                (2 * n * d_out if row_b == 2 else 0)), "hbm"
     if op == "b200gat_proj_bwd":
         return 4 * (n * d + (2 if need_gx else 1) * n * f + 2 * d * f), "tensor"
     raise KeyError(op)
@@ -313,7 +315,7 @@ class Env:
 class Runner:
     """One workload on this rank's GPU: model, optimizer, host / device buffers and the train step."""
 
-    def __init__(self, name, env, *, heads=8, num_graphs=128, dp="weak", capturable=False):
+    def __init__(self, name, env, *, heads=8, num_graphs=128, dp="weak", capturable=False, gather_bf16=False):
         from types import SimpleNamespace
         from atmlgraphattentionnetworks_b200.gatnet import GATNet, GATStack
         from atmlgraphattentionnetworks_b200.parallel import GradBucket, shard_graphs
@@ -345,6 +347,10 @@ class Runner:
         else:
             self.module = GATStack(spec, dropout=0.0).to(dev)
             self.model = self.module
+        if gather_bf16:      # the separately toleranced mode: gathered rows stored as bf16
+            from atmlgraphattentionnetworks_b200.gat import set_gather_dtype
+            set_gather_dtype(self.module, torch.bfloat16)
+        self.gather_bf16 = bool(gather_bf16)
         self.params = list(self.module.parameters())
         # gradients are set to None every step and autograd adopts the kernels' packed output buffers as .grad without a
         # copy; N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (all_reduce_packed_grads).
@@ -647,7 +653,8 @@ class Runner:
                     ts = ts[:reps]
                 ms = statistics.median(ts)
                 need_gx = li > 0
-                nbytes, bound = algorithmic_bytes(op, n_loc, ep_loc, f, c, h, concat, need_gx, cached=cached)
+                nbytes, bound = algorithmic_bytes(op, n_loc, ep_loc, f, c, h, concat, need_gx, cached=cached,
+                                                  row_b=2 if self.gather_bf16 else 4)
                 rec = {"op": op, "layer": li, "geom": f"{f}->{h}x{c}{'cat' if concat else 'mean'}", "ms": ms,
                        "alg_bytes": nbytes, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / peaks["hbm"]}
                 fl = gemm_flops(op, n_loc, f, c, h, need_gx)
@@ -694,10 +701,11 @@ class Runner:
             f, c, h, concat = self.spec[li]
             d = h * c
             d_out = d if concat else c
+            rb = 2 if self.gather_bf16 else 4
             if rec["op"] == "b200gat_edge_fwd":
-                rec["gather_bytes"] = 4 * ep_loc * (d + h)
+                rec["gather_bytes"] = ep_loc * (rb * d + 4 * h)
             elif rec["op"] == "b200gat_edge_bwd":
-                rec["gather_bytes"] = 4 * ep_loc * (d_out + 4 * h)
+                rec["gather_bytes"] = ep_loc * (rb * d_out + 16 * h)
             if "gather_bytes" in rec:
                 rec["gather_TBps"] = rec["gather_bytes"] / rec["ms"] / 1e9
         edge_ms = sum(r["ms"] for r in kernels if r["op"].startswith("b200gat_edge"))
@@ -730,12 +738,13 @@ class Runner:
 
 
 def run_workload(name, env, steps, warmup, args, *, heads=8, num_graphs=128, dp="weak", e2e=True, cpu=True, breakdown=True,
-                 cuda_graph=False, traffic_name=None, captured=False):
+                 cuda_graph=False, traffic_name=None, captured=False, gather_bf16=False):
     """-> the record of one workload (all ranks take part; only rank 0's record is complete)."""
     from atmlgraphattentionnetworks_b200 import _abi
     t_wall = time.perf_counter()
-    run = Runner(name, env, heads=heads, num_graphs=num_graphs, dp=dp, capturable=cuda_graph or captured)
+    run = Runner(name, env, heads=heads, num_graphs=num_graphs, dp=dp, capturable=cuda_graph or captured, gather_bf16=gather_bf16)
     rec = {"config": run.config, "n_gpus": env.world, "steps": steps, "warmup": warmup,
+           "gather_dtype": "bf16 (gathered rows stored as bf16, fp32 arithmetic; tolerance 1e-2, tests/test_gpu_parity.py)" if gather_bf16 else "f32",
            "scaling": "strong" if (run.partitioned or run.dp == "strong") else "weak"}
     if env.world > 1:
         rec["check"] = run.check()
@@ -834,6 +843,8 @@ def main():
     ap.add_argument("--heads", type=int, default=8, help="--workload heads: number of heads (x 64 channels); 0 = the whole sweep")
     ap.add_argument("--graphs", type=int, default=128, help="--workload cifar: graphs per batch")
     ap.add_argument("--dp", default="weak", choices=["weak", "strong"], help="--workload cifar at N > 1")
+    ap.add_argument("--gather-dtype", default="f32", choices=["f32", "bf16"],
+                    help="storage of the rows the edge kernels gather: f32 (default, 1e-5 parity) or bf16 (tolerance 1e-2)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the resident train step in a CUDA graph and time replays (launch-bound workloads)")
     ap.add_argument("--cpu-sample-graphs", type=int, default=0,
@@ -895,11 +906,20 @@ def main():
                      head["points"][-1]["gpu_launches"], "n_gpus": world, "steps": args.steps, "warmup": warmup, "scaling": "weak"})
     else:
         head = run_workload(head_name, env, args.steps, warmup, args, heads=args.heads or 8, num_graphs=args.graphs, dp=args.dp,
-                            cuda_graph=args.cuda_graph, captured=(world == 1 and head_name != "large"))
+                            cuda_graph=args.cuda_graph, captured=(world == 1 and head_name != "large"),
+                            gather_bf16=args.gather_dtype == "bf16")
     subs = {}
     if everything:
         sub_steps = min(args.steps, 10)
         subs["large"] = run_workload("large", env, sub_steps, 3, args)
+        # the separately toleranced bf16-gather mode on the two roofline workloads (NOT the parity path; see gather_dtype)
+        subs["bf16_gather"] = {
+            "note": "gathered rows (Wh forward, gradient rows backward, and the all-gathered copies at N > 1) stored as bf16; "
+                    "fp32 arithmetic; tolerance 1e-2 instead of 1e-5 (tests/test_gpu_parity.py::test_bf16_gathered_rows_*)",
+            "large": run_workload("large", env, sub_steps, 3, args, gather_bf16=True, e2e=False, cpu=False, traffic_name="large_bf16")}
+        if world == 1:
+            subs["bf16_gather"]["ppi"] = run_workload("ppi", env, args.steps, warmup, args, gather_bf16=True, e2e=False, cpu=False,
+                                                      traffic_name="ppi_bf16")
         if world == 1:
             subs["cifar"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, captured=True)
             subs["cifar"]["batch512"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=512, cpu=False,

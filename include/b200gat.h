@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 13
+#define B200GAT_ABI_VERSION 14
 
 enum {
   B200GAT_OK = 0,
@@ -160,6 +160,11 @@ typedef struct {
    * reads the gathered buffer.  Tensor-core path only (b200gat_proj_split_bytes() != 0), else B200GAT_E_UNSUPPORTED. */
   float* wh_peers[B200GAT_MAX_PEERS];
   int32_t num_peers;
+  /* Optional bf16 storage of the GATHERED rows (a separately toleranced mode, never the default): wh_bf16 [N, Dp] receives a
+   * bf16 (round-to-nearest-even) copy of wh next to the fp32 one.  b200gat_edge_fwd gathers from it when given there, which
+   * halves the bytes every edge pulls through L2 / HBM — and over NVLink when the rows are all-gathered (row-partitioned
+   * mode).  The arithmetic (logits, softmax, accumulation) stays fp32. */
+  void* wh_bf16;
 } b200gat_proj_fwd_args;
 size_t b200gat_proj_fwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of an x_split buffer for this geometry; 0 when the shape runs on the CUDA-core path (pass x_split = NULL) */
@@ -179,6 +184,8 @@ typedef struct {
   float* o_heads;                 /* out [N, Dp]; required iff !concat && H > 1 (per-head aggregate) */
   uint32_t* out_amax;             /* optional out: device word <- bit pattern of max|out| (for the next layer's x_amax) */
   b200gat_dropout dropout;        /* in-kernel attention dropout, used when mask == NULL and dropout.p > 0 */
+  const void* wh_bf16;            /* optional [N, Dp] bf16 copy of wh (b200gat_proj_fwd_args.wh_bf16): gathered instead of wh.
+                                     Offered without dropout and with LeakyReLU logits (else B200GAT_E_UNSUPPORTED) */
 } b200gat_edge_fwd_args;
 int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream);
 
@@ -207,6 +214,8 @@ typedef struct {
   b200gat_dropout dropout;            /* as in the forward (same p and seed words => the same mask) */
   float* edge_scratch; size_t edge_scratch_bytes;   /* B200GAT_LOGIT_HEAD_SOFTMAX only: E' * H * 4 bytes (d loss / d e per
                                          CSC entry and head, consumed by the second pass); NULL otherwise */
+  int32_t gather_bf16;                /* the gatherable gradient rows G are written (by the prep pass, into the workspace) and
+                                         gathered (by the CSC pass) as bf16: the backward's half of the bf16 mode above */
 } b200gat_edge_bwd_args;
 size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of a g_t_split buffer; 0 when the projection backward of this geometry runs on the CUDA-core path */
@@ -230,6 +239,7 @@ typedef struct {
                                          [rows, c_pad]); NULL iff gout is directly gatherable (concat-like, C % 4 == 0) */
   float* g_bias;                      /* out [D_out] (this block's partial column sums) */
   int32_t out_activation;             /* as in b200gat_edge_bwd_args: gout is d/d act(out); needs g_pad (G = gout * act'(out)) */
+  void* g_pad_bf16;                   /* alternative to g_pad: the same rows (same element layout) written as bf16, ALWAYS */
 } b200gat_edge_bwd_prep_args;
 int b200gat_edge_bwd_prep(const b200gat_edge_bwd_prep_args* a, void* stream);
 
@@ -251,6 +261,7 @@ typedef struct {
   const int32_t* colend;              /* [rows] as b200gat_graph.colend (required when num_hub_cols > 0) */
   int64_t max_out_degree;             /* as b200gat_graph.max_out_degree for the own source rows */
   b200gat_dropout dropout;            /* as in the forward; ceid required (global original edge positions) */
+  const void* g_bf16;                 /* alternative to g: the rows as bf16 (ldg / g_head_stride still count ELEMENTS) */
 } b200gat_edge_bwd_csc_args;
 int b200gat_edge_bwd_csc(const b200gat_edge_bwd_csc_args* a, void* stream);
 
