@@ -137,7 +137,7 @@ def peer_push_enabled(world):
     return env == "1" if env is not None else world == 2
 
 
-def stage_proj(geom, params, x_own, block, peer=None, act_in=False, x_amax=None, keep_split=False):
+def stage_proj(geom, params, x_own, block, peer=None, act_in=False, x_amax=None, keep_split=False, rows16=False):
     """-> wh [block, Dp] (rows >= n_own zero), s_src [block, H], s_dst [n_own, H]   (GAT.py:42-52 on own rows)
     [, x_split when keep_split: the tensor-core operand split of x kept for stage_proj_bwd, or None on the CUDA-core path].
     peer: a PeerBuffer — wh is then the own row block INSIDE the gathered buffer and the kernel also stores it into every
@@ -165,13 +165,18 @@ def stage_proj(geom, params, x_own, block, peer=None, act_in=False, x_amax=None,
         for k, ptr in enumerate(ptrs):
             pa.wh_peers[k] = ptr
         pa.num_peers = len(ptrs)
+    # rows16: ALSO write a bf16 copy of the own rows — the buffer that is all-gathered and gathered from in the bf16 mode
+    wh16 = torch.zeros((block, dp), dtype=torch.bfloat16, device=dev) if rows16 else None
+    pa.wh_bf16 = _ptr(wh16)
     _call("b200gat_proj_fwd", lib.b200gat_proj_fwd, pa, stream, geom)
+    if rows16:
+        return wh, s_src, s_dst, x_split, wh16
     if keep_split:
         return wh, s_src, s_dst, x_split
     return wh, s_src, s_dst
 
 
-def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask, out_amax=None):
+def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask, out_amax=None, wh16_full=None):
     """-> out [n_own, D_out], rowmax, rowsum [n_own, H], o_heads or None   (GAT.py:53-67 for the own destination rows)
     out_amax: optional int32[1] device word <- bit pattern of max|out| over the OWN rows (the next layer's x_amax)"""
     lib = _abi.lib()
@@ -184,9 +189,10 @@ def stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst_own, bias, mask, out_a
     o_heads = torch.empty((n, dp), **f32) if heads_mode else None
     stream = torch.cuda.current_stream(dev).cuda_stream
     mask, drop = _split_mask(mask)      # [E', H] tensor in ORIGINAL (global) edge order, or (p, seed): in-kernel Philox
+    # wh16_full: the all-gathered bf16 rows (the fp32 pointer is then only a placeholder of the own rows: never gathered)
     ea = _abi.EdgeFwdArgs(layer, part.c_struct(), wh_full.data_ptr(), s_src_full.data_ptr(), s_dst_own.data_ptr(),
                           bias.data_ptr(), _ptr(mask), out.data_ptr(), d_out, rowmax.data_ptr(), rowsum.data_ptr(),
-                          _ptr(o_heads), _ptr(out_amax), _abi.dropout_struct(drop))
+                          _ptr(o_heads), _ptr(out_amax), _abi.dropout_struct(drop), _ptr(wh16_full))
     _call("b200gat_edge_fwd", lib.b200gat_edge_fwd, ea, stream, geom)
     return out, rowmax, rowsum, o_heads
 
@@ -203,17 +209,21 @@ def gather_layout(geom, act_out=False):
     return False, cp, cp, 0
 
 
-def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, block, act_out=False):
+def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, block, act_out=False, rows16=False):
     """-> rowrec [block, H, 4], g_rows [block, width] (zero padded), g_bias partial [D_out]
     act_out: gout is d/d ELU(out) of a layer whose activation was deferred to its consumer (concat-like layers)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = gout_own.device, gout_own.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
-    direct, width, _, _ = gather_layout(geom, act_out)
+    direct, width, _, _ = gather_layout(geom, act_out or rows16)      # bf16 rows: always the (bf16) copy
     rowrec = torch.zeros((block, h, 4), **f32)
     g_bias = torch.empty(d_out, **f32)
-    if direct:
+    g16 = None
+    if rows16:
+        g_rows = g16 = torch.zeros((block, width), dtype=torch.bfloat16, device=dev)
+        g_pad = None
+    elif direct:
         if n == block:
             g_rows = gout_own
         else:
@@ -228,18 +238,18 @@ def stage_prep(geom, gout_own, fwd_out_own, bias, s_dst_own, rowmax, rowsum, blo
                               None if heads_mode else fwd_out_own.data_ptr(), d_out,
                               fwd_out_own.data_ptr() if heads_mode else None, bias.data_ptr(),
                               s_dst_own.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), rowrec.data_ptr(),
-                              _ptr(g_pad), g_bias.data_ptr(), _abi.ACT_ELU if act_out else _abi.ACT_NONE)
+                              _ptr(g_pad), g_bias.data_ptr(), _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g16))
     _call("b200gat_edge_bwd_prep", lib.b200gat_edge_bwd_prep, pa, stream, geom)
     return rowrec, g_rows, g_bias
 
 
-def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out=False):
+def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out=False, rows16=False):
     """-> g_wh [n_own, Dp], g_s_src [n_own, H], g_s_dst_full [P*block, H] (this rank's partial sums for ALL nodes)"""
     lib = _abi.lib()
     layer, f_in, c, h, concat, cp, dp, d_out, heads_mode = _geom(geom)
     dev, n = wh_own.device, part.n_own
     f32 = dict(dtype=torch.float32, device=dev)
-    _, _, ldg, hs = gather_layout(geom, act_out)
+    _, _, ldg, hs = gather_layout(geom, act_out or rows16)
     g_wh = torch.empty((n, dp), **f32)
     g_s_src = torch.empty((n, h), **f32)
     g_s_dst_full = torch.zeros((part.padded_rows, h), **f32)
@@ -247,10 +257,10 @@ def stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out=
     mask, drop = _split_mask(mask)
     ca = _abi.EdgeBwdCscArgs(layer, n, part.colptr.data_ptr(), part.crow.data_ptr(), part.ceid.data_ptr(),
                              wh_own.data_ptr(), s_src_own.data_ptr(), rowrec_full.data_ptr(), _ptr(mask),
-                             g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
+                             None if rows16 else g_full.data_ptr(), ldg, hs, g_wh.data_ptr(), g_s_src.data_ptr(), g_s_dst_full.data_ptr(),
                              part.num_nodes, part.hub_cols.data_ptr() if part.hub_cols.numel() else None,
                              int(part.hub_cols.numel()), part.colend.data_ptr() if part.hub_cols.numel() else None,
-                             part.max_out_degree, _abi.dropout_struct(drop))
+                             part.max_out_degree, _abi.dropout_struct(drop), g_full.data_ptr() if rows16 else None)
     _call("b200gat_edge_bwd_csc", lib.b200gat_edge_bwd_csc, ca, stream, geom)
     return g_wh, g_s_src, g_s_dst_full
 
@@ -324,7 +334,10 @@ class PartitionedGATFunction(torch.autograd.Function):
         # fuse = (act_in, act_out, x_amax): the layer-boundary fusions of gat.GATLayerFunction — the ELU between two layers
         # is applied by the CONSUMER while it loads its operand, the producer's backward multiplies by ELU'(out).
         # -> (out, out_amax): out_amax (int32[1]) bounds max|out| of the OWN rows for the next layer's operand scale
-        act_in, act_out, x_amax = fuse
+        act_in, act_out, x_amax = fuse[:3]
+        # bf16 storage of the gathered rows — which in this mode are also what travels over NVLink (half the wire bytes);
+        # only the plain configuration has kernels for it (no dropout / mask)
+        rows16 = bool(len(fuse) > 3 and fuse[3]) and mask is None
         # x_full: the layer's input for ALL nodes, replicated on every rank (the static input features of layer 1).  The
         # rank then projects all N rows itself and NOTHING is exchanged in this layer's forward: for the 2.4 M-node graph
         # a 100 -> 512 projection of every node costs 2.5 ms, its all-gather (4.3 GB received per rank) 6-7 ms.
@@ -339,19 +352,27 @@ class PartitionedGATFunction(torch.autograd.Function):
                     peer.barrier()
             if x_full is not None:
                 n_all = x_full.shape[0]
-                wh_full, s_src_full, s_dst_full = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_full.contiguous(), n_all, None)
+                res = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_full.contiguous(), n_all, None, rows16=rows16)
+                wh_full, s_src_full, s_dst_full = res[:3]
+                wh16_full = res[4] if rows16 else None
                 wh_pad, s_src_pad = wh_full[part.lo:], s_src_full[part.lo:]        # own rows first (only [:n_own] is used)
                 s_dst = s_dst_full[part.lo:part.hi]
                 peer, x_split = None, None
             else:
-                wh_pad, s_src_pad, s_dst, x_split = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer,
-                                                               act_in=act_in, x_amax=x_amax, keep_split=True)
+                res = stage_proj(geom, (w, bw, a1, a2, b1, b2), x_own, part.block, peer, act_in=act_in, x_amax=x_amax,
+                                 keep_split=True, rows16=rows16)
+                wh_pad, s_src_pad, s_dst, x_split = res[:4]
+                wh16_full = None
             if x_full is not None:
                 pass
             elif peer is not None:        # Wh went to every GPU from inside the projection kernel: wait for everybody's tiles
                 with _timed("peer_barrier", geom):
                     peer.barrier()
                 wh_full = peer.tensor
+            elif rows16:
+                with _timed("all_gather_wh", geom):
+                    wh16_full = all_gather_rows(res[4], group)
+                wh_full = wh_pad                # placeholder: the kernels gather from wh16_full
             else:
                 with _timed("all_gather_wh", geom):
                     wh_full = all_gather_rows(wh_pad, group)
@@ -359,10 +380,12 @@ class PartitionedGATFunction(torch.autograd.Function):
                 with _timed("all_gather_s_src", geom):
                     s_src_full = all_gather_rows(s_src_pad, group)
             out_amax = torch.zeros(1, dtype=torch.int32, device=x_own.device)
-            out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask, out_amax)
+            out, rowmax, rowsum, o_heads = stage_edge_fwd(geom, part, wh_full, s_src_full, s_dst, bias, mask, out_amax,
+                                                          wh16_full)
         n = part.n_own
         ctx.part, ctx.geom, ctx.mask, ctx.group = part, geom, mask, group
         ctx.act = (bool(act_in), bool(act_out))
+        ctx.rows16 = rows16
         # peer mode: wh_pad is a view of the layer's persistent symmetric buffer, which the NEXT forward through this layer
         # overwrites through raw pointers (no autograd version bump) — an eval forward, a second micro-batch or activation
         # checkpointing between this forward and its backward would silently corrupt the saved Wh.  Keep a private copy.
@@ -379,12 +402,13 @@ class PartitionedGATFunction(torch.autograd.Function):
         act_in, act_out = ctx.act
         gout = gout.contiguous()
         with torch.cuda.device(gout.device):
-            rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block, act_out)
+            rows16 = ctx.rows16
+            rowrec, g_rows, g_bias = stage_prep(geom, gout, fwd_out, bias, s_dst, rowmax, rowsum, part.block, act_out, rows16)
             with _timed("all_gather_g", geom):
                 g_full = all_gather_rows(g_rows, group)
             with _timed("all_gather_rowrec", geom):
                 rowrec_full = all_gather_rows(rowrec, group)
-            g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out)
+            g_wh, g_s_src, g_s_dst_full = stage_csc(geom, part, wh_own, s_src_own, rowrec_full, g_full, mask, act_out, rows16)
             with _timed("reduce_scatter_g_s_dst", geom):
                 g_s_dst_own = reduce_scatter_rows(g_s_dst_full, part.block, group)
             g_bw, g_a1, g_a2, g_b1, g_b2, g_split = stage_finish(geom, wh_own, a1, a2, g_s_src, g_s_dst_own, g_wh,
@@ -413,9 +437,11 @@ def partitioned_layer_forward(layer, x_own, part, group=None, x_full=None, act_i
     geom = (layer.input_channels, layer.output_channels, layer.num_heads, bool(layer.concat))
     if act_out and not layer.can_fuse_activation_out():
         raise ValueError("act_out needs a concat-like layer")
-    peer = None if x_full is not None else _peer_buffer(layer, geom, part, x_own, group)
+    # (the bf16 rows of the bf16 gather mode travel by NCCL: the peer push ships fp32 tiles)
+    rows16 = layer.gather_dtype == torch.bfloat16 and mask is None
+    peer = None if (x_full is not None or rows16) else _peer_buffer(layer, geom, part, x_own, group)
     out, amax = PartitionedGATFunction.apply(x_own, w, bw, a1, a2, b1, b2, layer.bias, part, geom, mask, group, peer, x_full,
-                                             (bool(act_in), bool(act_out), x_amax))
+                                             (bool(act_in), bool(act_out), x_amax, layer.gather_dtype == torch.bfloat16))
     return (out, amax) if return_amax else out
 
 

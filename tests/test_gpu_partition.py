@@ -192,7 +192,7 @@ def test_partitioned_layer_nccl_replicated_input():
     assert results["out"] <= 1e-5 and results["gx"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
 
 
-def _nccl_stack_worker(rank, world, port, results):
+def _nccl_stack_worker(rank, world, port, results, bf16=False):
     """3-layer stack row-partitioned over 2 GPUs (fused ELU boundaries, kept operand splits, replicated input for layer 1,
     in-kernel dropout with rank 0's seed) against the single-GPU GATStack on rank 0 fed the SAME dropout masks."""
     import torch.distributed as dist
@@ -207,7 +207,10 @@ def _nccl_stack_worker(rank, world, port, results):
     n, e, f = 3001, 40000, 64
     spec = [(f, 64, 4, True), (256, 32, 4, True), (128, 7, 2, False)]
     torch.manual_seed(0)
-    model = GATStack(spec, dropout=0.5).to(dev).train()
+    model = GATStack(spec, dropout=0.0 if bf16 else 0.5).to(dev).train()
+    if bf16:      # gathered rows — and the all-gathered copies on the wire — stored as bf16 (tolerance 1e-2, not parity)
+        from atmlgraphattentionnetworks_b200.gat import set_gather_dtype
+        set_gather_dtype(model, torch.bfloat16)
     gen = torch.Generator().manual_seed(1)
     x = torch.randn(n, f, generator=gen).to(dev)
     ei = torch.randint(0, n, (2, e), generator=gen).to(dev)
@@ -216,12 +219,14 @@ def _nccl_stack_worker(rank, world, port, results):
     pmodel = pt.PartitionedGATStack(model)
     xo = x[part.lo:part.hi].clone().requires_grad_(True)
     out = pmodel(xo, part, x_full=x)
-    seeds = [c._last_dropout_seed.clone() for c in model.convs]
+    seeds = [] if bf16 else [c._last_dropout_seed.clone() for c in model.convs]
     out.backward(gout[part.lo:part.hi])
     flat = torch.cat([p.grad.flatten() for p in model.parameters()])
     dist.all_reduce(flat)
     if rank == 0:
         model.zero_grad()
+        if bf16:
+            set_gather_dtype(model, torch.float32)          # the reference run: fp32 rows on one GPU
         for c, s in zip(model.convs, seeds):
             m = dropout_mask_tensor(0.5, s, e + n, c.num_heads)
             c.mask_hook = (lambda mm: (lambda shape: mm))(m)
@@ -247,3 +252,19 @@ def test_partitioned_stack_nccl_fused_boundaries_and_dropout():
     results = mgr.dict()
     mp.spawn(_nccl_stack_worker, args=(2, port, results), nprocs=2, join=True)
     assert results["out"] <= 1e-5 and results["gp"] <= 2e-5, dict(results)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_partitioned_stack_nccl_bf16_rows_on_the_wire():
+    """bf16 gather mode, row-partitioned: the all-gathered Wh / gradient rows are bf16 (half the NVLink bytes); results stay
+    within the mode's stated 1e-2 of the fp32 single-GPU stack"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_nccl_stack_worker, args=(2, port, results, True), nprocs=2, join=True)
+    assert 1e-6 < results["out"] <= 1e-2 and results["gp"] <= 1e-2, dict(results)
