@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gat.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -80,7 +80,7 @@ class EdgeBwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("out_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t),
                 ("dropout", Dropout), ("edge_scratch", C.c_void_p), ("edge_scratch_bytes", C.c_size_t),
-                ("gather_bf16", C.c_int32)]
+                ("gather_bf16", C.c_int32), ("rowrec_in", C.c_void_p)]
 
 
 class EdgeBwdPrepArgs(C.Structure):
@@ -117,7 +117,7 @@ class ProjBwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("x_split", C.c_void_p), ("x_split_bytes", C.c_size_t),
                 ("x_activation", C.c_int32), ("g_t_split", C.c_void_p), ("g_t_split_bytes", C.c_size_t),
-                ("parts", C.c_int32)]
+                ("parts", C.c_int32), ("fuse_prep", C.c_void_p)]
 
 
 class ReadoutGeom(C.Structure):
@@ -165,6 +165,7 @@ _SIGNATURES = {
     "b200gat_edge_bwd_finish": (C.c_int, [C.POINTER(EdgeBwdFinishArgs), C.c_void_p]),
     "b200gat_proj_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Layer), C.c_int64]),
     "b200gat_proj_bwd": (C.c_int, [C.POINTER(ProjBwdArgs), C.c_void_p]),
+    "b200gat_proj_bwd_can_fuse_prep": (C.c_int, [C.POINTER(Layer), C.c_int64, C.POINTER(Layer)]),
     "b200gat_readout_fwd": (C.c_int, [C.POINTER(ReadoutFwdArgs), C.c_void_p]),
     "b200gat_readout_bwd": (C.c_int, [C.POINTER(ReadoutBwdArgs), C.c_void_p]),
 }

@@ -1409,10 +1409,10 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   const b200gat_layer& L = a->layer;
   const int64_t N = a->graph.num_nodes;
   const Geom g = geom_of(L);
-  B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2 && a->g_bias, B200GAT_E_NULL,
+  B200GAT_REQUIRE(a->g_bw && a->g_a1 && a->g_a2 && a->g_b1 && a->g_b2 && (a->g_bias || a->rowrec_in), B200GAT_E_NULL,
                   "edge_bwd: NULL parameter-gradient pointer");
   if (N == 0) {
-    cudaError_t ce = cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream);
+    cudaError_t ce = a->g_bias ? cudaMemsetAsync(a->g_bias, 0, g.d_out * sizeof(float), stream) : cudaSuccess;
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
     return run_finish(L, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a->g_bw, a->g_a1, a->g_a2, a->g_b1, a->g_b2,
                       nullptr, nullptr, false, stream);
@@ -1444,8 +1444,15 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   // zero g_s_dst (accumulated atomically) and, right behind it, the amax slots
   cudaError_t ce = cudaMemsetAsync(g_s_dst, 0, w.off_gp - w.off_gdst, stream);
   if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
-  const int act = a->out_activation;
+  // rowrec_in: the prep pass already ran inside the consuming layer's gX GEMM — gout IS G (activation applied)
+  const bool prep_done = a->rowrec_in != nullptr;
+  const int act = prep_done ? ACT_NONE : a->out_activation;
   B200GAT_REQUIRE(act == ACT_NONE || act == ACT_ELU, B200GAT_E_UNSUPPORTED, "edge_bwd: unknown out_activation %d", act);
+  if (prep_done) {
+    B200GAT_REQUIRE(aligned16(a->rowrec_in) && gout_direct(g, a->gout, a->ldgo) && !a->gather_bf16, B200GAT_E_ALIGN,
+                    "edge_bwd: rowrec_in needs a directly gatherable fp32 gout (concat-like layer, C %% 4 == 0, aligned rows)");
+    rowrec = const_cast<float4*>(reinterpret_cast<const float4*>(a->rowrec_in));
+  }
   void* gsplit = a->g_t_split;
   if (gsplit) {
     const size_t need = blob_bytes(N, g.Dp);
@@ -1454,9 +1461,11 @@ extern "C" int b200gat_edge_bwd(const b200gat_edge_bwd_args* a, void* stream_) {
   }
   // with an output activation the gathered rows are gout * ELU'(out): always the copy
   const bool rows16 = a->gather_bf16 != 0;
-  const bool direct = !act && !rows16 && gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
-                      aligned16(a->bias);
-  if ((rc = run_prep(L, N, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum, rowrec,
+  const bool direct = prep_done ||
+                      (!act && !rows16 && gout_direct(g, a->gout, a->ldgo) && (!g.concat_like || (a->ldo % 4 == 0 && aligned16(a->out))) &&
+                       aligned16(a->bias));
+  if (!prep_done &&
+      (rc = run_prep(L, N, a->gout, a->ldgo, a->out, a->ldo, a->o_heads, a->bias, a->s_dst, a->rowmax, a->rowsum, rowrec,
                      direct ? nullptr : gp, a->g_bias, act, stream, rows16)))
     return rc;
   const float* grows = direct ? a->gout : gp;

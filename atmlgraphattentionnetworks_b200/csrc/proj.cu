@@ -122,6 +122,11 @@ extern "C" size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* L, int64
   return proj_tc_bwd_workspace_bytes(*L, N);
 }
 
+extern "C" int b200gat_proj_bwd_can_fuse_prep(const b200gat_layer* consumer, int64_t N, const b200gat_layer* producer) {
+  if (!consumer || !producer || N <= 0) return 0;
+  return proj_tc_can_fuse_prep(*consumer, N, *producer) ? 1 : 0;
+}
+
 extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200GAT_REQUIRE(a, B200GAT_E_NULL, "proj_bwd: NULL args");
@@ -144,6 +149,7 @@ extern "C" int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream_) {
   B200GAT_REQUIRE(a->ldx >= F && (!a->g_x || a->ldgx >= F), B200GAT_E_SHAPE, "proj_bwd: leading dimension < in_channels");
   if (proj_tc_bwd_supported(L, N)) return proj_tc_bwd(*a, stream);
   B200GAT_REQUIRE(a->g_t && a->x, B200GAT_E_NULL, "proj_bwd: the CUDA-core path needs fp32 g_t and x");
+  B200GAT_REQUIRE(!a->fuse_prep, B200GAT_E_UNSUPPORTED, "proj_bwd: fuse_prep needs the tensor-core path");
   if (a->g_x && a->parts != B200GAT_PROJ_BWD_GW) {
     rc = gemm_simt<true, false>(a->g_t, Dp, a->w, F, a->g_x, a->ldgx, nullptr, N, F, Dp, 1, stream);
     if (rc) return rc;

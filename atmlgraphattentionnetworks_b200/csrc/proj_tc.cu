@@ -187,9 +187,17 @@ struct TcGemmParams {
   // to the same (row, column) of n_peer peer-mapped copies of C
   float* peer_c[B200GAT_MAX_PEERS]; int n_peer;
   uint16_t* c16;           // optional bf16 copy of C (same ldc): the gathered-row storage of the bf16 mode (wh_bf16)
+  // EPI_PREP: the gX GEMM of layer k+1 also runs the PREP pass of layer k's edge backward (its output gX IS layer k's upstream
+  // gradient): C receives G = gX * act'(out_k) — the gatherable gradient rows — and the row records / g_bias are produced here
+  const float* pr_out; int64_t pr_ldo;        // layer k's pre-activation output [M, N]
+  const float* pr_bias;                       // [N]
+  const float* pr_s_dst; const float* pr_rowmax; const float* pr_rowsum;   // [M, pr_H]
+  float4* pr_rowrec;                          // out [M, pr_H] {s_dst, rowmax, 1/(rowsum + 1e-16), Drow}
+  float* pr_g_bias;                           // out [N], zero-initialised by the host, accumulated atomically
+  int pr_H, pr_C, pr_act;                     // layer k's heads / channels per head (N = pr_H * pr_C), 1: multiply by ELU'(out)
 };
 
-enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2 };
+enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2, EPI_PREP = 3 };
 
 // CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA PAIR (cluster of two SMs) computes one 256 x BN
 // tile: each CTA stages its own 128 A rows and HALF of the B tile (BN/2 rows), one tcgen05.mma.cta_group::2 issued by the
@@ -402,6 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           const int64_t col = int64_t(n0) + c;
           const bool ok = col < p.N;
           vec[c] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+          if (EPI == EPI_PREP) vec[BN + c] = ok ? __ldg(p.pr_bias + col) : 0.f;      // layer k's bias (O = out - bias)
           if (EPI == EPI_LOGITS) {
             vec[BN + c] = ok ? __ldg(p.a1 + col) : 0.f;
             vec[2 * BN + c] = ok ? __ldg(p.a2 + col) : 0.f;
@@ -485,6 +494,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             }
           }
         }
+        if (EPI == EPI_PREP) {
+          // ---- layer k's prep, fused: acc holds gX = d loss / d act(out_k) of this thread's row and 128 columns.  The
+          // matching out_k tile comes in through the warp's transposing buffer (coalesced 64-byte runs, 16 columns at a
+          // time); G = gX * ELU'(out) replaces acc, Drow[row, h] = <G, out - bias> is summed per head of layer k. ----
+          float* stg = stgbuf + ew * (32 * S::STG_ROW);
+          const int64_t wrow0 = int64_t(m0) + q * 32;
+          const int CPk = p.pr_C;                       // 8, 16, 32, 64, 128 or 256 (== BN): checked on the host
+          float dh[16];                                 // per-head partial dot products (up to 128 / 8 heads per thread)
+#pragma unroll
+          for (int t = 0; t < 16; ++t) dh[t] = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 128; cc += 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int idx = lane + 32 * i, r = idx >> 2, c4 = (idx & 3) << 2;
+              const int64_t rr = wrow0 + r, col = col0 + cc + c4;
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rr < p.M && col + 4 <= p.N) o = ldg4(p.pr_out + rr * p.pr_ldo + col);
+              *reinterpret_cast<float4*>(stg + r * S::STG_ROW + c4) = o;
+            }
+            __syncwarp();
+            float dc = 0.f;                             // this 16-column chunk's contribution (CPk >= 16: one head)
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(stg + lane * S::STG_ROW + j);
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+              float d4 = 0.f;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float g = acc[cc + j + t];
+                if (p.pr_act) g *= elu_grad(ov[t]);
+                acc[cc + j + t] = g;
+                d4 = fmaf(g, ov[t] - vec[BN + cbase + cc + j + t], d4);
+              }
+              if (CPk == 8) dh[(cc + j) >> 3] += d4;    // two 4-column groups per head
+              else dc += d4;
+            }
+            if (CPk >= 128) dh[0] += dc;
+            else if (CPk == 64) dh[cc >> 6] += dc;
+            else if (CPk == 32) dh[cc >> 5] += dc;
+            else if (CPk == 16) dh[cc >> 4] += dc;
+            __syncwarp();
+          }
+          if (CPk == 256) {                             // one head per 256-wide tile: combine the two column halves
+            const int r = q * 32 + lane;
+            if (half == 1) red[r] = dh[0];
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
+            if (half == 0 && row_ok && n0 < p.N) {
+              const int64_t item = row * p.pr_H + n0 / 256;
+              p.pr_rowrec[item] = make_float4(__ldg(p.pr_s_dst + item), __ldg(p.pr_rowmax + item),
+                                              1.f / (__ldg(p.pr_rowsum + item) + 1e-16f), dh[0] + red[r]);
+            }
+          } else if (row_ok) {
+            const int nh = CPk >= 128 ? 1 : 128 / CPk;  // heads inside this thread's 128 columns
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const int64_t col = col0 + int64_t(t) * CPk;
+              if (t < nh && col < p.N) {
+                const int64_t item = row * p.pr_H + col / CPk;
+                p.pr_rowrec[item] = make_float4(__ldg(p.pr_s_dst + item), __ldg(p.pr_rowmax + item),
+                                                1.f / (__ldg(p.pr_rowsum + item) + 1e-16f), dh[t]);
+              }
+            }
+          }
+        }
         const bool al_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
         if (al_ok) {
           // Coalesced stores.  A thread owns one ROW (TMEM lane) and 128 of its columns, so a direct 128-bit store hits 32
@@ -500,11 +574,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
               *reinterpret_cast<float4*>(stg + lane * S::STG_ROW + j) =
                   make_float4(acc[cc + j], acc[cc + j + 1], acc[cc + j + 2], acc[cc + j + 3]);
             __syncwarp();
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);        // EPI_PREP: column sums of G (layer k's g_bias)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int idx = lane + 32 * i, r = idx >> 2, c4 = (idx & 3) << 2;
               const float4 v = *reinterpret_cast<const float4*>(stg + r * S::STG_ROW + c4);
               const int64_t rr = wrow0 + r, col = col0 + cc + c4;
+              if (EPI == EPI_PREP && rr < p.M) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
               if (rr < p.M) {
                 float* d = p.C + rr * p.ldc + col;
                 if (col + 4 <= p.N) {
@@ -523,6 +599,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                     if (col + 2 < p.N) dk[2] = v.z;
                   }
                 }
+              }
+            }
+            if (EPI == EPI_PREP) {                      // lanes with equal (lane & 3) hold the same 4 columns: combine, then
+#pragma unroll
+              for (int o2 = 4; o2 < 32; o2 <<= 1) {     // lanes 0..3 add the warp's 32-row partial sums to g_bias
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o2); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o2);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o2); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o2);
+              }
+              const int64_t col = col0 + cc + (lane << 2);
+              if (lane < 4 && col + 4 <= p.N) {
+                atomicAdd(p.pr_g_bias + col, cs.x); atomicAdd(p.pr_g_bias + col + 1, cs.y);
+                atomicAdd(p.pr_g_bias + col + 2, cs.z); atomicAdd(p.pr_g_bias + col + 3, cs.w);
               }
             }
             __syncwarp();
@@ -781,6 +869,19 @@ bool proj_tc_fwd_supported(const b200gat_layer& L, int64_t N) {
 }
 bool proj_tc_bwd_supported(const b200gat_layer& L, int64_t N) { return proj_tc_fwd_supported(L, N); }
 
+// Can the gX GEMM of `consumer` (layer k+1) run the prep pass of `producer` (layer k) in its epilogue (EPI_PREP)?  The
+// producer must be concat-like with a head width the epilogue's per-thread 128-column block can sum (8 .. 128, or one whole
+// 256-wide tile) and its output must be exactly the consumer's input.
+bool proj_tc_can_fuse_prep(const b200gat_layer& consumer, int64_t N, const b200gat_layer& producer) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("B200GAT_NO_FUSE_PREP"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off || !proj_tc_bwd_supported(consumer, N)) return false;
+  const int64_t C = producer.out_channels, H = producer.heads, F = consumer.in_channels;
+  if (!(producer.concat || H == 1) || H * C != F || F % 4 != 0) return false;
+  if (C == 256) return F > 128;                          // BN == 256: one head per tile
+  return C == 8 || C == 16 || C == 32 || C == 64 || C == 128;
+}
+
 size_t proj_tc_split_bytes(const b200gat_layer& L, int64_t N) {
   return proj_tc_fwd_supported(L, N) ? blob_bytes(N, L.in_channels) : 0;
 }
@@ -869,7 +970,25 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
     if ((rc = launch_split(a.w, F, W, stream))) return rc;
     TcGemmParams p{};
     p.C = a.g_x; p.ldc = a.ldgx;
-    if ((rc = gemm_blobs<false, true, EPI_STORE>(G, W, N, F, Dp, p, 1, stream))) return rc;
+    if (a.fuse_prep) {
+      // the producer layer's prep pass rides in this GEMM's epilogue (b200gat_proj_bwd_args.fuse_prep)
+      const b200gat_edge_bwd_prep_args& f = *a.fuse_prep;
+      B200GAT_REQUIRE(proj_tc_can_fuse_prep(L, N, f.layer), B200GAT_E_UNSUPPORTED,
+                      "proj_bwd: fuse_prep is not offered for this pair of layers (b200gat_proj_bwd_can_fuse_prep)");
+      B200GAT_REQUIRE(f.num_rows == N && f.out && f.bias && f.s_dst && f.rowmax && f.rowsum && f.rowrec && f.g_bias,
+                      B200GAT_E_NULL, "proj_bwd: fuse_prep: NULL pointer or row count mismatch");
+      B200GAT_REQUIRE(f.ldo >= F && f.ldo % 4 == 0 && aligned16(f.out) && aligned16(f.rowrec) && a.ldgx % 4 == 0 && aligned16(a.g_x),
+                      B200GAT_E_ALIGN, "proj_bwd: fuse_prep needs 16-byte aligned out / g_x rows");
+      B200GAT_REQUIRE(f.out_activation == ACT_NONE || f.out_activation == ACT_ELU, B200GAT_E_UNSUPPORTED,
+                      "proj_bwd: fuse_prep: unknown out_activation %d", f.out_activation);
+      cudaError_t ce0 = cudaMemsetAsync(f.g_bias, 0, size_t(F) * sizeof(float), stream);
+      if (ce0 != cudaSuccess) return fail(static_cast<int>(ce0), "proj_bwd: memset: %s", cudaGetErrorString(ce0));
+      p.pr_out = f.out; p.pr_ldo = f.ldo; p.pr_bias = f.bias;
+      p.pr_s_dst = f.s_dst; p.pr_rowmax = f.rowmax; p.pr_rowsum = f.rowsum;
+      p.pr_rowrec = reinterpret_cast<float4*>(f.rowrec); p.pr_g_bias = f.g_bias;
+      p.pr_H = static_cast<int>(f.layer.heads); p.pr_C = static_cast<int>(f.layer.out_channels); p.pr_act = f.out_activation;
+      if ((rc = gemm_blobs<false, true, EPI_PREP>(G, W, N, F, Dp, p, 1, stream))) return rc;
+    } else if ((rc = gemm_blobs<false, true, EPI_STORE>(G, W, N, F, Dp, p, 1, stream))) return rc;
   }
   if (!want_gw) return 0;
   // gW[Dp,F] = gT^T · X : K = nodes; both operands MN-major straight from the row-major planes; split-K across CTAs

@@ -13,6 +13,7 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream);
 int launch_logits(const b200gat_proj_fwd_args& a, cudaStream_t stream);
 
 bool proj_tc_bwd_supported(const b200gat_layer& L, int64_t N);
+bool proj_tc_can_fuse_prep(const b200gat_layer& consumer, int64_t N, const b200gat_layer& producer);
 size_t proj_tc_bwd_workspace_bytes(const b200gat_layer& L, int64_t N);
 int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream);
 

@@ -62,6 +62,7 @@ class _timed:
 # layer k's edge backward), but the 2.4 M-node graph's step went 177 -> 234 ms — the GB-sized buffers that now live across two
 # streams defeat the caching allocator's reuse.  Off by default.
 _OVERLAP_GW = __import__("os").environ.get("B200GAT_OVERLAP_GW", "0") == "1"
+_NO_FUSE_PREP = __import__("os").environ.get("B200GAT_NO_FUSE_PREP", "0") == "1"
 _side_streams = {}
 _join_pending = set()
 
@@ -110,6 +111,18 @@ def _split_mask(mask):
     return (None, mask) if isinstance(mask, tuple) else (mask, None)
 
 
+class BoundaryLink:
+    """Hand-over between two consecutive layers whose ELU boundary is fused (producer called with act_out, consumer with
+    act_in).  The producer's forward fills in what its prep pass needs; in the backward the CONSUMER's gX GEMM runs that pass
+    in its epilogue (b200gat_proj_bwd_args.fuse_prep) and leaves the row records / g_bias here for the producer's
+    b200gat_edge_bwd (rowrec_in) — one streaming pass over [N, D] less per layer boundary."""
+    __slots__ = ("layer", "n", "d_out", "out", "bias", "s_dst", "rowmax", "rowsum", "rows16", "rowrec", "g_bias", "done")
+
+    def __init__(self):
+        self.done = False
+        self.layer = None
+
+
 class GATLayerFunction(torch.autograd.Function):
     """x [N,F], bias [D_out], the layer's persistent packed parameter storage `packed` = (W [Dp,F], bw/a1/a2 [Dp],
     b1/b2 [H]; the per-head parameters are views of it) and the 6H per-head parameters themselves (*params, in the
@@ -135,6 +148,7 @@ class GATLayerFunction(torch.autograd.Function):
         # bf16 storage of the gathered rows (GraphAttentionLayer.gather_dtype): only the plain configuration has kernels for
         # it (LeakyReLU logits, no dropout / mask); anything else keeps the fp32 rows — never less precise than asked
         rows16 = bool(len(fuse) > 4 and fuse[4]) and drop is None and mask is None and logit[0] == _abi.LOGIT_LEAKY_RELU
+        link_in, link_out = (fuse[5], fuse[6]) if len(fuse) > 6 else (None, None)
         lib = _abi.lib()
         dev = x.device
         n = x.shape[0]
@@ -176,6 +190,12 @@ class GATLayerFunction(torch.autograd.Function):
         ctx.graph, ctx.geom, ctx.mask, ctx.act, ctx.logit = graph, geom, mask, (bool(act_in), bool(act_out)), logit
         ctx.drop = drop
         ctx.rows16 = rows16
+        ctx.link_in = link_in if (link_in is not None and link_in.layer is not None and link_in.n == n) else None
+        ctx.link_out = None
+        if link_out is not None and act_out and not heads_mode and any(ctx.needs_input_grad):
+            link_out.layer, link_out.n, link_out.d_out, link_out.rows16 = layer, n, d_out, rows16
+            link_out.out, link_out.bias, link_out.s_dst, link_out.rowmax, link_out.rowsum = out, bias, s_dst, rowmax, rowsum
+            ctx.link_out = link_out
         # the kernels read the packed storage through raw pointers and the per-head Parameters alias it through `.data =`,
         # which does not share version counters: remember the Parameters' versions so that an in-place update between this
         # forward and its backward (optimizer.step, load_state_dict, ...) is an error, as it is in the reference
@@ -224,6 +244,10 @@ class GATLayerFunction(torch.autograd.Function):
             # the across-heads softmax logits couple the heads of an edge in the backward: the one variant with a per-edge
             # scratch buffer ([E', H] floats, include/b200gat.h)
             scratch = (_workspace(graph.num_edges * h * 4, dev) if ctx.logit[0] == _abi.LOGIT_HEAD_SOFTMAX else None)
+            # the prep pass of THIS layer already ran in the consuming layer's gX GEMM (BoundaryLink): gout is G itself
+            lo = ctx.link_out if (ctx.link_out is not None and ctx.link_out.done) else None
+            if lo is not None:
+                g_bias = lo.g_bias
             ea = _abi.EdgeBwdArgs(layer, graph.c_struct(), gout.data_ptr(), d_out,
                                   None if heads_mode else fwd_out.data_ptr(), d_out,
                                   fwd_out.data_ptr() if heads_mode else None, bias.data_ptr(),
@@ -233,16 +257,28 @@ class GATLayerFunction(torch.autograd.Function):
                                   g_b1.data_ptr(), g_b2.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes,
                                   _abi.ACT_ELU if act_out else _abi.ACT_NONE, _ptr(g_split), gs_bytes,
                                   _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0,
-                                  1 if ctx.rows16 else 0)
+                                  1 if ctx.rows16 else 0, lo.rowrec.data_ptr() if lo is not None else None)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
             ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
+
+            # the PRODUCING layer's prep pass rides in this layer's gX GEMM when the pair qualifies (BoundaryLink)
+            li = ctx.link_in
+            fuse_prep = None
+            if (li is not None and need_gx and gs_bytes and act_in and not li.rows16 and not _NO_FUSE_PREP and
+                    lib.b200gat_proj_bwd_can_fuse_prep(ctypes.byref(layer), n, ctypes.byref(li.layer))):
+                li.rowrec = torch.empty((n, int(li.layer.heads), 4), **f32)
+                li.g_bias = torch.empty(li.d_out, **f32)
+                fuse_prep = _abi.EdgeBwdPrepArgs(li.layer, n, None, 0, li.out.data_ptr(), li.d_out, None, li.bias.data_ptr(),
+                                                 li.s_dst.data_ptr(), li.rowmax.data_ptr(), li.rowsum.data_ptr(),
+                                                 li.rowrec.data_ptr(), None, li.g_bias.data_ptr(), _abi.ACT_ELU, None)
 
             def proj_bwd(parts, strm):
                 ws2 = _workspace(ws2_bytes, dev)
                 pb = _abi.ProjBwdArgs(layer, n, g_t.data_ptr(), x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(),
                                       _ptr(g_x), f_in, g_w.data_ptr(), ws2.data_ptr(), ws2_bytes,
                                       _ptr(x_split), x_split.numel() if x_split is not None else 0,
-                                      _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes, parts)
+                                      _abi.ACT_ELU if act_in else _abi.ACT_NONE, _ptr(g_split), gs_bytes, parts,
+                                      ctypes.addressof(fuse_prep) if (fuse_prep is not None and parts != _abi.PROJ_BWD_GW) else None)
                 _call("b200gat_proj_bwd", lib.b200gat_proj_bwd, pb, strm, ctx.geom)
                 return ws2
             # gX feeds the previous layer's backward; gW feeds nobody until the optimizer.  When this layer has a
@@ -267,6 +303,8 @@ class GATLayerFunction(torch.autograd.Function):
                 _queue_join(dev, main, side)
             else:
                 proj_bwd(0, stream)
+            if fuse_prep is not None:
+                li.done = True
             _abi.launches += 2
         # per-head gradients are views of the packed buffers, in the order of _head_parameters (autograd takes them as
         # the parameters' .grad without a copy when no gradient is accumulated yet)
@@ -319,6 +357,7 @@ class GraphAttentionLayer(torch.nn.Module):
             self.bias = torch.nn.Parameter(torch.zeros(output_channels * num_heads))
         self.graph_cache = GLOBAL_CACHE
         self.mask_hook = None   # parity tests: callable (E', H) -> keep-multiplier [E', H] in ORIGINAL edge order
+        self.last_link = None   # BoundaryLink of the last forward_fused(act_out=True) call, for the consuming layer
         self._store = None      # persistent packed parameter storage (see _packed_storage)
         # the function applied to the edge logits before the softmax: (B200GAT_LOGIT_* code, negative slope); GAT.py:30
         self.logit_activation = (_abi.LOGIT_LEAKY_RELU, NEGATIVE_SLOPE)
@@ -417,7 +456,7 @@ class GraphAttentionLayer(torch.nn.Module):
         """the ELU that follows this layer can be deferred to its consumer (concat-like layers only, edge_bwd contract)"""
         return bool(self.concat) or self.num_heads == 1
 
-    def forward_fused(self, x, edge_index, graph=None, act_in=False, act_out=False, x_amax=None):
+    def forward_fused(self, x, edge_index, graph=None, act_in=False, act_out=False, x_amax=None, producer_link=None):
         """Internal composition entry (GATStack / GATNet): -> (out, out_amax).  act_in: x is a pre-activation tensor
         produced by a layer called with act_out, and ELU(x) is what is projected; act_out: return the pre-activation
         output (see GATLayerFunction).  Never hand an act_out tensor to anything but an act_in layer."""
@@ -439,9 +478,12 @@ class GraphAttentionLayer(torch.nn.Module):
             raise TypeError("GraphAttentionLayer parameters must be float32 CUDA tensors (move the module with .to(device))")
         packed = self._packed_storage()
         geom = (self.input_channels, self.output_channels, self.num_heads, bool(self.concat))
+        # producer_link: the BoundaryLink of the layer that produced x (act_in); self.last_link: this layer's, for its consumer
+        self.last_link = BoundaryLink() if act_out else None
         return GATLayerFunction.apply(x, self.bias, graph, geom, mask,
                                       (bool(act_in), bool(act_out), x_amax, tuple(self.logit_activation),
-                                       self.gather_dtype == torch.bfloat16), packed, *self._head_parameters())
+                                       self.gather_dtype == torch.bfloat16, producer_link if act_in else None, self.last_link),
+                                      packed, *self._head_parameters())
 
 
 def _logit_code(fn):

@@ -136,7 +136,8 @@ class GATNet(torch.nn.Module):
                 # elu(conv1) is fused into the conv1 -> conv2 boundary, elu(conv2) into the readout's load of x, and
                 # scatter_mean -> lin1 -> relu -> lin2 -> log_softmax (GATNet.py:73-75) run as ONE fused op
                 x, amax = self.conv1.forward_fused(x, edge_index, act_out=True)
-                x = self.conv2.forward_fused(x, edge_index, act_in=True, act_out=True, x_amax=amax)[0]
+                x = self.conv2.forward_fused(x, edge_index, act_in=True, act_out=True, x_amax=amax,
+                                             producer_link=self.conv1.last_link)[0]
                 return readout_head(x, data.batch.long(), self.lin1, self.lin2, getattr(data, "num_graphs", None), act_in=True)
             else:
                 x = act(self.conv1(x, edge_index))
@@ -147,7 +148,7 @@ class GATNet(torch.nn.Module):
         x = F.dropout(x, p=0.6, training=self.training)        # GATNet.py:78
         if self.model_name == "GAT" and not self.training:     # no feature dropout in between: fuse elu(conv1)
             x, amax = self.conv1.forward_fused(x, edge_index, act_out=True)
-            x = self.conv2.forward_fused(x, edge_index, act_in=True, x_amax=amax)[0]
+            x = self.conv2.forward_fused(x, edge_index, act_in=True, x_amax=amax, producer_link=self.conv1.last_link)[0]
             return F.log_softmax(x, dim=1)
         x = act(self.conv1(x, edge_index))
         x = F.dropout(x, p=0.6, training=self.training)
@@ -165,12 +166,13 @@ class GATStack(torch.nn.Module):
             [GraphAttentionLayer(i, o, num_heads=h, concat=c, dropout=dropout) for (i, o, h, c) in spec])
 
     def forward(self, x, edge_index):
-        pending, amax = False, None      # pending: x is a pre-activation tensor whose ELU the next layer applies
+        pending, amax, link = False, None, None      # pending: x is a pre-activation tensor whose ELU the next layer applies
         last = len(self.convs) - 1
         for k, conv in enumerate(self.convs):
             fuse_out = k < last and conv.can_fuse_activation_out() and not os.environ.get("B200GAT_NO_FUSE_ACT")
-            x, amax = conv.forward_fused(x, edge_index, act_in=pending, act_out=fuse_out, x_amax=amax if pending else None)
-            pending = fuse_out
+            x, amax = conv.forward_fused(x, edge_index, act_in=pending, act_out=fuse_out, x_amax=amax if pending else None,
+                                         producer_link=link if pending else None)
+            pending, link = fuse_out, conv.last_link
             if k < last and not fuse_out:
                 x = F.elu(x)
         return x

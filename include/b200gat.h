@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GAT_ABI_VERSION 14
+#define B200GAT_ABI_VERSION 15
 
 enum {
   B200GAT_OK = 0,
@@ -216,6 +216,9 @@ typedef struct {
                                          CSC entry and head, consumed by the second pass); NULL otherwise */
   int32_t gather_bf16;                /* the gatherable gradient rows G are written (by the prep pass, into the workspace) and
                                          gathered (by the CSC pass) as bf16: the backward's half of the bf16 mode above */
+  const float* rowrec_in;             /* optional [N, H, 4]: the prep pass already ran in the CONSUMING layer's gX GEMM
+                                         (b200gat_proj_bwd_args.fuse_prep): gout is then G itself (activation applied,
+                                         directly gatherable), out_activation is ignored and g_bias is NOT written */
 } b200gat_edge_bwd_args;
 size_t b200gat_edge_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 /* bytes of a g_t_split buffer; 0 when the projection backward of this geometry runs on the CUDA-core path */
@@ -296,7 +299,16 @@ typedef struct {
                                          independent: a caller may issue gW on a second stream so that it overlaps the
                                          previous layer's edge backward, which only waits for gX (each call needs its own
                                          workspace) */
+  /* Fusion across the layer boundary in the backward: this layer's gX IS the upstream gradient of the PRODUCING layer k
+   * (whose output is this layer's x), and the first pass of layer k's edge backward ("prep": G = gX * act'(out_k), the row
+   * records {s_dst, rowmax, 1/rowsum, Drow = <G, out_k - bias_k>}, g_bias_k = column sums of G) only streams gX and out_k
+   * once more.  With fuse_prep = layer k's prep arguments (layer, num_rows, out / ldo, bias, s_dst, rowmax, rowsum, rowrec,
+   * g_bias, out_activation; gout / g_pad ignored) the gX GEMM does that pass in its epilogue: g_x then receives G, and
+   * layer k's b200gat_edge_bwd is called with rowrec_in = that rowrec.  Offered when b200gat_proj_bwd_can_fuse_prep()
+   * returns 1 (tensor-core path; producer concat-like with 8 / 16 / 32 / 64 / 128 / 256 channels per head). */
+  const b200gat_edge_bwd_prep_args* fuse_prep;
 } b200gat_proj_bwd_args;
+int b200gat_proj_bwd_can_fuse_prep(const b200gat_layer* consumer, int64_t num_nodes, const b200gat_layer* producer);
 enum { B200GAT_PROJ_BWD_GX = 1, B200GAT_PROJ_BWD_GW = 2 };
 size_t b200gat_proj_bwd_workspace_bytes(const b200gat_layer* layer, int64_t num_nodes);
 int b200gat_proj_bwd(const b200gat_proj_bwd_args* a, void* stream);
