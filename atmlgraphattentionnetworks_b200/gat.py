@@ -194,7 +194,10 @@ class GATLayerFunction(torch.autograd.Function):
         ctx.link_out = None
         if link_out is not None and act_out and not heads_mode and any(ctx.needs_input_grad):
             link_out.layer, link_out.n, link_out.d_out, link_out.rows16 = layer, n, d_out, rows16
-            link_out.out, link_out.bias, link_out.s_dst, link_out.rowmax, link_out.rowsum = out, bias, s_dst, rowmax, rowsum
+            # (detached aliases only: `out` itself will own this node — holding it here would tie ctx -> link -> out ->
+            #  grad_fn -> ctx into a reference cycle and keep every saved tensor of the step alive until the GC runs)
+            link_out.out, link_out.bias, link_out.s_dst, link_out.rowmax, link_out.rowsum = (
+                out.detach(), bias.detach(), s_dst, rowmax, rowsum)
             ctx.link_out = link_out
         # the kernels read the packed storage through raw pointers and the per-head Parameters alias it through `.data =`,
         # which does not share version counters: remember the Parameters' versions so that an in-place update between this
