@@ -418,6 +418,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * S::EPI_WARPS) : "memory");
       }
+      if (EPI == EPI_PREP) {
+        // the epilogue has no slack for DRAM round trips (the MMA warp stalls once both TMEM buffers are full): pull this
+        // warp's 32 x 128 block of layer k's output into L2 now, while the tensor core works on the tile
+        const int64_t wr0 = int64_t(m0) + q * 32, c0 = int64_t(n0) + cbase;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int line = lane + 32 * i;                 // 32 rows x 4 lines of 128 bytes
+          const int64_t rr = wr0 + (line >> 2), col = c0 + ((line & 3) << 5);
+          if (rr < p.M && col < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pr_out + rr * p.pr_ldo + col));
+        }
+      }
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -504,16 +516,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           float dh[16];                                 // per-head partial dot products (up to 128 / 8 heads per thread)
 #pragma unroll
           for (int t = 0; t < 16; ++t) dh[t] = 0.f;
+          float4 nxt[4];                                // chunk cc + 16 travels while chunk cc is transposed and consumed
+          auto load_chunk = [&](int cc) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int idx = lane + 32 * i, r = idx >> 2, c4 = (idx & 3) << 2;
+              const int64_t rr = wrow0 + r, col = col0 + cc + c4;
+              nxt[i] = (rr < p.M && col + 4 <= p.N) ? ldg4(p.pr_out + rr * p.pr_ldo + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          load_chunk(0);
 #pragma unroll
           for (int cc = 0; cc < 128; cc += 16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int idx = lane + 32 * i, r = idx >> 2, c4 = (idx & 3) << 2;
-              const int64_t rr = wrow0 + r, col = col0 + cc + c4;
-              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rr < p.M && col + 4 <= p.N) o = ldg4(p.pr_out + rr * p.pr_ldo + col);
-              *reinterpret_cast<float4*>(stg + r * S::STG_ROW + c4) = o;
+              *reinterpret_cast<float4*>(stg + r * S::STG_ROW + c4) = nxt[i];
             }
+            if (cc + 16 < 128) load_chunk(cc + 16);
             __syncwarp();
             float dc = 0.f;                             // this 16-column chunk's contribution (CPk >= 16: one head)
 #pragma unroll

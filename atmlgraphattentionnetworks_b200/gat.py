@@ -62,7 +62,13 @@ class _timed:
 # layer k's edge backward), but the 2.4 M-node graph's step went 177 -> 234 ms — the GB-sized buffers that now live across two
 # streams defeat the caching allocator's reuse.  Off by default.
 _OVERLAP_GW = __import__("os").environ.get("B200GAT_OVERLAP_GW", "0") == "1"
-_NO_FUSE_PREP = __import__("os").environ.get("B200GAT_NO_FUSE_PREP", "0") == "1"
+# The producing layer's prep pass fused into this layer's gX GEMM epilogue (b200gat_proj_bwd_args.fuse_prep, BoundaryLink) is
+# OPT-IN (B200GAT_FUSE_PREP=1).  Measured on one B200 (PPI-shaped layers): edge_bwd 0.66 -> 0.50 ms per layer as intended, but
+# the gX GEMM 0.64 -> 1.24 ms — the GEMM's epilogue warps sit on the tensor pipe's critical path (the MMA warp stalls as soon as
+# both TMEM buffers are full), and the extra tile of `out` they must pull in (even L2-prefetched and double-buffered in
+# registers) drops the tensor pipe from 62 % to 16 % active (profiles/r2p_*).  Parity-green (the stack tests run it), kept for a
+# design with dedicated loader warps.
+_NO_FUSE_PREP = __import__("os").environ.get("B200GAT_FUSE_PREP", "0") != "1"
 _side_streams = {}
 _join_pending = set()
 

@@ -918,9 +918,8 @@ def main():
             "note": "gathered rows (Wh forward, gradient rows backward, and the all-gathered copies at N > 1) stored as bf16; "
                     "fp32 arithmetic; tolerance 1e-2 instead of 1e-5 (tests/test_gpu_parity.py::test_bf16_gathered_rows_*)",
             "large": run_workload("large", env, sub_steps, 3, args, gather_bf16=True, e2e=False, cpu=False, traffic_name="large_bf16")}
-        if world == 1:
-            subs["bf16_gather"]["ppi"] = run_workload("ppi", env, args.steps, warmup, args, gather_bf16=True, e2e=False, cpu=False,
-                                                      traffic_name="ppi_bf16")
+        # (not run on the PPI-shaped batch: with L2-resident rows the edge kernels are issue-bound, and the 8-byte loads +
+        #  conversions of the bf16 rows make them SLOWER — measured edge_fwd 0.257 -> 0.297 ms)
         if world == 1:
             subs["cifar"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=128, captured=True)
             subs["cifar"]["batch512"] = run_workload("cifar", env, args.steps, warmup, args, num_graphs=512, cpu=False,

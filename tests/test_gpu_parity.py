@@ -382,10 +382,14 @@ STACK_CASES = [
 ]
 
 
+@pytest.mark.parametrize("fuse_prep", [False, True], ids=["prep_pass", "prep_in_gx_gemm"])
 @pytest.mark.parametrize("case", STACK_CASES, ids=lambda c: c[0])
-def test_stack_with_fused_activation_matches_cpu_oracle(case):
+def test_stack_with_fused_activation_matches_cpu_oracle(case, fuse_prep, monkeypatch):
+    from atmlgraphattentionnetworks_b200 import gat as gat_module
     from atmlgraphattentionnetworks_b200.gatnet import GATStack
     from oracle.gat_port import PortStack
+    # fuse_prep: the opt-in variant that runs layer k's prep pass in the epilogue of layer k+1's gX GEMM (BoundaryLink)
+    monkeypatch.setattr(gat_module, "_NO_FUSE_PREP", not fuse_prep)
     name, n, e, f, spec = case
     gen = torch.Generator().manual_seed(sum(map(ord, name)))
     torch.manual_seed(3)
