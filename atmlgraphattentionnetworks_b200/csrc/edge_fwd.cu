@@ -267,22 +267,36 @@ __global__ void __launch_bounds__(256, 3) edge_fwd16_stream_kernel(const EdgeFwd
 template <int G, int NV>
 __global__ void __launch_bounds__(256) edge_fwd_act_kernel(const EdgeFwdParams p) { edge_fwd_body<G, NV, true, false, true>(p); }
 
-// concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c]
+// concat == False with H > 1 (GAT.py:65-66): out[i,c] = mean_h O[i,h,c] + bias[c].  One thread per FOUR channels of a node
+// (o_heads rows are 16-byte aligned, pad channels zero): the H 128-bit loads of a thread are independent and in flight
+// together.
 __global__ void __launch_bounds__(256)
 head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bias, float* __restrict__ out,
                  int64_t ldo, int64_t N, int H, int C, int Cp, uint32_t* __restrict__ out_amax) {
-  const int64_t total = N * C;
+  const int Q = Cp >> 2;
+  const int64_t total = N * Q;
+  const float inv_h = 1.f / static_cast<float>(H);
   float amax = 0.f;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t i = t / C;
-    const int c = static_cast<int>(t - i * C);
+    const int64_t i = t / Q;
+    const int c = 4 * static_cast<int>(t - i * Q);
     const float* src = o_heads + i * int64_t(H) * Cp + c;
-    float s = 0.f;
-    for (int h = 0; h < H; ++h) s += __ldg(src + h * Cp);
-    const float r = s / static_cast<float>(H) + __ldg(bias + c);
-    out[i * ldo + c] = r;
-    amax = fmaxf(amax, fabsf(r));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int h = 0; h < H; ++h) {
+      const float4 v = ldg4(src + h * Cp);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c + u < C) {
+        const float r = sv[u] / static_cast<float>(H) + __ldg(bias + c + u);
+        out[i * ldo + c + u] = r;
+        amax = fmaxf(amax, fabsf(r));
+      }
   }
+  (void)inv_h;
   if (out_amax) warp_atomic_amax(out_amax, amax);
 }
 
@@ -929,7 +943,7 @@ extern "C" int b200gat_edge_fwd(const b200gat_edge_fwd_args* a, void* stream_) {
   if (rc) return rc;
   if ((rc = launch_edge_fwd_hub(p, stream))) return rc;
   if (heads_mode) {
-    const int64_t total = N * C;
+    const int64_t total = N * (Cp / 4);
     const int64_t want = ceil_div(total, 256);
     const int64_t cap = int64_t(sm_count()) * 8;
     head_mean_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, stream>>>(a->o_heads, a->bias, a->out, a->ldo,
