@@ -32,7 +32,10 @@ class CapturedStep:
     ingested inside the graph; `num_nodes` defaults to inputs['x'].shape[0].  Anything fn allocates lives in the graph's
     private memory pool, so the TMA descriptors and pointers baked into the captured launches stay valid."""
 
-    def __init__(self, fn, inputs, *, edge_index_key="edge_index", num_nodes=None, warmup=3, cache=None):
+    def __init__(self, fn, inputs, *, edge_index_key="edge_index", num_nodes=None, warmup=3, cache=None, static_graph=False):
+        """static_graph: the graph never changes (full-graph training, run_inductive.py:74-95 passes the same
+        data.edge_index every epoch): its CSR / CSC is built ONCE, outside the captured graph (with the degree classes and
+        the index check of the synchronous build), and replays skip the ingestion; passing a new edge_index then raises."""
         dev = next(iter(inputs.values())).device
         if dev.type != "cuda":
             raise ValueError("CapturedStep needs CUDA tensors")
@@ -42,6 +45,10 @@ class CapturedStep:
         self.num_nodes = int(num_nodes if num_nodes is not None else inputs["x"].shape[0]) if self.edge_index_key else None
         self.cache = cache if cache is not None else GLOBAL_CACHE
         self.csr = None
+        self.static_graph = bool(static_graph) and self.edge_index_key is not None
+        if self.static_graph:
+            ei = self.static[self.edge_index_key]
+            self.csr = self.cache.put(ei, self.num_nodes, build_csr(ei, self.num_nodes))
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -55,7 +62,7 @@ class CapturedStep:
         self.replays = 0
 
     def _run(self):
-        if self.edge_index_key is not None:
+        if self.edge_index_key is not None and not self.static_graph:
             ei = self.static[self.edge_index_key]
             self.csr = self.cache.put(ei, self.num_nodes, build_csr(ei, self.num_nodes, sync=False))
         return self.fn(**self.static)
@@ -63,6 +70,9 @@ class CapturedStep:
     def __call__(self, **inputs):
         """copy the given inputs into the static buffers (same shapes; omitted ones keep their content) and replay"""
         for k, v in inputs.items():
+            if self.static_graph and k == self.edge_index_key:
+                raise ValueError("this step was captured with static_graph=True: its CSR is built once; capture with "
+                                 "static_graph=False to feed a new edge_index per step")
             dst = self.static[k]
             if v.shape != dst.shape or v.dtype != dst.dtype:
                 raise ValueError(f"{k}: expected {tuple(dst.shape)} {dst.dtype}, got {tuple(v.shape)} {v.dtype} "
@@ -74,7 +84,7 @@ class CapturedStep:
 
     def check(self):
         """one device->host read: raise IndexError if the LAST edge_index held out-of-range indices"""
-        if self.csr is not None:
+        if self.csr is not None and not self.static_graph:
             self.csr.check()
         return self
 
@@ -118,7 +128,7 @@ def _data_inputs(data):
     return {k: getattr(data, k) for k in keys}
 
 
-def capture_train_step(model, optimizer, loss_fn, data, warmup=3):
+def capture_train_step(model, optimizer, loss_fn, data, warmup=3, static_graph=False):
     """One train step of run_inductive.py:75-85 / run_gnn_benchmark.py:60-66 — zero_grad, forward, loss, backward,
     optimizer step — as ONE graph launch.  model(data_like) takes a namespace with x / edge_index (/ batch / num_graphs);
     `optimizer` must be capturable (torch.optim.Adam(..., capturable=True)).  -> CapturedStep; call it with the fields of
@@ -135,10 +145,10 @@ def capture_train_step(model, optimizer, loss_fn, data, warmup=3):
         loss.backward()
         optimizer.step()
         return loss.detach()
-    return CapturedStep(fn, _data_inputs(data), warmup=warmup)
+    return CapturedStep(fn, _data_inputs(data), warmup=warmup, static_graph=static_graph)
 
 
-def capture_eval_forward(model, data, warmup=2):
+def capture_eval_forward(model, data, warmup=2, static_graph=False):
     """The per-epoch evaluation forward of run_inductive.py:87-95 as one graph launch.  The module must be in eval() mode
     when this is called; -> CapturedStep returning the static output tensor."""
     if model.training:
@@ -149,4 +159,4 @@ def capture_eval_forward(model, data, warmup=2):
         with torch.no_grad():
             return model(SimpleNamespace(x=t["x"], edge_index=t["edge_index"], batch=t.get("batch"), num_graphs=num_graphs))
     inputs = {k: v for k, v in _data_inputs(data).items() if k != "y"}
-    return CapturedStep(fn, inputs, warmup=warmup)
+    return CapturedStep(fn, inputs, warmup=warmup, static_graph=static_graph)

@@ -174,3 +174,31 @@ def test_readout_head_matches_torch_ops(shape, act_in):
     got = [out.detach(), xg.grad, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad]
     for name, a, b in zip(("logp", "g_x", "g_w1", "g_b1", "g_w2", "g_b2"), got, want):
         assert nerr(a.cpu().numpy(), b.numpy()) <= 1e-5, name
+
+
+def test_captured_step_with_a_static_graph_builds_the_csr_once():
+    """full-graph training (run_inductive.py:74-95): static_graph=True keeps the ingestion out of the replayed graph, gives
+    the same losses as the dynamic capture on the same inputs (lr = 0, eval-free model without dropout) and refuses a new
+    edge_index"""
+    from atmlgraphattentionnetworks_b200 import synth
+    from atmlgraphattentionnetworks_b200.capture import CapturedStep
+    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    d = _to_dev(synth.cora_shaped(num_nodes=700, undirected_pairs=1500, num_features=48))
+    torch.manual_seed(4)
+    model = GATStack([(48, 8, 4, True), (32, 7, 1, False)], dropout=0.0).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=0.0, fused=True, capturable=True)
+
+    def fn(x, edge_index, y):
+        opt.zero_grad(set_to_none=True)
+        loss = F.nll_loss(F.log_softmax(model(x, edge_index), dim=1), y)
+        loss.backward()
+        opt.step()
+        return loss.detach()
+    inputs = dict(x=d.x, edge_index=d.edge_index, y=d.y)
+    dyn, sta = CapturedStep(fn, inputs), CapturedStep(fn, inputs, static_graph=True)
+    a, b = float(dyn()), float(sta())
+    assert abs(a - b) <= 1e-6 * abs(a)
+    x2 = torch.randn_like(d.x)
+    assert abs(float(dyn(x=x2)) - float(sta(x=x2))) <= 1e-6 * abs(a) and abs(float(sta()) - b) > 1e-4
+    with pytest.raises(ValueError):
+        sta(edge_index=d.edge_index)
