@@ -210,6 +210,7 @@ class GATLayerFunction(torch.autograd.Function):
         # forward and its backward (optimizer.step, load_state_dict, ...) is an error, as it is in the reference
         ctx.param_versions = tuple(p._version for p in params)
         ctx.params = params
+        ctx.grad_store = fuse[7] if len(fuse) > 7 else None
         ctx.save_for_backward(x, w, a1, a2, bias, wh, s_src, s_dst, rowmax, rowsum, out if not heads_mode else o_heads,
                               x_split)
         ctx.mark_non_differentiable(out_amax)
@@ -234,13 +235,24 @@ class GATLayerFunction(torch.autograd.Function):
         gout = gout.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         g_t = torch.empty((n, dp), **f32)
-        g_bw = torch.empty(dp, **f32)
-        g_a1 = torch.empty(dp, **f32)
-        g_a2 = torch.empty(dp, **f32)
-        g_b1 = torch.empty(h, **f32)
-        g_b2 = torch.empty(h, **f32)
-        g_bias = torch.empty(d_out, **f32)
-        g_w = torch.empty((dp, f_in), **f32)
+        # parameter-gradient outputs: slices of the layer's PERSISTENT gradient arena when it has one (assign_grad_arena: one
+        # flat buffer per model => the data-parallel exchange is ONE all-reduce with no per-step bookkeeping) and no parameter
+        # already holds a gradient (the arena is overwritten, not accumulated: with an existing .grad — gradient
+        # accumulation, a layer used twice — fresh buffers are used and autograd adds them)
+        store = ctx.grad_store
+        if store is not None and store["flat"].device == dev and all(p.grad is None for p in ctx.params):
+            g_w, g_bw, g_a1, g_a2, g_b1, g_b2, g_bias = (store[k] for k in ("g_w", "g_bw", "g_a1", "g_a2", "g_b1", "g_b2", "g_bias"))
+            store["used"] = True
+        else:
+            if store is not None:
+                store["used"] = False
+            g_bw = torch.empty(dp, **f32)
+            g_a1 = torch.empty(dp, **f32)
+            g_a2 = torch.empty(dp, **f32)
+            g_b1 = torch.empty(h, **f32)
+            g_b2 = torch.empty(h, **f32)
+            g_bias = torch.empty(d_out, **f32)
+            g_w = torch.empty((dp, f_in), **f32)
         need_gx = ctx.needs_input_grad[0]
         g_x = torch.empty((n, f_in), **f32) if need_gx else None
         with torch.cuda.device(dev):
@@ -256,7 +268,10 @@ class GATLayerFunction(torch.autograd.Function):
             # the prep pass of THIS layer already ran in the consuming layer's gX GEMM (BoundaryLink): gout is G itself
             lo = ctx.link_out if (ctx.link_out is not None and ctx.link_out.done) else None
             if lo is not None:
-                g_bias = lo.g_bias
+                if store is not None and store.get("used"):
+                    g_bias.copy_(lo.g_bias)             # keep the arena slice as THE bias gradient
+                else:
+                    g_bias = lo.g_bias
             ea = _abi.EdgeBwdArgs(layer, graph.c_struct(), gout.data_ptr(), d_out,
                                   None if heads_mode else fwd_out.data_ptr(), d_out,
                                   fwd_out.data_ptr() if heads_mode else None, bias.data_ptr(),
@@ -327,6 +342,40 @@ class GATLayerFunction(torch.autograd.Function):
 _DEFAULT_GATHER_DTYPE = torch.bfloat16 if __import__("os").environ.get("B200GAT_GATHER_DTYPE", "") in ("bf16", "bfloat16") else torch.float32
 
 
+def grad_arena_numel(layer):
+    c, h, f = layer.output_channels, layer.num_heads, layer.input_channels
+    dp = h * ((c + 3) // 4 * 4)
+    d_out = h * c if layer.concat else c
+    return dp * f + 3 * dp + 2 * h + d_out
+
+
+def assign_grad_arena(module):
+    """Give every GraphAttentionLayer under `module` a slice of ONE persistent flat fp32 buffer for its packed parameter
+    gradients (g_w [Dp, F], g_bw / g_a1 / g_a2 [Dp], g_b1 / g_b2 [H], g_bias [D_out]).  The backward then writes into the same
+    memory every step, the per-head .grad tensors are views of it, and a data-parallel step exchanges the whole model's GAT
+    gradients with one all-reduce of the returned tensor (parallel.ArenaExchange).  -> the flat tensor."""
+    layers = [m for m in module.modules() if isinstance(m, GraphAttentionLayer)]
+    if not layers:
+        raise ValueError("no GraphAttentionLayer under this module")
+    dev = layers[0].bias.device
+    flat = torch.zeros(sum(grad_arena_numel(m) for m in layers), dtype=torch.float32, device=dev)
+    off = 0
+    for m in layers:
+        c, h, f = m.output_channels, m.num_heads, m.input_channels
+        dp = h * ((c + 3) // 4 * 4)
+        d_out = h * c if m.concat else c
+        store = {"flat": flat, "used": False}
+        for key, shape in (("g_w", (dp, f)), ("g_bw", (dp,)), ("g_a1", (dp,)), ("g_a2", (dp,)), ("g_b1", (h,)), ("g_b2", (h,)),
+                           ("g_bias", (d_out,))):
+            numel = 1
+            for v in shape:
+                numel *= v
+            store[key] = flat[off:off + numel].view(shape)
+            off += numel
+        m._grad_store = store
+    return flat
+
+
 def set_gather_dtype(module, dtype):
     """Switch every GraphAttentionLayer under `module` to fp32 (default) or bf16 storage of the gathered rows."""
     if dtype not in (torch.float32, torch.bfloat16):
@@ -367,6 +416,7 @@ class GraphAttentionLayer(torch.nn.Module):
         self.graph_cache = GLOBAL_CACHE
         self.mask_hook = None   # parity tests: callable (E', H) -> keep-multiplier [E', H] in ORIGINAL edge order
         self.last_link = None   # BoundaryLink of the last forward_fused(act_out=True) call, for the consuming layer
+        self._grad_store = None  # persistent gradient arena slices (assign_grad_arena)
         self._store = None      # persistent packed parameter storage (see _packed_storage)
         # the function applied to the edge logits before the softmax: (B200GAT_LOGIT_* code, negative slope); GAT.py:30
         self.logit_activation = (_abi.LOGIT_LEAKY_RELU, NEGATIVE_SLOPE)
@@ -491,7 +541,8 @@ class GraphAttentionLayer(torch.nn.Module):
         self.last_link = BoundaryLink() if act_out else None
         return GATLayerFunction.apply(x, self.bias, graph, geom, mask,
                                       (bool(act_in), bool(act_out), x_amax, tuple(self.logit_activation),
-                                       self.gather_dtype == torch.bfloat16, producer_link if act_in else None, self.last_link),
+                                       self.gather_dtype == torch.bfloat16, producer_link if act_in else None, self.last_link,
+                                       self._grad_store),
                                       packed, *self._head_parameters())
 
 

@@ -118,3 +118,31 @@ def all_reduce_packed_grads(params, group=None, weight=None):
         for b in bases:
             dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
     return len(bases)
+
+
+class ArenaExchange:
+    """Data-parallel gradient exchange of a model whose GAT layers write their parameter gradients into ONE persistent arena
+    (gat.assign_grad_arena): per step one in-place scale and ONE all-reduce of the arena — no per-step discovery of gradient
+    buffers — plus a coalesced all-reduce of the few parameters outside the GAT layers (GATNet's lin1 / lin2).  Falls back to
+    all_reduce_packed_grads for a step in which a layer could not use its arena slice (a parameter already held a gradient)."""
+
+    def __init__(self, module):
+        from .gat import GraphAttentionLayer, assign_grad_arena
+        self.module = module
+        self.layers = [m for m in module.modules() if isinstance(m, GraphAttentionLayer)]
+        self.arena = assign_grad_arena(module)
+        inside = {id(p) for m in self.layers for p in m.parameters()}
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.others = [p for p in self.params if id(p) not in inside]
+
+    def all_reduce(self, group=None, weight=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if not all(m._grad_store["used"] for m in self.layers):
+            all_reduce_packed_grads(self.params, group, weight)
+            return
+        scale = (1.0 / dist.get_world_size(group)) if weight is None else float(weight)
+        self.arena.mul_(scale)
+        dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=group)
+        if self.others:
+            all_reduce_packed_grads(self.others, group, weight)

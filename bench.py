@@ -331,7 +331,7 @@ class Runner:
         self.global_data = data
         mode = (f"row{world} (destination-row partition; input features replicated, so layer 1 exchanges nothing forward; all-gather of Wh (layers 2, 3) / gradient rows (all layers), reduce-scatter of g_s_dst, grad all-reduce)"
                 if self.partitioned else
-                f"dp{world} {self.dp} (independent graphs per rank, one-group NCCL all-reduce of the packed gradient buffers)")
+                f"dp{world} {self.dp} (independent graphs per rank, one NCCL all-reduce of the persistent gradient arena)")
         self.config, self.flush = describe_config(name, desc, data, spec, world, mode)
         if self.dp == "strong":
             data = synth.select_graphs(data, shard_graphs(data.num_graphs, world, rank))
@@ -356,6 +356,10 @@ class Runner:
         # copy; N > 1 (graph batches): those few buffers are all-reduced in ONE NCCL group (all_reduce_packed_grads).
         # The row-partitioned large graph keeps the flat bucket (its stage functions build gradients through torch ops).
         self.bucket = GradBucket(self.params) if self.partitioned else None
+        self.arena = None
+        if self.dp is not None:          # data parallel: the GAT layers' gradients live in one persistent arena => one all-reduce
+            from atmlgraphattentionnetworks_b200.parallel import ArenaExchange
+            self.arena = ArenaExchange(self.module)
         self.opt = torch.optim.Adam(self.params, lr=5e-3, weight_decay=5e-4, fused=True,   # run_inductive.py:18-19,65
                                     capturable=capturable)
         self.part = None
@@ -392,7 +396,9 @@ class Runner:
         else:
             loss = self.loss_fn(self.model(x, ei), y)
             loss.backward()
-            if self.env.world > 1:
+            if self.arena is not None:
+                self.arena.all_reduce()
+            elif self.env.world > 1:
                 all_reduce_packed_grads(self.params)
         return loss
 
@@ -832,7 +838,7 @@ def reference_arm(args):
         sample = args.cpu_sample_graphs
     data, spec, _, desc = make_workload(name, 0, heads=args.heads)
     world = max(args.gpus, 1)
-    mode = f"dp{world} weak (independent graphs per rank, one-group NCCL all-reduce of the packed gradient buffers)"
+    mode = f"dp{world} weak (independent graphs per rank, one NCCL all-reduce of the persistent gradient arena)"
     config, _ = describe_config(name, desc, data, spec, world, mode)
     del data
     val, dt, sdesc, kind = cpu_reference_leg(name, args.steps, args.warmup, sample, heads=args.heads)

@@ -216,3 +216,35 @@ def test_two_shards_through_the_packed_gradient_exchange_match_the_whole_batch()
         total += g_r
     assert abs(total_loss - want_loss) <= 1e-5 * abs(want_loss)
     assert float((total - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_gradient_arena_holds_the_same_gradients_in_one_flat_buffer():
+    """gat.assign_grad_arena: the layers' parameter gradients land in ONE persistent flat buffer (what the data-parallel
+    exchange all-reduces in one call); values equal the arena-less backward; a second backward with gradients still in
+    place accumulates correctly (fresh buffers, autograd adds)."""
+    from atmlgraphattentionnetworks_b200 import synth
+    from atmlgraphattentionnetworks_b200.gat import assign_grad_arena
+    from atmlgraphattentionnetworks_b200.gatnet import GATStack
+    import torch.nn.functional as F
+    data = synth.ppi_shaped(keep_graphs=3)
+    spec = [(50, 64, 4, True), (256, 8, 8, True), (64, 121, 6, False)]
+    torch.manual_seed(0)
+    model = GATStack(spec, dropout=0.0).to(DEV)
+    params = list(model.parameters())
+    x, ei, y = data.x.to(DEV), data.edge_index.to(DEV), data.y.to(DEV)
+
+    def backward():
+        F.binary_cross_entropy_with_logits(model(x, ei), y).backward()
+        return torch.cat([p.grad.flatten() for p in params]).clone()
+    want = backward()
+    for p in params:
+        p.grad = None
+    arena = assign_grad_arena(model)
+    got = backward()
+    assert torch.equal(got, want) or float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * 4
+    assert all(lo <= p.grad.data_ptr() < hi for p in params)          # every .grad is a view of the arena
+    assert all(m._grad_store["used"] for m in model.convs)
+    twice = backward()                                                   # .grad still set: accumulate, do not overwrite
+    assert float((twice - 2 * want).abs().max()) <= 2e-6 * float(want.abs().max())
+    assert not any(m._grad_store["used"] for m in model.convs)
