@@ -336,7 +336,9 @@ class GATLayerFunction(torch.autograd.Function):
         per_head = []
         for k in range(h):
             per_head += [gw3[k, :c], gbw2[k, :c], ga12[k:k + 1, :c], g_b1[k:k + 1], ga22[k:k + 1, :c], g_b2[k:k + 1]]
-        return (g_x, g_bias, None, None, None, None, None, *per_head)
+        # (a FRESH alias of g_bias: autograd adopts an incoming gradient as .grad without a copy only if nobody else holds
+        #  that tensor object — the arena's dict does hold the slice itself)
+        return (g_x, g_bias.view(-1), None, None, None, None, None, *per_head)
 
 
 _DEFAULT_GATHER_DTYPE = torch.bfloat16 if __import__("os").environ.get("B200GAT_GATHER_DTYPE", "") in ("bf16", "bfloat16") else torch.float32
