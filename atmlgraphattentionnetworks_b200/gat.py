@@ -97,6 +97,20 @@ def _queue_join(dev, main, side):
         join()
 
 
+_ws_cache = {}
+
+
+def _ws_bytes(kind, fn, layer, n):
+    """workspace / split sizes depend on (geometry, N) only: one ctypes query per distinct pair instead of one per call"""
+    key = (kind, layer.in_channels, layer.out_channels, layer.heads, layer.concat, n)
+    v = _ws_cache.get(key)
+    if v is None:
+        v = _ws_cache[key] = int(fn(ctypes.byref(layer), n))
+        if len(_ws_cache) > 4096:
+            _ws_cache.clear()
+    return v
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -173,14 +187,14 @@ class GATLayerFunction(torch.autograd.Function):
         rowmax = torch.empty((n, h), **f32)
         rowsum = torch.empty((n, h), **f32)
         o_heads = torch.empty((n, dp), **f32) if heads_mode else None
-        out_amax = torch.zeros(1, dtype=torch.int32, device=dev)
+        out_amax = torch.empty(1, dtype=torch.int32, device=dev)      # zeroed by b200gat_edge_fwd itself
         wh16 = torch.empty((n, dp), dtype=torch.bfloat16, device=dev) if rows16 else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            ws_bytes = int(lib.b200gat_proj_fwd_workspace_bytes(ctypes.byref(layer), n))
+            ws_bytes = _ws_bytes("pf", lib.b200gat_proj_fwd_workspace_bytes, layer, n)
             ws = _workspace(ws_bytes, dev)
             # the tensor-core operand split of x is kept for the backward's gW GEMM when a backward will run
-            split_bytes = int(lib.b200gat_proj_split_bytes(ctypes.byref(layer), n)) if any(ctx.needs_input_grad) else 0
+            split_bytes = _ws_bytes("ps", lib.b200gat_proj_split_bytes, layer, n) if any(ctx.needs_input_grad) else 0
             x_split = _workspace(split_bytes, dev) if split_bytes else None
             pa = _abi.ProjFwdArgs(layer, n, x.data_ptr(), x.stride(0) if n else f_in, w.data_ptr(), bw.data_ptr(),
                                   a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), wh.data_ptr(),
@@ -257,10 +271,10 @@ class GATLayerFunction(torch.autograd.Function):
         g_x = torch.empty((n, f_in), **f32) if need_gx else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            ws_bytes = int(lib.b200gat_edge_bwd_workspace_bytes(ctypes.byref(layer), n))
+            ws_bytes = _ws_bytes("eb", lib.b200gat_edge_bwd_workspace_bytes, layer, n)
             ws = _workspace(ws_bytes, dev)
             # gT goes straight into the tensor-core operand format when the projection backward runs there
-            gs_bytes = int(lib.b200gat_edge_bwd_split_bytes(ctypes.byref(layer), n))
+            gs_bytes = _ws_bytes("es", lib.b200gat_edge_bwd_split_bytes, layer, n)
             g_split = _workspace(gs_bytes, dev) if gs_bytes else None
             # the across-heads softmax logits couple the heads of an edge in the backward: the one variant with a per-edge
             # scratch buffer ([E', H] floats, include/b200gat.h)
@@ -283,7 +297,7 @@ class GATLayerFunction(torch.autograd.Function):
                                   _abi.dropout_struct(ctx.drop), _ptr(scratch), scratch.numel() if scratch is not None else 0,
                                   1 if ctx.rows16 else 0, lo.rowrec.data_ptr() if lo is not None else None)
             _call("b200gat_edge_bwd", lib.b200gat_edge_bwd, ea, stream, ctx.geom)
-            ws2_bytes = int(lib.b200gat_proj_bwd_workspace_bytes(ctypes.byref(layer), n))
+            ws2_bytes = _ws_bytes("pb", lib.b200gat_proj_bwd_workspace_bytes, layer, n)
 
             # the PRODUCING layer's prep pass rides in this layer's gX GEMM when the pair qualifies (BoundaryLink)
             li = ctx.link_in
