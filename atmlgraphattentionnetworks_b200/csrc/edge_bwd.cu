@@ -273,6 +273,84 @@ struct PrepMeanParams {
   float* g_bias;                      // [C], zero-initialised, accumulated atomically
 };
 
+// ---- the same for head widths up to 128 channels (Cp / 4 <= 32 float4 slots: every mean layer of the BASELINE models — 6 x 121,
+// 4 x 47, 8 x 3 ...): a lane GROUP of G = pow2ceil(Cp / 4) lanes per destination row and ONE slot per lane, 32 / G rows per warp,
+// and the H per-head dot products reduced together.  (ncu on the 2.4 M-node graph's 4 x 47 layer, warp-per-row form: 12 of 32
+// lanes busy, 1 TB/s = 13 % of DRAM peak, 2.9 ms.)
+template <int G>
+__global__ void __launch_bounds__(256) bwd_prep_mean_narrow_kernel(const PrepMeanParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int Q = p.Cp >> 2, c = 4 * gl;
+  const bool live = gl < Q;
+  const bool vec_in = (p.C % 4 == 0) && (p.ldgo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.gout) & 15u) == 0);
+  const float gscale = 1.f / static_cast<float>(p.H);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t base = warp * RPW; base < p.N; base += nwarps * RPW) {
+    const int64_t i = base + gi;
+    const bool valid = live && i < p.N;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float* g = p.gout + i * p.ldgo;
+      if (vec_in) gv = ldg4(g + c);
+      else {
+        if (c + 0 < p.C) gv.x = __ldg(g + c + 0);
+        if (c + 1 < p.C) gv.y = __ldg(g + c + 1);
+        if (c + 2 < p.C) gv.z = __ldg(g + c + 2);
+        if (c + 3 < p.C) gv.w = __ldg(g + c + 3);
+      }
+      cs.x += gv.x; cs.y += gv.y; cs.z += gv.z; cs.w += gv.w;
+      gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
+      if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + i * int64_t(p.Cp) + c) = pack_bf16x4(gv.x, gv.y, gv.z, gv.w);
+      else *reinterpret_cast<float4*>(p.gp + i * int64_t(p.Cp) + c) = gv;
+    }
+    const float* o = p.o_heads + (i < p.N ? i : 0) * int64_t(p.H) * p.Cp + c;
+    for (int h0 = 0; h0 < p.H; h0 += 4) {                  // four heads' loads in flight together
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        d[u] = 0.f;
+        if (valid && h0 + u < p.H) {
+          const float4 ov = ldg4(o + (h0 + u) * p.Cp);
+          d[u] = gv.x * ov.x + gv.y * ov.y + gv.z * ov.z + gv.w * ov.w;
+        }
+      }
+#pragma unroll
+      for (int o2 = G >> 1; o2 > 0; o2 >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o2, G);
+      }
+      if (gl < 4 && h0 + gl < p.H && i < p.N) {            // lane u of the group writes head h0 + u's record
+        const float dv = gl == 0 ? d[0] : (gl == 1 ? d[1] : (gl == 2 ? d[2] : d[3]));
+        const int64_t item = i * p.H + h0 + gl;
+        p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), dv);
+      }
+    }
+  }
+  // g_bias column sums: the RPW groups of a warp, the 8 warps of the CTA, one atomic per column per CTA
+#pragma unroll
+  for (int o2 = G; o2 < 32; o2 <<= 1) {
+    cs.x += __shfl_xor_sync(FULL, cs.x, o2); cs.y += __shfl_xor_sync(FULL, cs.y, o2);
+    cs.z += __shfl_xor_sync(FULL, cs.z, o2); cs.w += __shfl_xor_sync(FULL, cs.w, o2);
+  }
+  __shared__ float4 red[8][G];
+  if (lane < G) red[threadIdx.x >> 5][lane] = cs;
+  __syncthreads();
+  if (threadIdx.x < G && threadIdx.x < Q) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += red[w][threadIdx.x].x; t.y += red[w][threadIdx.x].y; t.z += red[w][threadIdx.x].z; t.w += red[w][threadIdx.x].w; }
+    const int cc = 4 * threadIdx.x;
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cc + u < p.C) atomicAdd(p.g_bias + cc + u, tv[u]);
+  }
+}
+
 __global__ void __launch_bounds__(256) bwd_prep_mean_rows_kernel(const PrepMeanParams p) {
   constexpr int T = 4;                                    // float4 slots per lane: Cp <= 512
   const int lane = threadIdx.x & 31;
@@ -1247,8 +1325,19 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
     pm.N = rows; pm.H = g.H; pm.C = g.C; pm.Cp = g.Cp;
     pm.gout = gout; pm.ldgo = ldgo; pm.o_heads = o_heads; pm.s_dst = s_dst; pm.rowmax = rowmax; pm.rowsum = rowsum;
     pm.gp = gp; pm.gp16 = gp16 ? 1 : 0; pm.rowrec = rowrec; pm.g_bias = g_bias;
-    const int64_t want = ceil_div(rows, 8);
     const int64_t cap_rows = int64_t(sm_count()) * 8;
+    const int Qm = g.Cp / 4;
+    if (Qm <= 32) {                                        // lane group per row
+      const int G = Qm <= 4 ? 4 : (Qm <= 8 ? 8 : (Qm <= 16 ? 16 : 32));
+      const int64_t want = ceil_div(rows, int64_t(8) * (32 / G) * 2);
+      const int blocks = static_cast<int>(want < cap_rows ? (want > 0 ? want : 1) : cap_rows);
+      if (G == 4) bwd_prep_mean_narrow_kernel<4><<<blocks, 256, 0, stream>>>(pm);
+      else if (G == 8) bwd_prep_mean_narrow_kernel<8><<<blocks, 256, 0, stream>>>(pm);
+      else if (G == 16) bwd_prep_mean_narrow_kernel<16><<<blocks, 256, 0, stream>>>(pm);
+      else bwd_prep_mean_narrow_kernel<32><<<blocks, 256, 0, stream>>>(pm);
+      return check_launch("bwd_prep_mean_narrow_kernel");
+    }
+    const int64_t want = ceil_div(rows, 8);
     bwd_prep_mean_rows_kernel<<<static_cast<int>(want < cap_rows ? want : cap_rows), 256, 0, stream>>>(pm);
     return check_launch("bwd_prep_mean_rows_kernel");
   }
