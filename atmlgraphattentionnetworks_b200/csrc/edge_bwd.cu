@@ -1455,7 +1455,7 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
       if (ce != cudaSuccess) return fail(static_cast<int>(ce), "edge_bwd: memset: %s", cudaGetErrorString(ce));
     }
   }
-  const int tx_shift = g.Dp <= 64 ? 4 : (g.Dp <= 256 ? 6 : 8);   // TX = 16 / 64 / 256 column groups per CTA
+  const int tx_shift = g.Dp <= 64 ? 4 : (g.Dp <= 256 ? 6 : (g.Dp <= 512 ? 7 : 8));   // TX = 16 / 64 / 128 / 256 column groups per CTA
   const int TX = 1 << tx_shift, RY = 256 >> tx_shift;
   const int xblocks = static_cast<int>(ceil_div(g.Dp, 4 * TX));
   int64_t ysplit = ceil_div(cap, xblocks);
@@ -1466,10 +1466,12 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
   if (gsplit) {
     if (tx_shift == 4) bwd_finish_kernel<true, 4><<<grid, 256, 0, stream>>>(f);
     else if (tx_shift == 6) bwd_finish_kernel<true, 6><<<grid, 256, 0, stream>>>(f);
+    else if (tx_shift == 7) bwd_finish_kernel<true, 7><<<grid, 256, 0, stream>>>(f);
     else bwd_finish_kernel<true, 8><<<grid, 256, 0, stream>>>(f);
   } else {
     if (tx_shift == 4) bwd_finish_kernel<false, 4><<<grid, 256, 0, stream>>>(f);
     else if (tx_shift == 6) bwd_finish_kernel<false, 6><<<grid, 256, 0, stream>>>(f);
+    else if (tx_shift == 7) bwd_finish_kernel<false, 7><<<grid, 256, 0, stream>>>(f);
     else bwd_finish_kernel<false, 8><<<grid, 256, 0, stream>>>(f);
   }
   return check_launch("bwd_finish_kernel");
