@@ -1458,7 +1458,9 @@ static int run_finish(const b200gat_layer& L, int64_t rows, const float* wh, con
   const int tx_shift = g.Dp <= 64 ? 4 : (g.Dp <= 256 ? 6 : (g.Dp <= 512 ? 7 : 8));   // TX = 16 / 64 / 128 / 256 column groups per CTA
   const int TX = 1 << tx_shift, RY = 256 >> tx_shift;
   const int xblocks = static_cast<int>(ceil_div(g.Dp, 4 * TX));
-  int64_t ysplit = ceil_div(cap, xblocks);
+  // one resident wave (4 CTAs / SM): every CTA ends in a column-sum atomic tail, so a second wave only adds tail
+  // (PPI step 5.12 -> 5.05 ms against 8 CTAs / SM; 2 and 16 per SM are both slower; the 2.4 M-node graph is unchanged)
+  int64_t ysplit = ceil_div(int64_t(sm_count()) * 4, xblocks);
   const int64_t max_y = ceil_div(rows, int64_t(16) * RY);      // at least 4 batches of 4 rows per thread
   if (ysplit > max_y) ysplit = max_y;
   if (ysplit < 1) ysplit = 1;
