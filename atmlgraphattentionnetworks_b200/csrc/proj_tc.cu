@@ -694,8 +694,14 @@ split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t co
   if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = 1.f / s;
   const int64_t groups = ldp >> 3, total = rows * groups;
   const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = t / groups, c0 = (t - r * groups) << 3;
+  // (row, column group) of item t are stepped incrementally: the 64-bit division per item made this pass issue-bound
+  // (84 % issue slots busy at half the copy rate, ncu)
+  const int64_t nth = int64_t(gridDim.x) * blockDim.x, t_first = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t dr = nth / groups, dg = nth - dr * groups;
+  int64_t r = t_first / groups, g = t_first - r * groups;
+  for (int64_t t = t_first; t < total; t += nth, r += dr, g += dg) {
+    if (g >= groups) { g -= groups; ++r; }
+    const int64_t c0 = g << 3;
     float v[8];
     const float* p = src + r * ld + c0;
     if (vec && c0 + 8 <= cols) {
