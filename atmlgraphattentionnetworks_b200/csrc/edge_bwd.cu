@@ -105,99 +105,104 @@ struct PrepRowsParams {
   float* g_bias;                      // [D], zero-initialised, accumulated atomically
 };
 
-// (256, 2): 128 registers.  Measured with (256, 3): 80 registers + 260 bytes of spills, 154 -> 202 us per PPI layer.
-template <bool ACT>
-__global__ void __launch_bounds__(256, 2) bwd_prep_rows_kernel(const PrepRowsParams p) {
+// ---- the same pass laid out like bwd_finish_kernel: one thread per FOUR adjacent columns (TX = pow2ceil(D / 4) column
+// groups x RY = 256 / TX row lanes), batches of RB rows per thread with all 2 * RB 128-bit loads issued before the first
+// store, row batches interleaved over the CTAs (one moving window of rows, DRAM pages walked in address order).
+// ~64 registers -> 4 CTAs / SM (a warp-per-row layout holds a row's 8 float4 x 2 arrays + 8 column-sum float4 per lane:
+// 126 registers, 2 CTAs / SM, 37 % issue slots, 4.3 TB/s measured; this one: 157 -> 121 us per PPI layer).  Heads of >= 128 channels span whole warps: warp sums
+// go through a double-buffered shared array (ONE barrier per batch) and the first warp writes the row records; narrower
+// heads (power-of-two widths) are reduced by segmented shuffles and written by their lead lanes.
+template <bool ACT, int TXS>
+__global__ void __launch_bounds__(256, 4) bwd_prep_rows_wide_kernel(const PrepRowsParams p) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int T = 8;                                    // float4 slots per lane: D <= 4 * 32 * 8 = 1024
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  constexpr int TX = 1 << TXS, RY = 256 >> TXS, RB = 4, WPR = TX / 32;    // WPR: warps per row
+  const int tx = threadIdx.x & (TX - 1), ry = threadIdx.x >> TXS, lane = threadIdx.x & 31;
   const int Q = p.C >> 2, DQ = p.D >> 2;
-  float4 cs[T];
+  const bool active = tx < DQ;
+  const int c = 4 * (active ? tx : 0);
+  const int h = c / p.C;
+  const float4 bv = ldg4(p.bias + c);
+  const bool wide_heads = Q >= 32;                        // (Q % 32 == 0: checked by the host)
+  const int per = Q >> 5;                                 // warps per head (wide heads)
+  __shared__ float red[2][RB][8];
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the writer threads of the wide-head form: thread w < RY * RB * H  <->  (row lane, batch slot, head)
+  const int w_h = threadIdx.x % p.H, w_u = (threadIdx.x / p.H) % RB, w_ry = threadIdx.x / (p.H * RB);
+  const bool writer = wide_heads && w_ry < RY;
+  int buf = 0;
+  for (int64_t base = int64_t(blockIdx.x) * (RY * RB); base < p.N; base += int64_t(gridDim.x) * (RY * RB), buf ^= 1) {
+    const int64_t rb = base + ry * RB;
+    float4 gv[RB], ov[RB];
 #pragma unroll
-  for (int t = 0; t < T; ++t) cs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = warp; i < p.N; i += nwarps) {
-    const float* g = p.gout + i * p.ldgo;
-    const float* o = p.out + i * p.ldo;
-    float pd[T];
-    // two halves of T/2 slots: 8 128-bit loads in flight per lane, half the live registers of a single pass
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 gv[T / 2], ov[T / 2];
-#pragma unroll
-      for (int u = 0; u < T / 2; ++u) {
-        const int q = lane + 32 * (half * (T / 2) + u);
-        if (q < DQ) {
-          gv[u] = ldg4(g + 4 * q);
-          ov[u] = ldg4(o + 4 * q);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < T / 2; ++u) {
-        const int t = half * (T / 2) + u;
-        const int q = lane + 32 * t;
-        pd[t] = 0.f;
-        if (q < DQ) {
-          const float4 bv = ldg4(p.bias + 4 * q);
-          if (ACT) {
-            gv[u].x *= elu_grad(ov[u].x); gv[u].y *= elu_grad(ov[u].y);
-            gv[u].z *= elu_grad(ov[u].z); gv[u].w *= elu_grad(ov[u].w);
-          }
-          if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + i * int64_t(p.D) + 4 * q) = pack_bf16x4(gv[u].x, gv[u].y, gv[u].z, gv[u].w);
-          else if (ACT) *reinterpret_cast<float4*>(p.gp + i * int64_t(p.D) + 4 * q) = gv[u];
-          cs[t].x += gv[u].x; cs[t].y += gv[u].y; cs[t].z += gv[u].z; cs[t].w += gv[u].w;
-          pd[t] = gv[u].x * (ov[u].x - bv.x) + gv[u].y * (ov[u].y - bv.y) + gv[u].z * (ov[u].z - bv.z) + gv[u].w * (ov[u].w - bv.w);
-        }
-      }
+    for (int u = 0; u < RB; ++u) {
+      const int64_t r = rb + u < p.N ? rb + u : p.N - 1;    // tail rows re-read the last row and are not stored
+      gv[u] = ldg4(p.gout + r * p.ldgo + c);
+      ov[u] = ldg4(p.out + r * p.ldo + c);
     }
-    if (Q >= 32) {                                        // a head spans Q/32 whole slots
-      const int per = Q >> 5;
-      for (int h = 0; h < p.H; ++h) {
+    float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t w_item = (base + w_ry * RB + w_u) * p.H + w_h;
+    const bool w_live = writer && base + w_ry * RB + w_u < p.N;
+    if (w_live) {                                           // in flight together with the row loads
+      rec.x = __ldg(p.s_dst + w_item); rec.y = __ldg(p.rowmax + w_item); rec.z = __ldg(p.rowsum + w_item);
+    }
+    float pd[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      pd[u] = 0.f;
+      if (!active || rb + u >= p.N) continue;
+      const int64_t r = rb + u;
+      if (ACT) {
+        gv[u].x *= elu_grad(ov[u].x); gv[u].y *= elu_grad(ov[u].y);
+        gv[u].z *= elu_grad(ov[u].z); gv[u].w *= elu_grad(ov[u].w);
+      }
+      if (p.gp16) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.gp) + r * int64_t(p.D) + c) = pack_bf16x4(gv[u].x, gv[u].y, gv[u].z, gv[u].w);
+      else if (ACT) *reinterpret_cast<float4*>(p.gp + r * int64_t(p.D) + c) = gv[u];
+      cs.x += gv[u].x; cs.y += gv[u].y; cs.z += gv[u].z; cs.w += gv[u].w;
+      pd[u] = gv[u].x * (ov[u].x - bv.x) + gv[u].y * (ov[u].y - bv.y) + gv[u].z * (ov[u].z - bv.z) + gv[u].w * (ov[u].w - bv.w);
+    }
+    if (wide_heads) {
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) pd[u] += __shfl_xor_sync(FULL, pd[u], o2);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) red[buf][u][threadIdx.x >> 5] = pd[u];
+      }
+      __syncthreads();
+      if (w_live) {
         float d = 0.f;
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-          if (t >= h * per && t < (h + 1) * per) d += pd[t];
-        d = group_sum<32>(d);
-        if (lane == 0) {
-          const int64_t item = i * p.H + h;
-          p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
-        }
+        for (int k = 0; k < per; ++k) d += red[buf][w_u][w_ry * WPR + w_h * per + k];
+        p.rowrec[w_item] = make_float4(rec.x, rec.y, 1.f / (rec.z + 1e-16f), d);
       }
-    } else {                                              // 32/Q heads per slot: width-Q segmented sums
-      const int hps = 32 / Q;
+    } else {                                                // Q a power of two < 32: 32 / Q heads per warp
+      for (int o2 = Q >> 1; o2 > 0; o2 >>= 1) {
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        if (32 * t >= DQ) break;
-        float d = pd[t];
-        for (int o2 = Q >> 1; o2 > 0; o2 >>= 1) d += __shfl_xor_sync(FULL, d, o2);
-        const int h = t * hps + lane / Q;
-        if ((lane & (Q - 1)) == 0 && h < p.H) {
-          const int64_t item = i * p.H + h;
-          p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), d);
+        for (int u = 0; u < RB; ++u) pd[u] += __shfl_xor_sync(FULL, pd[u], o2);
+      }
+      if (active && (lane & (Q - 1)) == 0) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          if (rb + u >= p.N) break;
+          const int64_t item = (rb + u) * p.H + h;
+          p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), pd[u]);
         }
       }
     }
   }
-  // column sums: combine the 8 warps of the CTA through shared memory, then one atomic per column per CTA
-  __shared__ float4 red[8][32];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    if (32 * t >= DQ) break;
+  // column sums: the RY row lanes of the CTA through shared memory, then one atomic per column per CTA
+  if constexpr (RY > 1) {
+    __shared__ float4 csred[RY][TX];
+    csred[ry][tx] = cs;
     __syncthreads();
-    red[threadIdx.x >> 5][lane] = cs[t];
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float4 s = red[0][lane];
+    if (ry != 0) return;
 #pragma unroll
-      for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
-      const int q = lane + 32 * t;
-      if (q < DQ) {
-        atomicAdd(p.g_bias + 4 * q + 0, s.x); atomicAdd(p.g_bias + 4 * q + 1, s.y);
-        atomicAdd(p.g_bias + 4 * q + 2, s.z); atomicAdd(p.g_bias + 4 * q + 3, s.w);
-      }
-    }
+    for (int y = 1; y < RY; ++y) { const float4 t = csred[y][tx]; cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w; }
   }
+  if (!active) return;
+  atomicAdd(p.g_bias + c + 0, cs.x); atomicAdd(p.g_bias + c + 1, cs.y);
+  atomicAdd(p.g_bias + c + 2, cs.z); atomicAdd(p.g_bias + c + 3, cs.w);
 }
 
 // ---- the same for NARROW concat-like layers (D_out <= 128: the 8 x 8 layers of GATNet, the heads sweep's 1 x 64 / 2 x 64):
@@ -1302,9 +1307,7 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
     pr.N = rows; pr.H = g.H; pr.C = g.C; pr.D = static_cast<int>(g.d_out);
     pr.gout = gout; pr.ldgo = ldgo; pr.out = out; pr.ldo = ldo; pr.bias = bias;
     pr.s_dst = s_dst; pr.rowmax = rowmax; pr.rowsum = rowsum; pr.gp = gp; pr.gp16 = gp16 ? 1 : 0; pr.rowrec = rowrec; pr.g_bias = g_bias;
-    const int64_t want = ceil_div(rows, 8);
     const int64_t cap_rows = int64_t(sm_count()) * 4;       // few, fat CTAs: one g_bias atomic per column per CTA
-    const int blocks = static_cast<int>(want < cap_rows ? want : cap_rows);
     const int DQ = static_cast<int>(g.d_out / 4);
     if (DQ <= 32 && (Q & (Q - 1)) == 0) {                   // narrow rows: a lane group per row instead of a warp
       const int64_t rows_per_cta = DQ <= 4 ? 64 : (DQ <= 8 ? 32 : (DQ <= 16 ? 16 : 8));
@@ -1316,9 +1319,13 @@ static int run_prep(const b200gat_layer& L, int64_t rows, const float* gout, int
       else launch_prep_narrow<32>(pr, act != 0, blocks_n, stream);
       return check_launch("bwd_prep_rows_narrow_kernel");
     }
-    if (act) bwd_prep_rows_kernel<true><<<blocks, 256, 0, stream>>>(pr);
-    else bwd_prep_rows_kernel<false><<<blocks, 256, 0, stream>>>(pr);
-    return check_launch("bwd_prep_rows_kernel");
+    const int txs = DQ <= 64 ? 6 : (DQ <= 128 ? 7 : 8);
+    const int64_t want_w = ceil_div(rows, int64_t(256 >> txs) * 4 * 4);     // at least 4 batches per thread
+    const int blocks_w = static_cast<int>(want_w < cap_rows ? (want_w > 0 ? want_w : 1) : cap_rows);
+    if (txs == 6) { if (act) bwd_prep_rows_wide_kernel<true, 6><<<blocks_w, 256, 0, stream>>>(pr); else bwd_prep_rows_wide_kernel<false, 6><<<blocks_w, 256, 0, stream>>>(pr); }
+    else if (txs == 7) { if (act) bwd_prep_rows_wide_kernel<true, 7><<<blocks_w, 256, 0, stream>>>(pr); else bwd_prep_rows_wide_kernel<false, 7><<<blocks_w, 256, 0, stream>>>(pr); }
+    else { if (act) bwd_prep_rows_wide_kernel<true, 8><<<blocks_w, 256, 0, stream>>>(pr); else bwd_prep_rows_wide_kernel<false, 8><<<blocks_w, 256, 0, stream>>>(pr); }
+    return check_launch("bwd_prep_rows_wide_kernel");
   }
   if (!g.concat_like && gp && aligned16(o_heads) && aligned16(gp)) {
     PrepMeanParams pm;

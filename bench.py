@@ -107,9 +107,9 @@ def describe_config(name, desc, data, spec, world, mode):
             "edges_per_layer_incl_self_loops": ep, "layers": len(spec),
             "step": "zero_grad + fwd + loss + bwd + grad all-reduce (N > 1) + fused Adam (lr 5e-3, wd 5e-4)",
             "parallelism": mode if world > 1 else "single GPU",
-            "l2": (f"per-step working set {ws / 1e6:.0f} MB < 2 x L2 (126 MB): L2 flushed (256 MB memset) before every timed step, "
+            "l2": (f"per-step algorithmic traffic {ws / 1e6:.0f} MB < 2 x L2 (126 MB): L2 flushed (256 MB memset) before every timed step, "
                    "steps timed one by one with CUDA events" if flush else
-                   f"inputs larger than L2 (per-step working set {ws / 1e9:.2f} GB vs 126 MB L2); no explicit flush")}, flush
+                   f"inputs larger than L2 (per-step algorithmic traffic {ws / 1e9:.2f} GB vs 126 MB L2); no explicit flush")}, flush
 
 
 # ------------------------------------------------------------------------------------ algorithmic bytes
