@@ -59,6 +59,93 @@ logits_kernel(const float* __restrict__ wh, const float* __restrict__ a1, const 
   }
 }
 
+// ---- heads of >= 9 float4 slots (c_pad > 32): a lane group per HEAD, walking the nodes
+template <int G>
+__global__ void __launch_bounds__(256, 3)
+logits_head_kernel(const float* __restrict__ wh, const float* __restrict__ a1, const float* __restrict__ a2,
+              const float* __restrict__ b1, const float* __restrict__ b2, float* __restrict__ s_src,
+              float* __restrict__ s_dst, int64_t N, int H, int Cp) {
+  constexpr int GPW = 32 / G;
+  constexpr int U = 8;                                     // nodes per lane group and trip: their loads are all in flight
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1);  // together (one item per trip left the kernel latency-bound)
+  // A lane group keeps ONE head for the whole kernel (its slices of a1 / a2 stay in registers: re-loading them per item
+  // was two L1 loads per row load, 2.4 TB/s on the 6 x 121 PPI layer) and walks the nodes; adjacent groups take adjacent
+  // heads of the same node, so the grid still streams one window of consecutive rows.
+  const int64_t group = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = (int64_t(gridDim.x) * blockDim.x) / G;
+  const int64_t per_head = ngroups / H;                    // groups per head (the host launches >= H groups)
+  if (group >= per_head * H) return;                       // < H left-over groups idle (whole groups: shuffles stay group-local)
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+  const int h = static_cast<int>(group % H);
+  const int Q = Cp >> 2;
+  const float bb1 = __ldg(b1 + h), bb2 = __ldg(b2 + h);
+  if (Q <= G) {                                            // the usual case: one 128-bit slot per lane
+    const bool on = gl < Q;
+    const int c = 4 * (on ? gl : 0);
+    const float4 p = ldg4(a1 + h * Cp + c), r = ldg4(a2 + h * Cp + c);
+    for (int64_t n0 = (group / H) * U; n0 < N; n0 += per_head * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t n = n0 + u < N ? n0 + u : N - 1;       // tail: re-read the last node, never stored
+        v[u] = ldg4(wh + (n * H + h) * Cp + c);              // rows are [N, H, Cp]
+      }
+      float d1[U], d2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        d1[u] = on ? v[u].x * p.x + v[u].y * p.y + v[u].z * p.z + v[u].w * p.w : 0.f;
+        d2[u] = on ? v[u].x * r.x + v[u].y * r.y + v[u].z * r.z + v[u].w * r.w : 0.f;
+      }
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          d1[u] += __shfl_xor_sync(gmask, d1[u], o, G);
+          d2[u] += __shfl_xor_sync(gmask, d2[u], o, G);
+        }
+      }
+      if (gl < U && n0 + gl < N) {                            // lane u of the group writes node n0 + u (G >= U: see the host)
+        float s1 = d1[0], s2 = d2[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u)
+          if (gl == u) { s1 = d1[u]; s2 = d2[u]; }
+        s_src[(n0 + gl) * H + h] = s1 + bb1;
+        s_dst[(n0 + gl) * H + h] = s2 + bb2;
+      }
+    }
+    return;
+  }
+  // wide heads (Cp > 128, G = 32): several slots per lane, U / 2 nodes in flight
+  constexpr int UW = U / 2;
+  for (int64_t n0 = (group / H) * UW; n0 < N; n0 += per_head * UW) {
+    float d1[UW], d2[UW];
+#pragma unroll
+    for (int u = 0; u < UW; ++u) d1[u] = d2[u] = 0.f;
+    for (int q = gl; q < Q; q += G) {
+      const float4 p = ldg4(a1 + h * Cp + 4 * q), r = ldg4(a2 + h * Cp + 4 * q);
+      float4 v[UW];
+#pragma unroll
+      for (int u = 0; u < UW; ++u) {
+        const int64_t n = n0 + u < N ? n0 + u : N - 1;
+        v[u] = ldg4(wh + (n * H + h) * Cp + 4 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < UW; ++u) {
+        d1[u] += v[u].x * p.x + v[u].y * p.y + v[u].z * p.z + v[u].w * p.w;
+        d2[u] += v[u].x * r.x + v[u].y * r.y + v[u].z * r.z + v[u].w * r.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UW; ++u) {
+      const float s1 = group_sum<G>(d1[u]), s2 = group_sum<G>(d2[u]);
+      if (gl == 0 && n0 + u < N) {
+        s_src[(n0 + u) * H + h] = s1 + bb1;
+        s_dst[(n0 + u) * H + h] = s2 + bb2;
+      }
+    }
+  }
+}
+
 // fp32 rows -> bf16 copy (the CUDA-core projection path of the bf16 gather mode; the tensor-core path writes it in its epilogue)
 __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += int64_t(gridDim.x) * blockDim.x) {
@@ -77,13 +164,22 @@ int launch_logits(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
     const int64_t want = ceil_div(ceil_div(items, (32 / g) * 4), threads / 32);
     return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   };
+  auto grid_head = [&](int g) {
+    // one lane group per (head, 8-node strip): at least H groups, at most `cap` CTAs
+    const int64_t groups = ceil_div(N, 8) * H, gpc = threads / g;
+    const int64_t want = ceil_div(groups, gpc), least = ceil_div(int64_t(H), gpc);
+    const int64_t n = want < cap ? want : cap;
+    return static_cast<int>(n > least ? n : least);
+  };
 #define B200GAT_LOGITS(G) logits_kernel<G><<<grid(G), threads, 0, stream>>>(a.wh, a.a1, a.a2, a.b1, a.b2, a.s_src, a.s_dst, items, H, Cp)
+#define B200GAT_LOGITS_HEAD(G) logits_head_kernel<G><<<grid_head(G), threads, 0, stream>>>(a.wh, a.a1, a.a2, a.b1, a.b2, a.s_src, a.s_dst, N, H, Cp)
   if (Q <= 1) B200GAT_LOGITS(1);
   else if (Q <= 2) B200GAT_LOGITS(2);
   else if (Q <= 4) B200GAT_LOGITS(4);
   else if (Q <= 8) B200GAT_LOGITS(8);
-  else if (Q <= 16) B200GAT_LOGITS(16);
-  else B200GAT_LOGITS(32);
+  else if (Q <= 16) B200GAT_LOGITS_HEAD(16);
+  else B200GAT_LOGITS_HEAD(32);
+#undef B200GAT_LOGITS_HEAD
 #undef B200GAT_LOGITS
   return check_launch("logits_kernel");
 }
