@@ -313,10 +313,11 @@ __global__ void __launch_bounds__(256) bwd_prep_mean_narrow_kernel(const PrepMea
       else *reinterpret_cast<float4*>(p.gp + i * int64_t(p.Cp) + c) = gv;
     }
     const float* o = p.o_heads + (i < p.N ? i : 0) * int64_t(p.H) * p.Cp + c;
-    for (int h0 = 0; h0 < p.H; h0 += 4) {                  // four heads' loads in flight together
-      float d[4];
+    constexpr int HB = G >= 8 ? 8 : 4;                     // heads whose loads are in flight together
+    for (int h0 = 0; h0 < p.H; h0 += HB) {
+      float d[HB];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < HB; ++u) {
         d[u] = 0.f;
         if (valid && h0 + u < p.H) {
           const float4 ov = ldg4(o + (h0 + u) * p.Cp);
@@ -326,10 +327,13 @@ __global__ void __launch_bounds__(256) bwd_prep_mean_narrow_kernel(const PrepMea
 #pragma unroll
       for (int o2 = G >> 1; o2 > 0; o2 >>= 1) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o2, G);
+        for (int u = 0; u < HB; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o2, G);
       }
-      if (gl < 4 && h0 + gl < p.H && i < p.N) {            // lane u of the group writes head h0 + u's record
-        const float dv = gl == 0 ? d[0] : (gl == 1 ? d[1] : (gl == 2 ? d[2] : d[3]));
+      if (gl < HB && h0 + gl < p.H && i < p.N) {           // lane u of the group writes head h0 + u's record
+        float dv = d[0];
+#pragma unroll
+        for (int u = 1; u < HB; ++u)
+          if (gl == u) dv = d[u];
         const int64_t item = i * p.H + h0 + gl;
         p.rowrec[item] = make_float4(__ldg(p.s_dst + item), __ldg(p.rowmax + item), 1.f / (__ldg(p.rowsum + item) + 1e-16f), dv);
       }

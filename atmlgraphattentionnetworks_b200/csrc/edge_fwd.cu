@@ -275,17 +275,22 @@ head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bi
                  int64_t ldo, int64_t N, int H, int C, int Cp, uint32_t* __restrict__ out_amax) {
   const int Q = Cp >> 2;
   const int64_t total = N * Q;
-  const float inv_h = 1.f / static_cast<float>(H);
   float amax = 0.f;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t i = t / Q;
-    const int c = 4 * static_cast<int>(t - i * Q);
+  // (node, slot) of item t are stepped incrementally (no 64-bit division per item); up to 8 heads' loads in flight together
+  const int64_t nth = int64_t(gridDim.x) * blockDim.x, t0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t di = nth / Q, dq = nth - di * Q;
+  int64_t i = t0 / Q, q = t0 - i * Q;
+  for (int64_t t = t0; t < total; t += nth, i += di, q += dq) {
+    if (q >= Q) { q -= Q; ++i; }
+    const int c = 4 * static_cast<int>(q);
     const float* src = o_heads + i * int64_t(H) * Cp + c;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int h = 0; h < H; ++h) {
-      const float4 v = ldg4(src + h * Cp);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int h0 = 0; h0 < H; h0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = h0 + u < H ? ldg4(src + (h0 + u) * Cp) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
     const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
@@ -296,7 +301,6 @@ head_mean_kernel(const float* __restrict__ o_heads, const float* __restrict__ bi
         amax = fmaxf(amax, fabsf(r));
       }
   }
-  (void)inv_h;
   if (out_amax) warp_atomic_amax(out_amax, amax);
 }
 
