@@ -909,7 +909,8 @@ bool proj_tc_can_fuse_prep(const b200gat_layer& consumer, int64_t N, const b200g
 }
 
 size_t proj_tc_split_bytes(const b200gat_layer& L, int64_t N) {
-  return proj_tc_fwd_supported(L, N) ? blob_bytes(N, L.in_channels) : 0;
+  // [x blob][W blob]: the backward's gX GEMM reads the same W planes as the forward (MN-major), so they are kept too
+  return proj_tc_fwd_supported(L, N) ? blob_bytes(N, L.in_channels) + blob_bytes(L.heads * L.c_pad, L.in_channels) : 0;
 }
 
 size_t proj_tc_fwd_workspace_bytes(const b200gat_layer& L, int64_t N) {
@@ -928,16 +929,17 @@ int proj_tc_fwd(const b200gat_proj_fwd_args& a, cudaStream_t stream) {
   const int64_t N = a.num_nodes, F = L.in_channels, H = L.heads, Cp = L.c_pad, Dp = H * Cp;
   const size_t xb = blob_bytes(N, F), wb = blob_bytes(Dp, F);
   int rc;
-  // the split of x is written into the caller's x_split buffer when given (kept for b200gat_proj_bwd), else into workspace
+  // the splits of x and W are written into the caller's x_split buffer when given (kept for b200gat_proj_bwd), else into
+  // the workspace
   const bool keep = a.x_split != nullptr;
   if (keep) {
-    B200GAT_REQUIRE(a.x_split_bytes >= xb, B200GAT_E_WORKSPACE, "proj_fwd: x_split %zu < %zu bytes", a.x_split_bytes, xb);
+    B200GAT_REQUIRE(a.x_split_bytes >= xb + wb, B200GAT_E_WORKSPACE, "proj_fwd: x_split %zu < %zu bytes", a.x_split_bytes, xb + wb);
     B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.x_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_fwd: x_split must be 256-byte aligned");
   }
-  if ((rc = check_ws(a.workspace, a.workspace_bytes, (keep ? 0 : xb) + wb, "proj_fwd"))) return rc;
-  char* base = static_cast<char*>(a.workspace);
-  const Blob X = make_blob(keep ? a.x_split : static_cast<void*>(base), N, F);
-  const Blob W = make_blob(base + (keep ? 0 : xb), Dp, F);
+  if (!keep && (rc = check_ws(a.workspace, a.workspace_bytes, xb + wb, "proj_fwd"))) return rc;
+  char* base = static_cast<char*>(keep ? a.x_split : a.workspace);
+  const Blob X = make_blob(base, N, F);
+  const Blob W = make_blob(base + xb, Dp, F);
   if ((rc = launch_split(a.x, a.ldx, X, stream, a.x_activation, a.x_amax))) return rc;
   if ((rc = launch_split(a.w, F, W, stream))) return rc;
   TcGemmParams p{};
@@ -972,7 +974,7 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   const size_t gb = blob_bytes(N, Dp), wb = blob_bytes(Dp, F), xb = blob_bytes(N, F);
   const bool have_x = a.x_split != nullptr;
   if (have_x) {
-    B200GAT_REQUIRE(a.x_split_bytes >= xb, B200GAT_E_WORKSPACE, "proj_bwd: x_split %zu < %zu bytes", a.x_split_bytes, xb);
+    B200GAT_REQUIRE(a.x_split_bytes >= xb + wb, B200GAT_E_WORKSPACE, "proj_bwd: x_split %zu < %zu bytes", a.x_split_bytes, xb + wb);
     B200GAT_REQUIRE((reinterpret_cast<uintptr_t>(a.x_split) & 255u) == 0, B200GAT_E_ALIGN, "proj_bwd: x_split must be 256-byte aligned");
   }
   const bool have_g = a.g_t_split != nullptr;
@@ -985,7 +987,8 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   // workspace layout: [W blob][gT blob unless g_t_split][x blob unless x_split]
   if ((rc = check_ws(a.workspace, a.workspace_bytes, wb + (have_g ? 0 : gb) + (have_x ? 0 : xb), "proj_bwd"))) return rc;
   char* base = static_cast<char*>(a.workspace);
-  const Blob W = make_blob(base, Dp, F);
+  // (W planes: the forward's, behind the x blob in x_split — same W, same layout, read MN-major here — else split again)
+  const Blob W = make_blob(have_x ? static_cast<char*>(const_cast<void*>(a.x_split)) + xb : base, Dp, F);
   const Blob G = make_blob(have_g ? const_cast<void*>(a.g_t_split) : static_cast<void*>(base + wb), N, Dp);
   const Blob X = make_blob(have_x ? const_cast<void*>(a.x_split) : static_cast<void*>(base + wb + (have_g ? 0 : gb)), N, F);
   if (!have_g && (rc = launch_split(a.g_t, Dp, G, stream))) return rc;
@@ -993,7 +996,7 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   const bool want_gx = a.g_x && a.parts != B200GAT_PROJ_BWD_GW, want_gw = a.parts != B200GAT_PROJ_BWD_GX;
   if (want_gx) {
     // gX[N,F] = gT[N,Dp] · W[Dp,F] : K = Dp; B = the W planes read MN-major (F contiguous)
-    if ((rc = launch_split(a.w, F, W, stream))) return rc;
+    if (!have_x && (rc = launch_split(a.w, F, W, stream))) return rc;
     TcGemmParams p{};
     p.C = a.g_x; p.ldc = a.ldgx;
     if (a.fuse_prep) {

@@ -146,9 +146,10 @@ typedef struct {
   float* wh;                      /* out [N, Dp] */
   float* s_src; float* s_dst;     /* out [N, H]  (a1·Wh + b1 gathered at the source, a2·Wh + b2 at the target) */
   void* workspace; size_t workspace_bytes;
-  void* x_split; size_t x_split_bytes;   /* optional out: the tensor-core operand split of x (two fp16 planes + scale),
-                                            kept by the caller for b200gat_proj_bwd; b200gat_proj_split_bytes() bytes,
-                                            256-byte aligned.  NULL: the split lives in workspace and is redone in backward */
+  void* x_split; size_t x_split_bytes;   /* optional out: the tensor-core operand splits of x AND of w (two fp16 planes +
+                                            scale each), kept by the caller for b200gat_proj_bwd (w must not change in
+                                            between); b200gat_proj_split_bytes() bytes, 256-byte aligned.  NULL: the splits
+                                            live in workspace and are redone in the backward */
   int32_t x_activation;                  /* B200GAT_ACT_*: the projection consumes act(x) */
   const uint32_t* x_amax;                /* optional: device word holding the bit pattern of an upper bound of max|x|
                                             (b200gat_edge_fwd's out_amax of the producing layer); saves one pass over x */
@@ -292,7 +293,7 @@ typedef struct {
   float* g_x; int64_t ldgx;           /* out [N, F_in] or NULL (input does not require grad) */
   float* g_w;                         /* out [Dp, F_in] */
   void* workspace; size_t workspace_bytes;
-  const void* x_split; size_t x_split_bytes;   /* optional in: the split of x written by b200gat_proj_fwd */
+  const void* x_split; size_t x_split_bytes;   /* optional in: the splits of x and w written by b200gat_proj_fwd */
   int32_t x_activation;               /* as in the forward (used when x_split is absent) */
   const void* g_t_split; size_t g_t_split_bytes;   /* optional in: gT as written by b200gat_edge_bwd (g_t may be NULL) */
   int32_t parts;                      /* 0 = both products; B200GAT_PROJ_BWD_GX / _GW = only that one.  The two GEMMs are
