@@ -8,7 +8,7 @@ import csv, io, json, os, subprocess, sys
 # checked in this order ("gt_amax_kernel" must win over "amax_kernel")
 CLASSES = {"EB": ("bwd_prep", "colsum_kernel", "edge_bwd_", "gt_amax_kernel", "bwd_finish_kernel"),
            "EF": ("edge_fwd_", "head_mean_kernel"),
-           "P": ("amax_kernel", "split_kernel", "gemm_tc_kernel", "gemm_simt_kernel", "logits_kernel")}
+           "P": ("amax_kernel", "split_kernel", "gemm_tc_kernel", "gemm_simt_kernel", "logits_")}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
