@@ -19,7 +19,7 @@
 //
 // Tensor-core fp32 accumulation TRUNCATES (measured on B200: the error of one long TMEM accumulation chain grows
 // ~0.5 ulp per MMA), so a TMEM accumulator only ever holds a SHORT chain: two 128 x BN accumulators alternate every
-// TC_KC k-blocks (8 k-steps x 3 MMAs) and the epilogue warps promote each finished chunk into fp32 REGISTER
+// TC_KC k-blocks (16 k-steps x 3 MMAs) and the epilogue warps promote each finished chunk into fp32 REGISTER
 // accumulators with round-to-nearest adds while the tensor core fills the other buffer.
 //
 // Kernel anatomy (persistent: one CTA per SM walks a static list of (split, m-tile, n-tile) work items, n fastest):
@@ -41,7 +41,12 @@ namespace b200gat {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // fp16 elements per k-block row = 128 bytes = one SWIZZLE_128B atom row
-constexpr int TC_KC = 2;    // k-blocks per TMEM accumulation chunk (2 x 4 k-steps x 3 MMAs = 24 MMAs per chain)
+// k-blocks per TMEM accumulation chunk (4 x 4 k-steps x 3 MMAs = 48 MMAs per chain).  Measured (tools/gemm_error.py, normalised
+// max error of out / gX / gW against f64, independent of K beyond one chunk): 2 -> 6..8e-7, 4 -> 1.0..1.3e-6, 8 -> 2.0..2.7e-6,
+// 16 -> 3.5..5.2e-6 — the truncation bias grows linearly with the chain.  4 keeps the GEMMs at the error of a plain fp32
+// GEMM (8x inside the 1e-5 bar) and halves the chunk hand-offs (MMA -> epilogue drain -> MMA), which at 2 left the tensor
+// pipe idle 39 % of the time: PPI-shaped step 4.94 -> 4.75 ms.  B200GAT_TC_KC=<n> overrides (2 = the tighter setting).
+constexpr int TC_KC = 4;
 constexpr int TC_MN_CHUNK_BYTES = 64 * TC_BK * 2;   // one MN-major TMA box: 64 k-rows x 64 fp16 (128 B) = 8 KB
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -195,6 +200,7 @@ struct TcGemmParams {
   float4* pr_rowrec;                          // out [M, pr_H] {s_dst, rowmax, 1/(rowsum + 1e-16), Drow}
   float* pr_g_bias;                           // out [N], zero-initialised by the host, accumulated atomically
   int pr_H, pr_C, pr_act;                     // layer k's heads / channels per head (N = pr_H * pr_C), 1: multiply by ELU'(out)
+  int kc;                                     // k-blocks per TMEM accumulation chunk
 };
 
 enum { EPI_STORE = 0, EPI_LOGITS = 1, EPI_ATOMIC = 2, EPI_PREP = 3 };
@@ -354,8 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           const int b = chunk & 1;
-          const bool chunk_first = (i % TC_KC) == 0;
-          const bool chunk_last = (i % TC_KC) == TC_KC - 1 || i == nkb - 1;
+          const bool chunk_first = (i % p.kc) == 0;
+          const bool chunk_last = (i % p.kc) == p.kc - 1 || i == nkb - 1;
           if (chunk_first) {
             mbar_wait(&tempty_bar[b], ((chunk >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
             tc_fence_after();
@@ -400,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     for (int w = unit; w < total_items; w += nunits) {
       int m0, n0, kb0, nkb;
       item_coords(w, m0, n0, kb0, nkb);
-      const int nchunks = (nkb + TC_KC - 1) / TC_KC;
+      const int nchunks = (nkb + p.kc - 1) / p.kc;
       const int64_t row = int64_t(m0) + q * 32 + lane;
       const bool row_ok = row < p.M;
       if (EPI != EPI_ATOMIC) {
@@ -863,6 +869,7 @@ static int gemm_blobs(const Blob& A, const Blob& B, int64_t M, int64_t N, int64_
   if (splits < 1) splits = 1;
   p.k_blocks_per_split = static_cast<int>(ceil_div(p.k_blocks, splits));
   p.splits = static_cast<int>(ceil_div(p.k_blocks, p.k_blocks_per_split));
+  { static int kc = 0; if (!kc) { const char* e = getenv("B200GAT_TC_KC"); kc = e ? atoi(e) : TC_KC; if (kc < 1) kc = TC_KC; } p.kc = kc; }
   p.inv_a = A.inv_scale();
   p.inv_b = B.inv_scale();
   const int bn = N > 128 ? 256 : 128;
