@@ -784,6 +784,32 @@ static int launch_split(const float* src, int64_t ld, const Blob& b, cudaStream_
   return check_launch("split_kernel");
 }
 
+// co-resident CTA pairs of the cta_group::2 kernel (cached per instantiation; its shared-memory attribute must be set first)
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int max_active_pairs() {
+  using S = TcCfg<BN, 2>;
+  static int max_pairs = 0;
+  static std::once_flag once2;
+  std::call_once(once2, [&] {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, 2>;
+    (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(2 * sm_count());
+    q.blockDim = dim3(S::THREADS);
+    q.dynamicSmemBytes = S::TOTAL;
+    cudaLaunchAttribute qa;
+    qa.id = cudaLaunchAttributeClusterDimension;
+    qa.val.clusterDim.x = 2; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+    q.attrs = &qa;
+    q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) n = sm_count() / 2 - 4;
+    max_pairs = n;
+    (void)cudaGetLastError();
+  });
+  return max_pairs;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      TcGemmParams p, cudaStream_t stream) {
@@ -804,23 +830,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     kern<<<grid, S::THREADS, S::TOTAL, stream>>>(ah, al, bh, bl, p);
   } else {
     // persistent pairs: as many clusters as can be co-resident (GPCs with an odd SM count leave an SM without a partner)
-    static int max_pairs = 0;
-    static std::once_flag once2;
-    std::call_once(once2, [&] {
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(2 * sm_count());
-      q.blockDim = dim3(S::THREADS);
-      q.dynamicSmemBytes = S::TOTAL;
-      cudaLaunchAttribute qa;
-      qa.id = cudaLaunchAttributeClusterDimension;
-      qa.val.clusterDim.x = 2; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
-      q.attrs = &qa;
-      q.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) n = sm_count() / 2 - 4;
-      max_pairs = n;
-      (void)cudaGetLastError();
-    });
+    const int max_pairs = max_active_pairs<BN, A_MN, B_MN, EPI>();
     const int64_t units = max_pairs;
     const int grid = static_cast<int>((items < units ? items : units) * CG);
     cudaLaunchConfig_t cfg = {};
@@ -1034,9 +1044,23 @@ int proj_tc_bwd(const b200gat_proj_bwd_args& a, cudaStream_t stream) {
   const int bn = F > 128 ? 256 : 128;
   const int64_t tiles = ceil_div(Dp, TC_BM) * ceil_div(F, bn);
   const int64_t kblocks = ceil_div(N, TC_BK);
-  int64_t splits = ceil_div(int64_t(sm_count()) * 2, tiles);       // ~2 work items per SM
-  if (splits > kblocks / (2 * TC_KC)) splits = kblocks / (2 * TC_KC);
-  if (splits < 1) splits = 1;
+  // split-K factor: the persistent units (CTAs, or CTA pairs) walk tiles x splits items in waves; pick the number of waves
+  // w (splits = floor(units * w / tiles): the last wave is full) that minimises  w * (k-blocks per item + epilogue), the
+  // red.global.add epilogue of an item costed at ~4 k-blocks.  (It was "~2 items per SM": 19 splits x 16 tiles = 304 items
+  // on 74 pairs = 4.1 -> 5 waves on the PPI-shaped layers, the last one nearly empty.)
+  const bool pair = use_pair(Dp, bn, N, true);
+  const int64_t units = pair ? (bn == 256 ? max_active_pairs<256, true, true, EPI_ATOMIC>() : 1) : sm_count();
+  const int64_t work_tiles = pair ? ceil_div(Dp, 2 * TC_BM) * ceil_div(F, bn) : tiles;
+  const int64_t max_splits = kblocks / (2 * TC_KC) > 1 ? kblocks / (2 * TC_KC) : 1;
+  int64_t splits = 1, best = -1;
+  for (int64_t w = 1; w <= 8; ++w) {
+    int64_t sp = units * w / work_tiles;
+    if (sp < 1) continue;
+    if (sp > max_splits) sp = max_splits;
+    const int64_t waves = ceil_div(work_tiles * sp, units);
+    const int64_t cost = waves * (ceil_div(kblocks, sp) + 4);
+    if (best < 0 || cost < best) { best = cost; splits = sp; }
+  }
   TcGemmParams p{};
   p.C = a.g_w; p.ldc = F;
   return gemm_blobs<true, true, EPI_ATOMIC>(G, X, Dp, F, N, p, static_cast<int>(splits), stream);
