@@ -494,11 +494,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             }
           } else {
             // Cp == 256 == BN: one head per tile, its two halves live in two warps -> combine through shared memory
+            float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};   // four chains each instead of one of 128 FMAs
 #pragma unroll
-            for (int j = 0; j < 128; ++j) {
-              d1 = fmaf(acc[j], vec[BN + cbase + j], d1);
-              d2 = fmaf(acc[j], vec[2 * BN + cbase + j], d2);
+            for (int j = 0; j < 128; j += 4) {
+              const float4 v1 = *reinterpret_cast<const float4*>(vec + BN + cbase + j);
+              const float4 v2 = *reinterpret_cast<const float4*>(vec + 2 * BN + cbase + j);
+              e1[0] = fmaf(acc[j], v1.x, e1[0]); e1[1] = fmaf(acc[j + 1], v1.y, e1[1]);
+              e1[2] = fmaf(acc[j + 2], v1.z, e1[2]); e1[3] = fmaf(acc[j + 3], v1.w, e1[3]);
+              e2[0] = fmaf(acc[j], v2.x, e2[0]); e2[1] = fmaf(acc[j + 1], v2.y, e2[1]);
+              e2[2] = fmaf(acc[j + 2], v2.z, e2[2]); e2[3] = fmaf(acc[j + 3], v2.w, e2[3]);
             }
+            d1 = (e1[0] + e1[1]) + (e1[2] + e1[3]);
+            d2 = (e2[0] + e2[1]) + (e2[2] + e2[3]);
             const int r = q * 32 + lane;
             if (half == 1) {
               red[r] = d1;
@@ -593,6 +600,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           // shared buffer 16 columns at a time and leaves as 64-byte runs: 8 lines per instruction, whole sectors.
           float* stg = stgbuf + ew * (32 * S::STG_ROW);
           const int64_t wrow0 = int64_t(m0) + q * 32;
+          // the common case — whole 128 columns inside C, no bf16 copy, no peers: the lane's four row pointers (rows
+          // lane / 4 + 8 i, its 16-byte piece of a 64-byte run) and row predicates are computed ONCE per tile and every store
+          // is pointer + immediate.  (The general loop below recomputed a 64-bit address and three predicates per store: ncu
+          // showed the tile-end phase spread over IMAD.X / spill reloads, 11 us per 128 x 256 tile.)
+          if (EPI != EPI_PREP && col0 + 128 <= p.N && p.c16 == nullptr && p.n_peer == 0) {
+            const int r0 = lane >> 2, c4 = (lane & 3) << 2;
+            float* d0 = p.C + (wrow0 + r0) * p.ldc + col0 + c4;
+            const int64_t step = 8 * p.ldc;
+            const float* sl = stg + r0 * S::STG_ROW + c4;
+            const int64_t left = p.M - wrow0 - r0;               // rows r0 + 8 i exist while 8 i < left
+#pragma unroll
+            for (int cc = 0; cc < 128; cc += 16) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(stg + lane * S::STG_ROW + j) =
+                    make_float4(acc[cc + j], acc[cc + j + 1], acc[cc + j + 2], acc[cc + j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(sl + 8 * i * S::STG_ROW);
+                if (8 * i < left) *reinterpret_cast<float4*>(d0 + i * step + cc) = v;
+              }
+              __syncwarp();
+            }
+            continue;
+          }
 #pragma unroll
           for (int cc = 0; cc < 128; cc += 16) {
 #pragma unroll
@@ -825,7 +858,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   p.m_tiles = static_cast<int>(ceil_div(p.M, TC_BM * CG));
   p.n_tiles = static_cast<int>(ceil_div(p.N, BN));
   const int64_t items = int64_t(p.m_tiles) * p.n_tiles * p.splits;
-  if (CG == 1) {
+  if constexpr (CG == 1) {
     const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
     kern<<<grid, S::THREADS, S::TOTAL, stream>>>(ah, al, bh, bl, p);
   } else {
