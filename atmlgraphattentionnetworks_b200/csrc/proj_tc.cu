@@ -475,7 +475,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 128; ++j) acc[j] = fmaf(acc[j], inv, vec[cbase + j]);
+        for (int j = 0; j < 128; j += 4) {                // (128-bit broadcast reads of the staged bias slice)
+          const float4 bv = *reinterpret_cast<const float4*>(vec + cbase + j);
+          acc[j] = fmaf(acc[j], inv, bv.x); acc[j + 1] = fmaf(acc[j + 1], inv, bv.y);
+          acc[j + 2] = fmaf(acc[j + 2], inv, bv.z); acc[j + 3] = fmaf(acc[j + 3], inv, bv.w);
+        }
         if (EPI == EPI_LOGITS) {
           float d1 = 0.f, d2 = 0.f;
           if (p.Cp <= 128) {
