@@ -11,7 +11,7 @@ for WL in ppi large cifar cora; do
       python bench.py --profile --steps 1 --warmup 3 --workload $WL > gpurun_out/${TAG}_ncu_$WL.log 2>&1
   echo "$WL launches rc=$?"; python tools/launch_summary.py gpurun_out/${TAG}_launches_$WL.csv 12 | head -14
 done
-ncu --set full --clock-control none -k regex:"$RE" -s ${NCU_SKIP:-105} -c ${NCU_COUNT:-35} -f -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none -k regex:"$RE" -s ${NCU_SKIP:-108} -c ${NCU_COUNT:-35} -f -o gpurun_out/${TAG}_prof \
     python bench.py --profile --steps 1 --warmup 3 --workload ppi > gpurun_out/${TAG}_ncufull.log 2>&1
 echo "ncu full rc=$?"; tail -2 gpurun_out/${TAG}_ncufull.log
 python tools/ncu_summary.py gpurun_out/${TAG}_prof.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.md
