@@ -166,3 +166,27 @@ def test_product_package_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
     for f in ("GAT.py", "GATNet.py"):
         assert "oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_shipped_library_is_sm_100a_tcgen05_code(built_lib):
+    """The hot GEMMs are hand-written Blackwell code: the shipped .so holds sm_100a SASS with tcgen05.mma (UTCHMMA, incl. the
+    cta_group::2 form), TMA tensor loads (UTMALDG), tcgen05.ld (LDTM), tcgen05.commit (UTCBAR) and red.global.add (REDG) —
+    the mnemonics B200_PROFILING.md names (the per-kernel table: tools/sass_summary.py -> profiles/r3_sass_summary.md)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    # every cubin that holds a kernel is sm_100a (nvcc's link step adds one EMPTY default-arch cubin: no functions in it)
+    arch, kernels_per_arch = None, {}
+    for line in sass.splitlines():
+        m = re.search(r"arch = (sm_\w+)", line)
+        if m:
+            arch = m.group(1)
+        elif "Function :" in line:
+            kernels_per_arch[arch] = kernels_per_arch.get(arch, 0) + 1
+    assert set(kernels_per_arch) == {"sm_100a"}, kernels_per_arch
+    assert kernels_per_arch["sm_100a"] > 100
+    for mnemonic, least in (("UTCHMMA", 100), ("UTCHMMA.2CTA", 10), ("UTMALDG.2D", 100), ("LDTM", 50), ("UTCBAR", 10),
+                            ("REDG.E.ADD.F32", 90)):
+        assert sass.count(mnemonic) >= least, f"{mnemonic}: {sass.count(mnemonic)} < {least}"
